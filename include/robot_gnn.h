@@ -1,0 +1,163 @@
+/*
+ * robot_gnn.h - C ABI of librobotgnn.so: B200 (sm_100a) kernels for the robot-graph
+ * message-passing hot path of xjh19971/multi-robot-perception-gnn-1.
+ *
+ * Conventions:
+ *   - every pointer is a CALLER-OWNED DEVICE pointer (torch tensors' data_ptr()); the
+ *     library never allocates or frees user-visible memory - scratch is passed in;
+ *   - every call takes sizes and a `stream` (cudaStream_t cast to void*), enqueues
+ *     work on it and returns without a host sync;
+ *   - return value: 0 = ok, <0 = invalid argument (RGNN_E_*), >0 = cudaError_t;
+ *     rgnn_last_error() gives a thread-local message for the last non-zero return;
+ *   - dtype codes: RGNN_F32 = 0 (parity mode), RGNN_BF16 = 1 (throughput mode; fp32
+ *     accumulation everywhere); integer graph arrays are int64 where DGL exposes them
+ *     (bit-exact contract) and int32 in the compact copies the compute kernels walk;
+ *   - feature maps are NCHW flattened to [N, F, P] (P = h*w, contiguous), exactly the
+ *     memory the reference hands to the layer (dgl/model/models.py:179-180);
+ *   - no CPU fallback exists: with no CUDA device every compute entry returns an error.
+ *
+ * Each entry cites the reference interface (file:line under /root/reference) it replaces.
+ */
+#ifndef ROBOT_GNN_H_
+#define ROBOT_GNN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGNN_VERSION 100
+
+#define RGNN_F32 0
+#define RGNN_BF16 1
+
+#define RGNN_E_ARG (-1)       /* null pointer / negative size / bad enum */
+#define RGNN_E_ALIGN (-2)     /* pointer or row size not aligned as the kernel requires */
+#define RGNN_E_RANGE (-3)     /* size exceeds what the kernel supports (e.g. >= 2^31 edges) */
+#define RGNN_E_UNSUPPORTED (-4)
+
+/* reduce modes of rgnn_aggregate_* */
+#define RGNN_POST_NONE 0      /* plain sum                                   (fn.sum)            */
+#define RGNN_POST_MEAN 1      /* sum / in-degree, 0 for isolated nodes       (mailbox.mean(1))   */
+#define RGNN_POST_SCALE 2     /* sum * dst_scale[v]                          (GraphConv norm)    */
+
+/* epilogue flags of rgnn_gemm (bit-or):  v = alpha*acc [+ beta*aux[m,n]] [+ bias_m[m]] [+ bias_n[n]];
+ * then optionally sigmoid(v), or v * (aux[m,n] > 0) */
+#define RGNN_EPI_BIAS_M 1     /* + bias[m]            (1x1 conv bias, models.py:164)              */
+#define RGNN_EPI_BIAS_N 2     /* + bias[n]            (nn.Linear bias, models.py:149)             */
+#define RGNN_EPI_SIGMOID 4    /* sigmoid(v)           (edge encoder, models.py:150)               */
+#define RGNN_EPI_RELU_MASK 8  /* v * (aux[m,n] > 0)   (ReLU backward, models.py:148)              */
+#define RGNN_EPI_ADD_AUX 16   /* + beta*aux[m,n]      (accumulate / GCN2Conv identity mapping)    */
+
+/* ---- library queries ------------------------------------------------------------------- */
+int rgnn_version(void);                 /* RGNN_VERSION */
+int rgnn_arch(void);                    /* 100: compiled for sm_100a only */
+const char* rgnn_last_error(void);      /* thread-local, never NULL */
+int rgnn_device_ok(void);               /* 0 if the current device is sm_100; else error code */
+
+/* ---- A2: dgl.batch index work  (dgl/training.py:57-58, dgl/eval.py:54-55) ---------------
+ * local_src/local_dst [E]: per-graph LOCAL node ids concatenated in graph order.
+ * batch_num_nodes/batch_num_edges [G].  Outputs: node_offsets/edge_offsets [G+1]
+ * (exclusive scans), src/dst [E] = local id + node offset of the owning graph. */
+int rgnn_batch_graphs(const int64_t* local_src, const int64_t* local_dst,
+                      const int64_t* batch_num_nodes, const int64_t* batch_num_edges,
+                      int64_t num_graphs, int64_t num_edges,
+                      int64_t* node_offsets, int64_t* edge_offsets,
+                      int64_t* src, int64_t* dst, void* stream);
+
+/* ---- A3: in-degree / in-edge lookup / GraphConv norm -----------------------------------
+ * Replaces what DGL does inside update_all (call site dgl/model/models.py:223): in_degrees,
+ * in_edges(form='eid') sorted ascending, and GraphConv's degree norms.
+ * src/dst [E] global ids.  node_offsets/edge_offsets [G+1] describe the batch (every edge of
+ * graph g joins two nodes of graph g); pass G = 1 with offsets {0,N},{0,E} for an unbatched graph.
+ * Outputs (int64, DGL-visible, bit-exact): in_deg/out_deg [N]; in_ptr/out_ptr [N+1];
+ * in_src/in_eid, out_dst/out_eid [E] (stable: ascending edge id inside a node).
+ * Outputs (int32 compact copies walked by the kernels), packed back to back:
+ *   ptr32 [2(N+1) + G+1] = {in_ptr32 [N+1], out_ptr32 [N+1], node_offsets32 [G+1]},
+ *   idx32 [6E] = {in_src32, in_eid32, out_dst32, out_eid32, src32, dst32} each [E].
+ * norm [3N] fp32 = {1/in_deg (0 if isolated), clamp(in_deg,1)^-1/2, clamp(out_deg,1)^-1/2}.
+ * status [1] int32: set non-zero on device if an edge leaves its graph's node range.
+ * Any int64 output may be NULL (skipped). */
+int rgnn_build_batched_csr(const int64_t* src, const int64_t* dst, int64_t num_nodes, int64_t num_edges,
+                           const int64_t* node_offsets, const int64_t* edge_offsets, int64_t num_graphs,
+                           int64_t* in_deg, int64_t* out_deg,
+                           int64_t* in_ptr, int64_t* in_src, int64_t* in_eid,
+                           int64_t* out_ptr, int64_t* out_dst, int64_t* out_eid,
+                           int32_t* ptr32, int32_t* idx32, float* norm, int32_t* status, void* stream);
+
+/* ---- A5/A6 (+A10, A11): fused gather -> FiLM / normalise -> sum|mean ----------------------
+ * out[v,c,p] = post_v( sum_{i in [ptr[v],ptr[v+1])} ( gamma(eid_i,c) * nbr_scale[nbr_i] * x[nbr_i,c,p]
+ *                                                    + beta(eid_i,c) ) ) + addend[v,c,p]
+ * Replaces edge_udf + node_udf + degree bucketing (dgl/model/models.py:207-211,223) - the
+ * [E,F,P] messages are never materialised - and update_all(copy_u, sum|mean)
+ * (dgl/model/dgl_models.py:126; GraphConv/GCN2Conv).  Summation order is ascending edge id and
+ * gamma*x, +beta are two roundings, so RGNN_F32 + RGNN_POST_MEAN reproduces the reference bit for bit.
+ *   x [N, F, P] with node stride ldx elements;  z [E, 2F] interleaved (gamma,beta) or NULL (gamma=1,beta=0);
+ *   use_beta = 0 ignores beta (the transposed pass of the backward);  nbr_scale [N] fp32 or NULL;
+ *   dst_scale [N] fp32 (RGNN_POST_SCALE);  addend [N,F,P] node stride ldadd, or NULL;
+ *   out node stride ldout (lets the result land in the 2nd half of a concat buffer);
+ *   copy_x_to: if non-NULL also writes x[v] to copy_x_to[v] (node stride ldout) = torch.cat((h,g_h),1)
+ *   (dgl/model/models.py:182) for free.
+ *   ptr32 [N+1], nbr32 [E], eid32 [E]: the in-CSR (forward) or out-CSR (backward).
+ *   node_offsets32 [G+1] or NULL: batch layout enabling the shared-memory staged path; max_graph_nodes /
+ *   max_graph_edges: host-known maxima over the batch (0 = unknown -> generic path). */
+int rgnn_aggregate(int dtype, const void* x, int64_t ldx, const void* z, int use_beta,
+                   const float* nbr_scale, int post, const float* dst_scale,
+                   const void* addend, int64_t ldadd,
+                   void* out, int64_t ldout, void* copy_x_to,
+                   const int32_t* ptr32, const int32_t* nbr32, const int32_t* eid32,
+                   const int32_t* node_offsets32, int64_t num_graphs,
+                   int64_t max_graph_nodes, int64_t max_graph_edges,
+                   int64_t num_nodes, int64_t num_edges, int64_t feat, int64_t pix, void* stream);
+
+/* ---- A10: per-edge FiLM gradients with the sigmoid derivative fused ----------------------
+ * dz[e,2c]   = z[e,2c]  (1-z[e,2c])   * w_e * sum_p x[src_e,c,p] * dagg[dst_e,c,p]
+ * dz[e,2c+1] = z[e,2c+1](1-z[e,2c+1]) * w_e * sum_p dagg[dst_e,c,p],     w_e = inv_in_deg[dst_e]
+ * (autograd of models.py:211 and :150).  fuse_sigmoid_grad = 0 drops the z(1-z) factors (true d/dz).
+ * src32/dst32 [E] in edge-id order. */
+int rgnn_film_edge_grad(int dtype, const void* x, int64_t ldx, const void* dagg, int64_t lddagg,
+                        const void* z, int fuse_sigmoid_grad, const float* inv_in_deg,
+                        const int32_t* src32, const int32_t* dst32,
+                        void* dz, int64_t num_edges, int64_t feat, int64_t pix, void* stream);
+
+/* ---- A4 (+A10): first edge-encoder layer, K = 9 -----------------------------------------
+ * a1 = relu(pose W1^T + b1)   (nn.Linear(9,F)+ReLU, dgl/model/models.py:147-148); pose [E,9] fp32
+ * (edge.float(), models.py:153); w1 [F,9], b1 [F] fp32 master weights; a1 [E,F] in `dtype`. */
+int rgnn_edge_mlp1_fwd(int dtype, const float* pose, const float* w1, const float* b1,
+                       void* a1, int64_t num_edges, int64_t feat, void* stream);
+/* dw1 [F,9], db1 [F] fp32 (overwritten) from da1 [E,F] (`dtype`, ReLU mask already applied). */
+int rgnn_edge_mlp1_bwd(int dtype, const float* pose, const void* da1,
+                       float* dw1, float* db1, int64_t num_edges, int64_t feat, void* stream);
+
+/* ---- A4/A8 (+A10, A11): strided GEMM family on CUDA cores (fp32-exact products) -----------
+ * For z in [0,batch):  C_z[m,n] = epi( sum_{r<red} sum_{k<K} A_z,r[m,k] * B_z,r[k,n] )
+ * with element strides (sAz,sAr,sAm,sAk), (sBz,sBr,sBk,sBn), (sCz,sCm,sCn); aux shares C's strides.
+ * split > 1: the `red` loop (or, when red == 1, the K loop) is cut into `split` chunks, partial sums go to
+ * `partial` ([split, M, N] fp32, batch must be 1) and are combined in a fixed order (deterministic), then `epi`.
+ * a_dtype/b_dtype/c_dtype: RGNN_F32 | RGNN_BF16; bias fp32.
+ * Covers nn.Linear(F,2F)+Sigmoid (models.py:149-150), Conv2d(2F,F,1) (models.py:164,184) and the
+ * dX / dW products of their autograd, plus the GraphConv / GCN2Conv weight transforms. */
+int rgnn_gemm(int a_dtype, const void* A, int64_t sAz, int64_t sAr, int64_t sAm, int64_t sAk,
+              int b_dtype, const void* B, int64_t sBz, int64_t sBr, int64_t sBk, int64_t sBn,
+              int c_dtype, void* C, int64_t sCz, int64_t sCm, int64_t sCn,
+              int64_t M, int64_t N, int64_t K, int64_t batch, int64_t red, int64_t split, float* partial,
+              int epi, const float* bias, const void* aux, float alpha, float beta, void* stream);
+
+/* dzpre = dz * z * (1 - z)  elementwise over n values (sigmoid backward, models.py:150) */
+int rgnn_sigmoid_grad(int dtype, const void* z, const void* dz, void* dzpre, int64_t n, void* stream);
+
+/* out = a*x + b*y elementwise over n values (GCN2Conv initial residual (1-alpha)*agg + alpha*feat_0) */
+int rgnn_axpby(int dtype, float a, const void* x, float b, const void* y, void* out, int64_t n, void* stream);
+
+/* out[r,c] = x[r,c] + bias[c]  (GraphConv bias after a plain aggregation) */
+int rgnn_bias_add(int dtype, const void* x, const float* bias, void* out, int64_t rows, int64_t cols, void* stream);
+
+/* out[j] = sum_{i<outer} sum_{k<inner} x[i*s_outer + j*s_j + k*s_inner]   (bias gradients: fp32 out) */
+int rgnn_reduce_sum(int dtype, const void* x, int64_t outer, int64_t s_outer, int64_t len, int64_t s_j,
+                    int64_t inner, int64_t s_inner, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROBOT_GNN_H_ */

@@ -1,0 +1,15 @@
+"""B200-native graph message-passing layers for multi-robot perception
+(hot path of xjh19971/multi-robot-perception-gnn-1, dgl/model/models.py).
+
+Import name: the directory is called ``multi-robot-perception-gnn-1_b200`` (not a Python identifier);
+``import robot_gnn_b200`` (repo-root alias module) loads it.
+"""
+from . import _lib
+from .graph import RobotGraph, graph, batch, robot_batch, function
+from . import functional
+from .functional import film_mean, film_mean_cat, copy_u_reduce, edge_mlp, compress, linear, axpby
+from .layers import edge_encoder, GCN, GNNBlock, GraphConv, GCN2Conv
+
+__all__ = ["RobotGraph", "graph", "batch", "robot_batch", "function", "functional", "film_mean", "film_mean_cat",
+           "copy_u_reduce", "edge_mlp", "compress", "linear", "axpby", "edge_encoder", "GCN", "GNNBlock",
+           "GraphConv", "GCN2Conv"]

@@ -1,0 +1,84 @@
+"""ctypes binding of librobotgnn.so (include/robot_gnn.h).  No fallback: a missing library or a failing
+call raises - the product path never computes on the CPU or through another backend."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librobotgnn.so")
+
+F32, BF16 = 0, 1
+POST_NONE, POST_MEAN, POST_SCALE = 0, 1, 2
+EPI_BIAS_M, EPI_BIAS_N, EPI_SIGMOID, EPI_RELU_MASK, EPI_ADD_AUX = 1, 2, 4, 8, 16
+
+_i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+
+# name -> argtypes; must list every symbol declared in include/robot_gnn.h (tests/test_cabi.py checks)
+SIGNATURES = {
+    "rgnn_version": [],
+    "rgnn_arch": [],
+    "rgnn_device_ok": [],
+    "rgnn_batch_graphs": [_vp] * 4 + [_i64] * 2 + [_vp] * 5,
+    "rgnn_build_batched_csr": [_vp, _vp, _i64, _i64, _vp, _vp, _i64] + [_vp] * 13,
+    "rgnn_aggregate": [_i32, _vp, _i64, _vp, _i32, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp]
+                      + [_i64] * 7 + [_vp],
+    "rgnn_film_edge_grad": [_i32, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
+    "rgnn_edge_mlp1_fwd": [_i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "rgnn_edge_mlp1_bwd": [_i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "rgnn_gemm": [_i32, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i64, _i64, _i64]
+                 + [_i64] * 6 + [_vp, _i32, _vp, _vp, _f32, _f32, _vp],
+    "rgnn_sigmoid_grad": [_i32, _vp, _vp, _vp, _i64, _vp],
+    "rgnn_axpby": [_i32, _f32, _vp, _f32, _vp, _vp, _i64, _vp],
+    "rgnn_bias_add": [_i32, _vp, _vp, _vp, _i64, _i64, _vp],
+    "rgnn_reduce_sum": [_i32, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp],
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"librobotgnn.so not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU / PyTorch fallback for the robot-graph layers.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = ctypes.c_int
+        l.rgnn_last_error.argtypes = []
+        l.rgnn_last_error.restype = ctypes.c_char_p
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().rgnn_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"robot-graph kernels support float32 and bfloat16, got {t.dtype}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("robot-graph layers run on CUDA (sm_100a) only - there is no CPU fallback; "
+                               "move the graph and its features to a B200 device first")

@@ -1,0 +1,302 @@
+// A4/A8 (+A10, A11): strided GEMM family on CUDA cores with fp32-exact products - the PARITY path
+// (fp32 1e-5 cannot be met by a single-pass bf16/tf32 MMA on the K = 2F contraction) and the
+// general-shape fallback of the tcgen05 path in gemm_tc.cu.
+// Tile 64x64x16, 256 threads, 4x4 register micro-tile, operands converted to fp32 in shared memory.
+#include "common.cuh"
+
+namespace rgnn {
+
+struct GemmParams {
+  const void* A; int64_t sAz, sAr, sAm, sAk;
+  const void* B; int64_t sBz, sBr, sBk, sBn;
+  void* C; int64_t sCz, sCm, sCn;
+  int64_t M, N, K, batch, red, split;
+  float* partial;
+  int epi; const float* bias; const void* aux; float alpha, beta;
+  int c_dtype;
+  int64_t tiles_m, tiles_n;
+};
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__device__ __forceinline__ float epilogue(int epi, float acc, int64_t m, int64_t n, const float* bias, float auxv, float alpha, float beta) {
+  float v = alpha * acc;
+  if (epi & RGNN_EPI_ADD_AUX) v = fmaf(beta, auxv, v);
+  if (epi & RGNN_EPI_BIAS_M) v += bias[m];
+  if (epi & RGNN_EPI_BIAS_N) v += bias[n];
+  if (epi & RGNN_EPI_SIGMOID) v = 1.0f / (1.0f + expf(-v));
+  if (epi & RGNN_EPI_RELU_MASK) v = auxv > 0.f ? v : 0.f;
+  return v;
+}
+
+__device__ __forceinline__ float load_aux(int c_dtype, const void* aux, int64_t idx) {
+  if (!aux) return 0.f;
+  return c_dtype == RGNN_F32 ? static_cast<const float*>(aux)[idx] : __bfloat162float(static_cast<const __nv_bfloat16*>(aux)[idx]);
+}
+__device__ __forceinline__ void store_c(int c_dtype, void* C, int64_t idx, float v) {
+  if (c_dtype == RGNN_F32) static_cast<float*>(C)[idx] = v;
+  else static_cast<__nv_bfloat16*>(C)[idx] = __float2bfloat16_rn(v);
+}
+
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256) k_gemm_simt(GemmParams p) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  int64_t bid = blockIdx.x;
+  const int64_t tn = bid % p.tiles_n; bid /= p.tiles_n;
+  const int64_t tm = bid % p.tiles_m; bid /= p.tiles_m;
+  const int64_t zs = bid;                       // batch index, or split index when split > 1
+  const int64_t z = p.split > 1 ? 0 : zs;
+  int64_t r0 = 0, r1 = p.red, kbeg = 0, kend = p.K;
+  if (p.split > 1) {
+    if (p.red > 1) {   // cut the reduction-batch loop
+      const int64_t chunk = (p.red + p.split - 1) / p.split;
+      r0 = zs * chunk; r1 = min(p.red, r0 + chunk);
+    } else {           // cut K itself (in multiples of the k-tile)
+      const int64_t chunk = ((p.K + p.split - 1) / p.split + BK - 1) / BK * BK;
+      kbeg = min(p.K, zs * chunk); kend = min(p.K, kbeg + chunk);
+    }
+  }
+  const int64_t m0 = tm * BM, n0 = tn * BN;
+  const TA* __restrict__ A = static_cast<const TA*>(p.A) + z * p.sAz;
+  const TB* __restrict__ B = static_cast<const TB*>(p.B) + z * p.sBz;
+  const bool a_kfast = p.sAk == 1, b_nfast = p.sBn == 1;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int64_t r = r0; r < r1; ++r) {
+    const TA* Ar = A + r * p.sAr;
+    const TB* Br = B + r * p.sBr;
+    for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int i = tid + it * 256;
+        int am, ak;
+        if (a_kfast) { ak = i & 15; am = i >> 4; } else { am = i & 63; ak = i >> 6; }
+        const int64_t gm = m0 + am, gk = k0 + ak;
+        As[ak][am] = (gm < p.M && gk < kend) ? to_f32<TA>(Ar[gm * p.sAm + gk * p.sAk]) : 0.f;
+        int bn, bk;
+        if (b_nfast) { bn = i & 63; bk = i >> 6; } else { bk = i & 15; bn = i >> 4; }
+        const int64_t gn = n0 + bn, gk2 = k0 + bk;
+        Bs[bk][bn] = (gn < p.N && gk2 < kend) ? to_f32<TB>(Br[gk2 * p.sBk + gn * p.sBn]) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+  if (p.split > 1) {
+    float* P = p.partial + zs * p.M * p.N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t m = m0 + ty * 4 + i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t n = n0 + tx * 4 + j;
+        if (m < p.M && n < p.N) P[m * p.N + n] = acc[i][j];
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t n = n0 + tx * 4 + j;
+      if (m < p.M && n < p.N) {
+        const int64_t idx = z * p.sCz + m * p.sCm + n * p.sCn;
+        store_c(p.c_dtype, p.C, idx, epilogue(p.epi, acc[i][j], m, n, p.bias, load_aux(p.c_dtype, p.aux, idx), p.alpha, p.beta));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_splitk_reduce(GemmParams p) {
+  const int64_t total = p.M * p.N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int64_t s = 0; s < p.split; ++s) acc += p.partial[s * total + i];   // fixed order -> deterministic
+    const int64_t m = i / p.N, n = i % p.N;
+    const int64_t idx = m * p.sCm + n * p.sCn;
+    store_c(p.c_dtype, p.C, idx, epilogue(p.epi, acc, m, n, p.bias, load_aux(p.c_dtype, p.aux, idx), p.alpha, p.beta));
+  }
+}
+
+// out[j] += sum over (i in chunk, k) x[i*s_outer + j*s_j + k*s_inner]
+template <typename T>
+__global__ void __launch_bounds__(256) k_reduce_sum(const T* __restrict__ x, int64_t outer, int64_t s_outer, int64_t len, int64_t s_j,
+                                                    int64_t inner, int64_t s_inner, float* __restrict__ out, int64_t chunk) {
+  const int64_t i0 = (int64_t)blockIdx.y * chunk, i1 = min(outer, i0 + chunk);
+  if (s_j == 1 || inner == 1) {
+    // j-contiguous: thread = j
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= len) return;
+    float acc = 0.f;
+    for (int64_t i = i0; i < i1; ++i)
+      for (int64_t k = 0; k < inner; ++k) acc += to_f32<T>(x[i * s_outer + j * s_j + k * s_inner]);
+    atomicAdd(out + j, acc);
+  } else {
+    // inner-contiguous (NCHW bias gradient): warp = j, lanes stride the inner run
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= len) return;
+    float acc = 0.f;
+    for (int64_t i = i0; i < i1; ++i)
+      for (int64_t k = lane; k < inner; k += 32) acc += to_f32<T>(x[i * s_outer + j * s_j + k * s_inner]);
+    acc = warp_sum(acc);
+    if (lane == 0) atomicAdd(out + j, acc);
+  }
+}
+
+}  // namespace rgnn
+
+using namespace rgnn;
+
+extern "C" int rgnn_gemm(int a_dtype, const void* A, int64_t sAz, int64_t sAr, int64_t sAm, int64_t sAk,
+                         int b_dtype, const void* B, int64_t sBz, int64_t sBr, int64_t sBk, int64_t sBn,
+                         int c_dtype, void* C, int64_t sCz, int64_t sCm, int64_t sCn,
+                         int64_t M, int64_t N, int64_t K, int64_t batch, int64_t red, int64_t split, float* partial,
+                         int epi, const float* bias, const void* aux, float alpha, float beta, void* stream) {
+  RGNN_REQUIRE((a_dtype | 1) == 1 && (b_dtype | 1) == 1 && (c_dtype | 1) == 1, RGNN_E_ARG, "rgnn_gemm: bad dtype");
+  RGNN_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 0 && red >= 0 && split >= 1, RGNN_E_ARG, "rgnn_gemm: bad sizes");
+  RGNN_REQUIRE(epi >= 0 && epi < 32, RGNN_E_ARG, "rgnn_gemm: bad epilogue %d", epi);
+  RGNN_REQUIRE(!((epi & RGNN_EPI_BIAS_M) && (epi & RGNN_EPI_BIAS_N)), RGNN_E_ARG, "rgnn_gemm: one bias vector only");
+  if (M == 0 || N == 0 || batch == 0) return 0;
+  RGNN_REQUIRE(A && B && C, RGNN_E_ARG, "rgnn_gemm: null operand");
+  RGNN_REQUIRE(!(epi & (RGNN_EPI_BIAS_M | RGNN_EPI_BIAS_N)) || bias, RGNN_E_ARG, "rgnn_gemm: epilogue needs bias");
+  RGNN_REQUIRE(!(epi & (RGNN_EPI_RELU_MASK | RGNN_EPI_ADD_AUX)) || aux, RGNN_E_ARG, "rgnn_gemm: epilogue needs aux");
+  RGNN_REQUIRE(split == 1 || (batch == 1 && partial), RGNN_E_ARG, "rgnn_gemm: split needs batch == 1 and a partial buffer");
+  GemmParams p;
+  p.A = A; p.sAz = sAz; p.sAr = sAr; p.sAm = sAm; p.sAk = sAk;
+  p.B = B; p.sBz = sBz; p.sBr = sBr; p.sBk = sBk; p.sBn = sBn;
+  p.C = C; p.sCz = sCz; p.sCm = sCm; p.sCn = sCn;
+  p.M = M; p.N = N; p.K = K; p.batch = batch; p.red = red; p.split = split;
+  if (red > 1 && p.split > red) p.split = red;
+  if (red <= 1 && p.split > (K + BK - 1) / BK) p.split = (K + BK - 1) / BK;
+  if (p.split < 1) p.split = 1;
+  p.partial = partial; p.epi = epi; p.bias = bias; p.aux = aux; p.alpha = alpha; p.beta = beta; p.c_dtype = c_dtype;
+  p.tiles_m = (M + BM - 1) / BM; p.tiles_n = (N + BN - 1) / BN;
+  const int64_t blocks = p.tiles_m * p.tiles_n * (p.split > 1 ? p.split : batch);
+  RGNN_REQUIRE(blocks < (1ll << 31), RGNN_E_RANGE, "rgnn_gemm: grid too large");
+  cudaStream_t st = as_stream(stream);
+  if (a_dtype == RGNN_F32 && b_dtype == RGNN_F32) k_gemm_simt<float, float><<<(unsigned)blocks, 256, 0, st>>>(p);
+  else if (a_dtype == RGNN_F32) k_gemm_simt<float, __nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(p);
+  else if (b_dtype == RGNN_F32) k_gemm_simt<__nv_bfloat16, float><<<(unsigned)blocks, 256, 0, st>>>(p);
+  else k_gemm_simt<__nv_bfloat16, __nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(p);
+  RGNN_LAUNCH_CHECK("k_gemm_simt");
+  if (p.split > 1) {
+    int64_t rb = (M * N + 255) / 256;
+    if (rb > 16 * kNumSMs) rb = 16 * kNumSMs;
+    k_splitk_reduce<<<(unsigned)rb, 256, 0, st>>>(p);
+    RGNN_LAUNCH_CHECK("k_splitk_reduce");
+  }
+  return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_sigmoid_grad(const T* __restrict__ z, const T* __restrict__ dz, T* __restrict__ o, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float zz = rgnn::to_f32<T>(z[i]);
+    o[i] = rgnn::from_f32<T>(rgnn::to_f32<T>(dz[i]) * zz * (1.f - zz));
+  }
+}
+
+extern "C" int rgnn_sigmoid_grad(int dtype, const void* z, const void* dz, void* dzpre, int64_t n, void* stream) {
+  RGNN_REQUIRE(dtype == RGNN_F32 || dtype == RGNN_BF16, RGNN_E_ARG, "rgnn_sigmoid_grad: bad dtype %d", dtype);
+  RGNN_REQUIRE(n >= 0, RGNN_E_ARG, "rgnn_sigmoid_grad: negative size");
+  if (n == 0) return 0;
+  RGNN_REQUIRE(z && dz && dzpre, RGNN_E_ARG, "rgnn_sigmoid_grad: null pointer");
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == RGNN_F32) k_sigmoid_grad<float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(z), static_cast<const float*>(dz), static_cast<float*>(dzpre), n);
+  else k_sigmoid_grad<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(z), static_cast<const __nv_bfloat16*>(dz), static_cast<__nv_bfloat16*>(dzpre), n);
+  RGNN_LAUNCH_CHECK("k_sigmoid_grad");
+  return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_axpby(float a, const T* __restrict__ x, float b, const T* __restrict__ y, T* __restrict__ o, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = a * rgnn::to_f32<T>(x[i]);
+    if (b != 0.f) v = fmaf(b, rgnn::to_f32<T>(y[i]), v);
+    o[i] = rgnn::from_f32<T>(v);
+  }
+}
+
+extern "C" int rgnn_axpby(int dtype, float a, const void* x, float b, const void* y, void* out, int64_t n, void* stream) {
+  RGNN_REQUIRE(dtype == RGNN_F32 || dtype == RGNN_BF16, RGNN_E_ARG, "rgnn_axpby: bad dtype %d", dtype);
+  RGNN_REQUIRE(n >= 0, RGNN_E_ARG, "rgnn_axpby: negative size");
+  if (n == 0) return 0;
+  RGNN_REQUIRE(x && y && out, RGNN_E_ARG, "rgnn_axpby: null pointer");
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == RGNN_F32) k_axpby<float><<<(unsigned)blocks, 256, 0, st>>>(a, static_cast<const float*>(x), b, static_cast<const float*>(y), static_cast<float*>(out), n);
+  else k_axpby<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(a, static_cast<const __nv_bfloat16*>(x), b, static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(out), n);
+  RGNN_LAUNCH_CHECK("k_axpby");
+  return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_bias_add(const T* __restrict__ x, const float* __restrict__ b, T* __restrict__ o, int64_t rows, int64_t cols) {
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    o[i] = rgnn::from_f32<T>(rgnn::to_f32<T>(x[i]) + b[i % cols]);
+}
+
+extern "C" int rgnn_bias_add(int dtype, const void* x, const float* bias, void* out, int64_t rows, int64_t cols, void* stream) {
+  RGNN_REQUIRE(dtype == RGNN_F32 || dtype == RGNN_BF16, RGNN_E_ARG, "rgnn_bias_add: bad dtype %d", dtype);
+  RGNN_REQUIRE(rows >= 0 && cols >= 0, RGNN_E_ARG, "rgnn_bias_add: negative size");
+  if (rows == 0 || cols == 0) return 0;
+  RGNN_REQUIRE(x && bias && out, RGNN_E_ARG, "rgnn_bias_add: null pointer");
+  int64_t blocks = (rows * cols + 255) / 256;
+  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == RGNN_F32) k_bias_add<float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(x), bias, static_cast<float*>(out), rows, cols);
+  else k_bias_add<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), bias, static_cast<__nv_bfloat16*>(out), rows, cols);
+  RGNN_LAUNCH_CHECK("k_bias_add");
+  return 0;
+}
+
+extern "C" int rgnn_reduce_sum(int dtype, const void* x, int64_t outer, int64_t s_outer, int64_t len, int64_t s_j,
+                               int64_t inner, int64_t s_inner, float* out, void* stream) {
+  RGNN_REQUIRE(dtype == RGNN_F32 || dtype == RGNN_BF16, RGNN_E_ARG, "rgnn_reduce_sum: bad dtype %d", dtype);
+  RGNN_REQUIRE(outer >= 0 && len >= 0 && inner >= 0, RGNN_E_ARG, "rgnn_reduce_sum: bad sizes");
+  if (len == 0) return 0;
+  RGNN_REQUIRE(out, RGNN_E_ARG, "rgnn_reduce_sum: null out");
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * len, st);
+  if (e != cudaSuccess) return cuda_fail(e, "memset reduce out");
+  if (outer == 0 || inner == 0) return 0;
+  RGNN_REQUIRE(x, RGNN_E_ARG, "rgnn_reduce_sum: null x");
+  const bool jfast = (s_j == 1 || inner == 1);
+  const int64_t bx = jfast ? (len + 255) / 256 : (len + 7) / 8;
+  int64_t chunks = (8 * kNumSMs + bx - 1) / bx;
+  if (chunks > outer) chunks = outer;
+  if (chunks > 65535) chunks = 65535;
+  if (chunks < 1) chunks = 1;
+  const int64_t chunk = (outer + chunks - 1) / chunks;
+  chunks = (outer + chunk - 1) / chunk;
+  RGNN_REQUIRE(bx < (1ll << 31), RGNN_E_RANGE, "rgnn_reduce_sum: too long");
+  dim3 grid((unsigned)bx, (unsigned)chunks);
+  if (dtype == RGNN_F32) k_reduce_sum<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), outer, s_outer, len, s_j, inner, s_inner, out, chunk);
+  else k_reduce_sum<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), outer, s_outer, len, s_j, inner, s_inner, out, chunk);
+  RGNN_LAUNCH_CHECK("k_reduce_sum");
+  return 0;
+}

@@ -1,0 +1,405 @@
+"""torch.autograd.Function wrappers over the C ABI of librobotgnn.so.
+
+Every forward/backward here is a sequence of kernel launches on torch's current stream - no host sync,
+no torch math on the data path (torch only allocates the output tensors).
+Reference math: SURVEY.md App. A; reference code: dgl/model/models.py:142-155 (edge encoder),
+:207-211 (FiLM message / mean), :182-184 (concat + 1x1 compress).
+"""
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, stream, dtype_code
+
+_POST = {"none": _lib.POST_NONE, "sum": _lib.POST_NONE, "mean": _lib.POST_MEAN, "scale": _lib.POST_SCALE}
+
+
+def _row_shape(x):
+    f = x.shape[1] if x.dim() > 1 else 1
+    p = 1
+    for s in x.shape[2:]:
+        p *= s
+    return f, p
+
+
+def _aggregate(ix, x, z, use_beta, nbr_scale, post, dst_scale, addend, out, copy_to, transposed,
+               ldx=None, ldadd=None, ldout=None, shape=None):
+    """One rgnn_aggregate launch.  x [N, F, *] (node stride ldx); out node stride ldout."""
+    f, p = shape if shape is not None else _row_shape(x)
+    if z is None:            # no per-channel modulation: channels and pixels are interchangeable
+        f, p = 1, f * p
+    row = f * p
+    if transposed:
+        ptr32, nbr, eid = ix.out_ptr32, ix.out_dst32, ix.out_eid32
+    else:
+        ptr32, nbr, eid = ix.in_ptr32, ix.in_src32, ix.in_eid32
+    check(lib().rgnn_aggregate(dtype_code(x), ptr(x), row if ldx is None else ldx, ptr(z), int(use_beta), ptr(nbr_scale), post,
+                               ptr(dst_scale), ptr(addend), row if ldadd is None else ldadd, ptr(out),
+                               row if ldout is None else ldout, ptr(copy_to),
+                               ptr(ptr32), ptr(nbr), ptr(eid), ptr(ix.noff32), ix.G, ix.max_nodes, ix.max_edges,
+                               ix.N, ix.E, f, p, stream()), "rgnn_aggregate")
+    return out
+
+
+class AggregateFn(torch.autograd.Function):
+    """out[v] = post_v( sum_{e in in(v)} (gamma_e * ns[src_e] * x[src_e] + beta_e) ).
+
+    z given  -> FiLM message + mean reduce of the reference GCN (edge_udf/node_udf, models.py:207-211).
+    z None   -> update_all(copy_u, sum|mean) with optional GraphConv-style degree scales.
+    """
+
+    @staticmethod
+    def forward(ctx, x, z, g, post, nbr_scale, dst_scale):
+        ix = g.index()
+        _lib.require_cuda(x, z)
+        x = x.contiguous()
+        if z is not None:
+            if post != "mean" or nbr_scale is not None:
+                raise ValueError("FiLM modulation is defined for the mean reduce without degree scales")
+            z = z.contiguous()
+            if z.dtype != x.dtype:
+                raise TypeError("z and x must share a dtype")
+            if z.shape != (ix.E, 2 * x.shape[1]):
+                raise ValueError(f"z must be [E, 2F] = [{ix.E}, {2 * x.shape[1]}], got {tuple(z.shape)}")
+        if x.shape[0] != ix.N:
+            raise ValueError(f"feature rows ({x.shape[0]}) != graph nodes ({ix.N})")
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _aggregate(ix, x, z, True, nbr_scale, _POST[post], dst_scale, None, out, None, False)
+        ctx.g, ctx.post = g, post
+        ctx.save_for_backward(x, z, nbr_scale, dst_scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, z, nbr_scale, dst_scale = ctx.saved_tensors
+        ix = ctx.g.index()
+        dout = dout.contiguous()
+        dx = dz = None
+        with torch.cuda.device(dout.device):
+            if ctx.needs_input_grad[0]:
+                back_nbr = {"mean": ix.inv_in_deg, "scale": dst_scale}.get(ctx.post)
+                dx = torch.empty_like(x)
+                _aggregate(ix, dout, z, False, back_nbr, _lib.POST_SCALE if nbr_scale is not None else _lib.POST_NONE,
+                           nbr_scale, None, dx, None, True)
+            if z is not None and ctx.needs_input_grad[1]:
+                f, p = _row_shape(x)
+                dz = torch.empty_like(z)
+                check(lib().rgnn_film_edge_grad(dtype_code(x), ptr(x), f * p, ptr(dout), f * p, ptr(z), 0, ptr(ix.inv_in_deg),
+                                                ptr(ix.src32), ptr(ix.dst32), ptr(dz), ix.E, f, p, stream()), "rgnn_film_edge_grad")
+        return dx, dz, None, None, None, None
+
+
+class FilmMeanCatFn(torch.autograd.Function):
+    """torch.cat((h, g_h), dim=1) with g_h = FiLM-mean(h)  (dgl/model/models.py:181-182) in ONE kernel: the
+    aggregate lands in the second channel half of the output and h is copied into the first half from the
+    tile already staged in shared memory."""
+
+    @staticmethod
+    def forward(ctx, h, z, g):
+        ix = g.index()
+        _lib.require_cuda(h, z)
+        h = h.contiguous()
+        f, p = _row_shape(h)
+        if z is not None:
+            z = z.contiguous()
+            if z.dtype != h.dtype or z.shape != (ix.E, 2 * f):
+                raise ValueError("z must be [E, 2F] in the dtype of h")
+        if h.shape[0] != ix.N:
+            raise ValueError(f"feature rows ({h.shape[0]}) != graph nodes ({ix.N})")
+        out = torch.empty((h.shape[0], 2 * f) + tuple(h.shape[2:]), dtype=h.dtype, device=h.device)
+        with torch.cuda.device(h.device):
+            _aggregate(ix, h, z, True, None, _lib.POST_MEAN, None, None, out.view(-1)[f * p:], out, False,
+                       ldout=2 * f * p, shape=(f, p))
+        ctx.g = g
+        ctx.save_for_backward(h, z)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, z = ctx.saved_tensors
+        ix = ctx.g.index()
+        dout = dout.contiguous()
+        f, p = _row_shape(h)
+        dagg = dout.view(-1)[f * p:]          # second channel half, node stride 2FP
+        dh = dz = None
+        with torch.cuda.device(dout.device):
+            if ctx.needs_input_grad[0]:
+                dh = torch.empty_like(h)
+                _aggregate(ix, dagg, z, False, ix.inv_in_deg, _lib.POST_NONE, None, dout, dh, None, True,
+                           ldx=2 * f * p, ldadd=2 * f * p, shape=(f, p))
+            if z is not None and ctx.needs_input_grad[1]:
+                dz = torch.empty_like(z)
+                check(lib().rgnn_film_edge_grad(dtype_code(h), ptr(h), f * p, ptr(dagg), 2 * f * p, ptr(z), 0, ptr(ix.inv_in_deg),
+                                                ptr(ix.src32), ptr(ix.dst32), ptr(dz), ix.E, f, p, stream()), "rgnn_film_edge_grad")
+        return dh, dz, None
+
+
+def film_mean_cat(g, h, z):
+    """cat(h, FiLM-mean(h)) along channels, [N, 2F, ...]."""
+    return FilmMeanCatFn.apply(h, z, g)
+
+
+def film_mean(g, h, z):
+    """agg = mean over in-edges of (gamma_e * h[src_e] + beta_e); z = [E, 2F] interleaved (gamma, beta)."""
+    return AggregateFn.apply(h, z, g, "mean", None, None)
+
+
+def copy_u_reduce(g, x, op="sum", nbr_scale=None, dst_scale=None):
+    """update_all(fn.copy_u, fn.sum|fn.mean) with optional per-source / per-destination scales."""
+    post = "scale" if (op == "sum" and dst_scale is not None) else op
+    return AggregateFn.apply(x, None, g, post, nbr_scale, dst_scale)
+
+
+def _gemm(a, sa, b, sb, c, sc, m, n, k, batch=1, red=1, split=1, partial=None, epi=0, bias=None, aux=None, alpha=1.0, beta=0.0):
+    check(lib().rgnn_gemm(dtype_code(a), ptr(a), *sa, dtype_code(b), ptr(b), *sb, dtype_code(c), ptr(c), *sc,
+                          m, n, k, batch, red, split, ptr(partial), epi, ptr(bias), ptr(aux), alpha, beta, stream()), "rgnn_gemm")
+
+
+def _splits(tiles, work_items):
+    """Enough split-K slices to fill 148 SMs about twice, at most one per work item."""
+    s = max(1, (2 * 148 + tiles - 1) // tiles)
+    return max(1, min(s, work_items))
+
+
+class EdgeMLPFn(torch.autograd.Function):
+    """z = sigmoid(relu(pose W1^T + b1) W2^T + b2)  - edge_encoder.layers (models.py:146-151); [E, 2F]."""
+
+    @staticmethod
+    def forward(ctx, pose, w1, b1, w2, b2, out_dtype):
+        _lib.require_cuda(pose, w1, b1, w2, b2)
+        pose = pose.float().contiguous()          # edge.float(), models.py:153
+        e, hid, f2 = pose.shape[0], w1.shape[0], w2.shape[0]
+        if pose.shape[1] != 9 or w1.shape != (hid, 9) or w2.shape != (f2, hid) or f2 % 2:
+            raise ValueError("edge encoder expects pose [E,9], W1 [H,9], W2 [2F,H]")
+        w1, b1, w2, b2 = (t.detach().float().contiguous() for t in (w1, b1, w2, b2))
+        a1 = torch.empty((e, hid), dtype=out_dtype, device=pose.device)
+        z = torch.empty((e, f2), dtype=out_dtype, device=pose.device)
+        with torch.cuda.device(pose.device):
+            check(lib().rgnn_edge_mlp1_fwd(dtype_code(a1), ptr(pose), ptr(w1), ptr(b1), ptr(a1), e, hid, stream()), "rgnn_edge_mlp1_fwd")
+            _gemm(a1, (0, 0, hid, 1), w2, (0, 0, 1, hid), z, (0, f2, 1), e, f2, hid,
+                  epi=_lib.EPI_BIAS_N | _lib.EPI_SIGMOID, bias=b2)
+        ctx.save_for_backward(pose, w2, a1, z)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        pose, w2, a1, z = ctx.saved_tensors
+        dz = dz.contiguous()
+        dev = dz.device
+        with torch.cuda.device(dev):
+            dzp = torch.empty_like(z)
+            check(lib().rgnn_sigmoid_grad(dtype_code(z), ptr(z), ptr(dz), ptr(dzp), z.numel(), stream()), "rgnn_sigmoid_grad")
+            dw1, db1, dw2, db2 = edge_mlp_param_grads(pose, w2, a1, dzp)
+        return None, dw1, db1, dw2, db2, None
+
+
+def edge_mlp_param_grads(pose, w2, a1, dzp):
+    """Parameter gradients of the edge encoder from dzp = dL/d(pre-sigmoid) [E, 2F] (autograd of models.py:146-151)."""
+    e, hid = a1.shape
+    f2 = w2.shape[0]
+    dev = a1.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    da1 = torch.empty_like(a1)
+    _gemm(dzp, (0, 0, f2, 1), w2, (0, 0, hid, 1), da1, (0, hid, 1), e, hid, f2, epi=_lib.EPI_RELU_MASK, aux=a1)
+    dw2 = torch.empty((f2, hid), **f32)
+    split = _splits(((f2 + 63) // 64) * ((hid + 63) // 64), max(1, (e + 63) // 64))
+    partial = torch.empty((split, f2, hid), **f32) if split > 1 else None
+    _gemm(dzp, (0, 0, 1, f2), a1, (0, 0, hid, 1), dw2, (0, hid, 1), f2, hid, e, split=split, partial=partial)
+    db2 = torch.empty((f2,), **f32)
+    check(lib().rgnn_reduce_sum(dtype_code(dzp), ptr(dzp), e, f2, f2, 1, 1, 1, ptr(db2), stream()), "rgnn_reduce_sum")
+    dw1, db1 = torch.empty((hid, 9), **f32), torch.empty((hid,), **f32)
+    check(lib().rgnn_edge_mlp1_bwd(dtype_code(da1), ptr(pose), ptr(da1), ptr(dw1), ptr(db1), e, hid, stream()), "rgnn_edge_mlp1_bwd")
+    return dw1, db1, dw2, db2
+
+
+def edge_mlp(pose, w1, b1, w2, b2, out_dtype=torch.float32):
+    return EdgeMLPFn.apply(pose, w1, b1, w2, b2, out_dtype)
+
+
+class CompressFn(torch.autograd.Function):
+    """y = Conv2d(2F, F, 1)(cat(h, g_h))  - dgl/model/models.py:182-184 - without materialising the concat:
+    y_v = Wc[:, :F] h_v + Wc[:, F:] g_v + bc per node (a [F x 2F] . [2F x P] product per robot)."""
+
+    @staticmethod
+    def forward(ctx, h, gh, wc, bc):
+        _lib.require_cuda(h, gh, wc, bc)
+        h, gh = h.contiguous(), gh.contiguous()
+        n, f = h.shape[0], h.shape[1]
+        _, p = _row_shape(h)
+        wc2 = wc.detach().float().reshape(wc.shape[0], -1).contiguous()
+        fo = wc2.shape[0]
+        if wc2.shape[1] != 2 * f or gh.shape != h.shape or h.dtype != gh.dtype:
+            raise ValueError("compress expects h, g_h [N,F,...] and weight [Fo, 2F(,1,1)]")
+        bcf = bc.detach().float().contiguous()
+        y = torch.empty((n, fo) + tuple(h.shape[2:]), dtype=h.dtype, device=h.device)
+        with torch.cuda.device(h.device):
+            if p == 1:    # [N,F,1,1] maps: the nodes form the N dimension of one product
+                sb, sc, bt, nn = (0, 0, 1, f), (0, 1, fo), 1, n
+            else:         # one [Fo x P] product per node
+                sb, sc, bt, nn = (f * p, 0, p, 1), (fo * p, p, 1), n, p
+            _gemm(wc2, (0, 0, 2 * f, 1), h, sb, y, sc, fo, nn, f, batch=bt, epi=_lib.EPI_BIAS_M, bias=bcf)
+            _gemm(wc2[:, f:], (0, 0, 2 * f, 1), gh, sb, y, sc, fo, nn, f, batch=bt, epi=_lib.EPI_ADD_AUX, aux=y, beta=1.0)
+        ctx.save_for_backward(h, gh, wc2)
+        ctx.wshape = tuple(wc.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, gh, wc2 = ctx.saved_tensors
+        dy = dy.contiguous()
+        n, f = h.shape[0], h.shape[1]
+        _, p = _row_shape(h)
+        fo = wc2.shape[0]
+        dev = dy.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        dh = dgh = dwc = dbc = None
+        with torch.cuda.device(dev):
+            if p == 1:
+                sb, sc, bt, nn = (0, 0, 1, fo), (0, 1, f), 1, n
+            else:
+                sb, sc, bt, nn = (fo * p, 0, p, 1), (f * p, p, 1), n, p
+            if ctx.needs_input_grad[0]:
+                dh = torch.empty_like(h)
+                _gemm(wc2, (0, 0, 1, 2 * f), dy, sb, dh, sc, f, nn, fo, batch=bt)
+            if ctx.needs_input_grad[1]:
+                dgh = torch.empty_like(gh)
+                _gemm(wc2[:, f:], (0, 0, 1, 2 * f), dy, sb, dgh, sc, f, nn, fo, batch=bt)
+            if ctx.needs_input_grad[2]:
+                dwc = torch.empty((fo, 2 * f), **f32)
+                split = _splits(((fo + 63) // 64) * ((f + 63) // 64), n)
+                partial = torch.empty((split, fo, f), **f32) if split > 1 else None
+                for half, src in ((0, h), (1, gh)):
+                    # dWc[o, k2] = sum_v sum_p dy[v,o,p] * src[v,k2,p]: K = P per node, reduced over the N nodes
+                    _gemm(dy, (0, fo * p, p, 1), src, (0, f * p, 1, p), dwc[:, half * f:], (0, 2 * f, 1), fo, f, p,
+                          red=n, split=split, partial=partial)
+                dwc = dwc.reshape(ctx.wshape)
+            if ctx.needs_input_grad[3]:
+                dbc = torch.empty((fo,), **f32)
+                check(lib().rgnn_reduce_sum(dtype_code(dy), ptr(dy), n, fo * p, fo, p, p, 1, ptr(dbc), stream()), "rgnn_reduce_sum")
+        return dh, dgh, dwc, dbc
+
+
+def compress(h, gh, wc, bc):
+    return CompressFn.apply(h, gh, wc, bc)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = alpha * (x @ W) + ident * x + bias on the last dim (W is [in, out] as in DGL).
+    ident = 0: GraphConv weight transform; ident = 1 - beta, alpha = beta: GCN2Conv's identity mapping
+    ((1-beta) I + beta W) - both fused in the GEMM epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, alpha, ident):
+        _lib.require_cuda(x, w, bias)
+        x = x.contiguous()
+        din, dout = w.shape
+        if x.shape[-1] != din or (ident != 0.0 and din != dout):
+            raise ValueError("linear: feature size mismatch")
+        rows = x.numel() // din
+        wf = w.detach().float().contiguous()
+        y = torch.empty(tuple(x.shape[:-1]) + (dout,), dtype=x.dtype, device=x.device)
+        epi, bf = 0, None
+        if bias is not None:
+            epi |= _lib.EPI_BIAS_N
+            bf = bias.detach().float().contiguous()
+        if ident != 0.0:
+            epi |= _lib.EPI_ADD_AUX
+        with torch.cuda.device(x.device):
+            _gemm(x, (0, 0, din, 1), wf, (0, 0, dout, 1), y, (0, dout, 1), rows, dout, din, epi=epi, bias=bf,
+                  aux=x if ident != 0.0 else None, alpha=float(alpha), beta=float(ident))
+        ctx.save_for_backward(x, wf)
+        ctx.alpha, ctx.ident, ctx.has_bias = float(alpha), float(ident), bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wf = ctx.saved_tensors
+        dy = dy.contiguous()
+        din, dout = wf.shape
+        rows = x.numel() // din
+        f32 = dict(dtype=torch.float32, device=dy.device)
+        dx = dw = db = None
+        with torch.cuda.device(dy.device):
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty_like(x)
+                _gemm(dy, (0, 0, dout, 1), wf, (0, 0, 1, dout), dx, (0, din, 1), rows, din, dout,
+                      epi=_lib.EPI_ADD_AUX if ctx.ident != 0.0 else 0, aux=dy if ctx.ident != 0.0 else None,
+                      alpha=ctx.alpha, beta=ctx.ident)
+            if ctx.needs_input_grad[1]:
+                dw = torch.empty((din, dout), **f32)
+                split = _splits(((din + 63) // 64) * ((dout + 63) // 64), max(1, (rows + 63) // 64))
+                partial = torch.empty((split, din, dout), **f32) if split > 1 else None
+                _gemm(x, (0, 0, 1, din), dy, (0, 0, dout, 1), dw, (0, dout, 1), din, dout, rows, split=split, partial=partial,
+                      alpha=ctx.alpha)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = torch.empty((dout,), **f32)
+                check(lib().rgnn_reduce_sum(dtype_code(dy), ptr(dy), rows, dout, dout, 1, 1, 1, ptr(db), stream()), "rgnn_reduce_sum")
+        return dx, dw, db, None, None
+
+
+def linear(x, w, bias=None, alpha=1.0, ident=0.0):
+    return LinearFn.apply(x, w, bias, alpha, ident)
+
+
+class AxpbyFn(torch.autograd.Function):
+    """out = a * x + b * y  (GCN2Conv's initial-residual mix (1-alpha) * agg + alpha * feat_0)."""
+
+    @staticmethod
+    def forward(ctx, x, y, a, b):
+        _lib.require_cuda(x, y)
+        x, y = x.contiguous(), y.contiguous()
+        if x.shape != y.shape or x.dtype != y.dtype:
+            raise ValueError("axpby operands must match")
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(lib().rgnn_axpby(dtype_code(x), float(a), ptr(x), float(b), ptr(y), ptr(out), x.numel(), stream()), "rgnn_axpby")
+        ctx.a, ctx.b = float(a), float(b)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        d = d.contiguous()
+        outs = []
+        with torch.cuda.device(d.device):
+            for need, coef in ((ctx.needs_input_grad[0], ctx.a), (ctx.needs_input_grad[1], ctx.b)):
+                if not need:
+                    outs.append(None)
+                    continue
+                o = torch.empty_like(d)
+                check(lib().rgnn_axpby(dtype_code(d), coef, ptr(d), 0.0, ptr(d), ptr(o), d.numel(), stream()), "rgnn_axpby")
+                outs.append(o)
+        return outs[0], outs[1], None, None
+
+
+def axpby(x, y, a, b):
+    return AxpbyFn.apply(x, y, a, b)
+
+
+class BiasAddFn(torch.autograd.Function):
+    """y = x + bias over the last dim (GraphConv bias when no weight transform follows the aggregation)."""
+
+    @staticmethod
+    def forward(ctx, x, bias):
+        _lib.require_cuda(x, bias)
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        bf = bias.detach().float().contiguous()
+        with torch.cuda.device(x.device):
+            check(lib().rgnn_bias_add(dtype_code(x), ptr(x), ptr(bf), ptr(y), x.numel() // bf.numel(), bf.numel(), stream()), "rgnn_bias_add")
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        cols = dy.shape[-1]
+        db = None
+        if ctx.needs_input_grad[1]:
+            db = torch.empty((cols,), dtype=torch.float32, device=dy.device)
+            with torch.cuda.device(dy.device):
+                check(lib().rgnn_reduce_sum(dtype_code(dy), ptr(dy), dy.numel() // cols, cols, cols, 1, 1, 1, ptr(db), stream()),
+                      "rgnn_reduce_sum")
+        return dy, db
+
+
+def bias_add(x, bias):
+    return BiasAddFn.apply(x, bias)
