@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py - robot-graph GNN-layer fwd+bwd throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step = one fwd+bwd pass of the GNN block (gcn1 -> compress -> gcn2 -> compress; dgl/model/models.py:180-189) over one
+synthetic batch of K-robot graphs per GPU (+ the NCCL all-reduce of the GNN-layer gradients when N > 1).
+Workload (BASELINE.json configs[1]): warehouse "gcn2" stack, ResNet-18 width F = 512, K = 5 robots,
+P = 8x8, two layers + compress, bf16 I/O with fp32 accumulation, G = 4096 graphs per GPU (h = 1.34 GB >> 126 MB L2).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+F_DIM, K_ROBOTS, PIX = 512, 5, 64
+METRIC = "gnn_layer_fwd_bwd_robot_graphs_per_sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--graphs", type=int, default=4096, help="graphs per GPU per step")
+    ap.add_argument("--feat", type=int, default=F_DIM)
+    ap.add_argument("--robots", type=int, default=K_ROBOTS)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-graphs", type=int, default=32, help="graphs in the bounded CPU-baseline sample")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"warehouse gcn2 stack (2x FiLM-GCN + 1x1 compress), F={a.feat} (resnet18 width), K={a.robots} robots, P=8x8, "
+            f"{a.graphs} graphs/GPU, {a.dtype}")
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(a, reps):
+    """The reference's CPU path (oracle/ref_port.py over oracle/dgl_shim; /root/reference cannot travel) on a bounded
+    sample of the same workload, fp32, all host threads."""
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sec = ref_port.time_block(a.feat, a.robots, a.cpu_graphs, True, True, reps=reps, threads=cores)
+    return a.cpu_graphs / sec, cores, sec
+
+
+def run_reference(a, rank):
+    if rank != 0:
+        return
+    t0 = time.time()
+    rate, cores, sec = cpu_reference_rate(a, reps=max(1, min(a.steps, 5)))
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "graphs/s", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "sample": f"{a.cpu_graphs} graphs per step (bounded sample of the workload)"},
+            "cpu_baseline": {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port",
+                             "sample": f"fwd+bwd of {a.cpu_graphs} graphs, best of {max(1, min(a.steps, 5))} after 1 warm-up, torch {torch.__version__} CPU"},
+            "e2e": {"value": rate, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.time() - t0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if a.impl == "reference":
+        run_reference(a, rank)
+        return
+    import torch.distributed as dist
+    import types
+    import robot_gnn_b200 as R
+    from multi_robot_check import make_block
+    from oracle import gnn_oracle as O   # parameter init + (rank 0) the cpu_baseline leg only
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    R._lib.check(R._lib.lib().rgnn_device_ok(), "rgnn_device_ok")
+
+    dtype = torch.bfloat16 if a.dtype == "bf16" else torch.float32
+    G, K, F = a.graphs, a.robots, a.feat
+    N, E = G * K, G * K * (K - 1)
+    blk, _ = make_block(R, O, F, True, True, seed=1)
+    blk.to(dev)
+    sync = R.parallel.GradSync(blk) if world > 1 else None
+
+    # synthetic inputs of the scripts' shape, seeded per rank; resident in HBM for `value`
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+    h = torch.relu(torch.randn((N, F, 8, 8), generator=gen, device=dev, dtype=torch.float32)).to(dtype).requires_grad_()
+    dy = torch.randn((N, F, 8, 8), generator=gen, device=dev, dtype=torch.float32).to(dtype)
+    pose = torch.randn((E, 9), generator=gen, device=dev, dtype=torch.float32)
+    pose[:, :3] *= 3.0
+    g = R.robot_batch(G, K, device=dev)
+    g.index()
+
+    def step():
+        h.grad = None
+        for p in blk.parameters():
+            p.grad = None
+        y = blk(g, h, pose)
+        y.backward(dy)
+        if sync is not None:
+            sync.finish()
+        return y
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
+    # ---- timed region: device-resident inputs ---------------------------------------------------------------
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    R._lib.PROFILE = {}
+    launches0 = R._lib.lib().rgnn_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(a.steps):
+        step()
+    ev1.record()
+    barrier()
+    launches = R._lib.lib().rgnn_launch_count() - launches0
+    prof = R._lib.profile_summary()
+    R._lib.PROFILE = None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clk = clocks.stop() if rank == 0 else None
+    value = world * G * a.steps / (ms_total * 1e-3)
+
+    # ---- e2e: the public call with HOST buffers; H2D of the step's inputs and D2H of its results inside the timed region
+    e2e = None
+    if not a.no_e2e:
+        hh = h.detach().cpu().pin_memory(); hdy = dy.cpu().pin_memory(); hpose = pose.cpu().pin_memory()
+        out_y = torch.empty((N, F, 8, 8), dtype=dtype).pin_memory(); out_dh = torch.empty((N, F, 8, 8), dtype=dtype).pin_memory()
+        h2d = hh.numel() * hh.element_size() + hdy.numel() * hdy.element_size() + hpose.numel() * 4
+        d2h = 2 * out_y.numel() * out_y.element_size()
+
+        def e2e_step():
+            hd = hh.to(dev, non_blocking=True).requires_grad_()
+            dyd = hdy.to(dev, non_blocking=True)
+            pd = hpose.to(dev, non_blocking=True)
+            for p in blk.parameters():
+                p.grad = None
+            y = blk(g, hd, pd)
+            y.backward(dyd)
+            if sync is not None:
+                sync.finish()
+            out_y.copy_(y.detach(), non_blocking=True)
+            out_dh.copy_(hd.grad, non_blocking=True)
+
+        n_e2e = max(3, min(a.steps, 10))
+        e2e_step(); e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        barrier()
+        ems = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * G * n_e2e / (float(ems.item()) * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": n_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (live CUDA-event timings from the timed region) --------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured" if peaks else "fallback"
+    by_time = sorted(prof.items(), key=lambda kv: -kv[1]["ms_total"])
+    kernels = {}
+    for name, d in prof.items():
+        is_mem = name.startswith(("aggregate", "film_edge"))
+        ach = d["work_total"] / (d["ms_total"] * 1e-3) / (1e9 if is_mem else 1e12) if d["ms_total"] > 0 else 0.0
+        kernels[name] = {"calls": d["calls"], "ms_avg": round(d["ms_avg"], 4), "share": round(d["ms_total"] / ms_total, 4),
+                         "achieved": round(ach, 2), "unit": "GB/s" if is_mem else "TFLOP/s",
+                         "frac": round(ach / (hbm_peak if is_mem else tc_peak), 4)}
+    top, topd = by_time[0]
+    top_mem = top.startswith(("aggregate", "film_edge"))
+    roofline = {"kernel": top, "bound": "hbm" if top_mem else "tensor", "achieved": kernels[top]["achieved"],
+                "peak": hbm_peak if top_mem else tc_peak, "unit": kernels[top]["unit"], "frac": kernels[top]["frac"],
+                "traffic": None, "peak_source": peak_src, "ms_avg_per_launch": kernels[top]["ms_avg"]}
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        rate, cores, sec = cpu_reference_rate(a, reps=3)
+        cpu = {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port",
+               "sample": f"reference CPU path (oracle/ref_port.py over the DGL-semantics shim), fp32, fwd+bwd of {a.cpu_graphs} graphs, "
+                         f"best of 3 after 1 warm-up ({sec * 1e3:.1f} ms)"}
+
+    line = {"metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(a), "graphs_per_gpu": G, "robots": K, "feature_dim": F, "pixels": PIX,
+                       "layers": 2, "compress": True, "l2_policy": "inputs (1.3 GB/GPU) larger than the 126 MB L2",
+                       "parallelism": f"dp{world}: graphs sharded, NCCL all-reduce of GNN-layer grads only"},
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clk}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

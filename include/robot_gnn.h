@@ -55,6 +55,7 @@ int rgnn_version(void);                 /* RGNN_VERSION */
 int rgnn_arch(void);                    /* 100: compiled for sm_100a only */
 const char* rgnn_last_error(void);      /* thread-local, never NULL */
 int rgnn_device_ok(void);               /* 0 if the current device is sm_100; else error code */
+long long rgnn_launch_count(void);      /* kernels this library has launched in this process (bench evidence) */
 
 /* ---- A2: dgl.batch index work  (dgl/training.py:57-58, dgl/eval.py:54-55) ---------------
  * local_src/local_dst [E]: per-graph LOCAL node ids concatenated in graph order.

@@ -7,6 +7,7 @@ Import name: the directory is called ``multi-robot-perception-gnn-1_b200`` (not 
 from . import _lib
 from .graph import RobotGraph, graph, batch, robot_batch, function
 from . import functional
+from . import parallel
 from .functional import film_mean, film_mean_cat, copy_u_reduce, edge_mlp, compress, linear, axpby
 from .layers import edge_encoder, GCN, GNNBlock, GraphConv, GCN2Conv
 

@@ -49,10 +49,45 @@ def lib():
             fn = getattr(l, name)
             fn.argtypes = args
             fn.restype = ctypes.c_int
+        l.rgnn_launch_count.argtypes = []
+        l.rgnn_launch_count.restype = ctypes.c_longlong
         l.rgnn_last_error.argtypes = []
         l.rgnn_last_error.restype = ctypes.c_char_p
         _lib = l
     return _lib
+
+
+# ---- optional per-call CUDA-event timing (bench.py turns it on around its timed region) ------------------
+PROFILE = None      # None = off; else dict: name -> list of (start_event, end_event, work)
+
+
+class timed:
+    """with timed("name", work): <C-ABI call>   - records CUDA events on the current stream when PROFILE is on."""
+
+    def __init__(self, name, work=0.0):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            PROFILE.setdefault(self.name, []).append((self.s, e, self.work))
+        return False
+
+
+def profile_summary():
+    """name -> dict(calls, ms_total, ms_avg, work_total) after a torch.cuda.synchronize()."""
+    out = {}
+    for name, evs in (PROFILE or {}).items():
+        ms = [s.elapsed_time(e) for s, e, _ in evs]
+        out[name] = dict(calls=len(ms), ms_total=sum(ms), ms_avg=sum(ms) / max(1, len(ms)), work_total=sum(w for _, _, w in evs))
+    return out
 
 
 def check(rc, what):

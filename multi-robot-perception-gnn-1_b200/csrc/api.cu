@@ -1,5 +1,6 @@
 // Library queries and error plumbing of librobotgnn.so (include/robot_gnn.h).
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 #include "common.cuh"
 
@@ -19,8 +20,12 @@ int cuda_fail(cudaError_t e, const char* what) {
   return (int)e;
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 }  // namespace rgnn
 
+extern "C" long long rgnn_launch_count(void) { return rgnn::g_launches.load(std::memory_order_relaxed); }
 extern "C" int rgnn_version(void) { return RGNN_VERSION; }
 extern "C" int rgnn_arch(void) { return 100; }
 extern "C" const char* rgnn_last_error(void) { return rgnn::g_err; }

@@ -19,8 +19,11 @@ int cuda_fail(cudaError_t e, const char* what);
     }                                            \
   } while (0)
 
+void count_launch();
+
 #define RGNN_LAUNCH_CHECK(what)                              \
   do {                                                       \
+    rgnn::count_launch();                                    \
     cudaError_t e__ = cudaGetLastError();                    \
     if (e__ != cudaSuccess) return rgnn::cuda_fail(e__, what); \
   } while (0)

@@ -32,7 +32,9 @@ def _aggregate(ix, x, z, use_beta, nbr_scale, post, dst_scale, addend, out, copy
         ptr32, nbr, eid = ix.out_ptr32, ix.out_dst32, ix.out_eid32
     else:
         ptr32, nbr, eid = ix.in_ptr32, ix.in_src32, ix.in_eid32
-    check(lib().rgnn_aggregate(dtype_code(x), ptr(x), row if ldx is None else ldx, ptr(z), int(use_beta), ptr(nbr_scale), post,
+    nbytes = x.element_size() * (ix.N * row * (2 + (addend is not None) + (copy_to is not None)) + (ix.E * 2 * f if z is not None else 0))
+    with _lib.timed("aggregate_bwd" if transposed else "aggregate_fwd", nbytes):
+      check(lib().rgnn_aggregate(dtype_code(x), ptr(x), row if ldx is None else ldx, ptr(z), int(use_beta), ptr(nbr_scale), post,
                                ptr(dst_scale), ptr(addend), row if ldadd is None else ldadd, ptr(out),
                                row if ldout is None else ldout, ptr(copy_to),
                                ptr(ptr32), ptr(nbr), ptr(eid), ptr(ix.noff32), ix.G, ix.max_nodes, ix.max_edges,
@@ -84,8 +86,9 @@ class AggregateFn(torch.autograd.Function):
             if z is not None and ctx.needs_input_grad[1]:
                 f, p = _row_shape(x)
                 dz = torch.empty_like(z)
-                check(lib().rgnn_film_edge_grad(dtype_code(x), ptr(x), f * p, ptr(dout), f * p, ptr(z), 0, ptr(ix.inv_in_deg),
-                                                ptr(ix.src32), ptr(ix.dst32), ptr(dz), ix.E, f, p, stream()), "rgnn_film_edge_grad")
+                with _lib.timed("film_edge_grad", x.element_size() * (2.0 * ix.E * f * p + 4.0 * ix.E * f)):
+                    check(lib().rgnn_film_edge_grad(dtype_code(x), ptr(x), f * p, ptr(dout), f * p, ptr(z), 0, ptr(ix.inv_in_deg),
+                                                    ptr(ix.src32), ptr(ix.dst32), ptr(dz), ix.E, f, p, stream()), "rgnn_film_edge_grad")
         return dx, dz, None, None, None, None
 
 
@@ -150,8 +153,10 @@ def copy_u_reduce(g, x, op="sum", nbr_scale=None, dst_scale=None):
     return AggregateFn.apply(x, None, g, post, nbr_scale, dst_scale)
 
 
-def _gemm(a, sa, b, sb, c, sc, m, n, k, batch=1, red=1, split=1, partial=None, epi=0, bias=None, aux=None, alpha=1.0, beta=0.0):
-    check(lib().rgnn_gemm(dtype_code(a), ptr(a), *sa, dtype_code(b), ptr(b), *sb, dtype_code(c), ptr(c), *sc,
+def _gemm(a, sa, b, sb, c, sc, m, n, k, batch=1, red=1, split=1, partial=None, epi=0, bias=None, aux=None, alpha=1.0, beta=0.0,
+          tag="gemm"):
+    with _lib.timed(tag, 2.0 * m * n * k * batch * red):
+      check(lib().rgnn_gemm(dtype_code(a), ptr(a), *sa, dtype_code(b), ptr(b), *sb, dtype_code(c), ptr(c), *sc,
                           m, n, k, batch, red, split, ptr(partial), epi, ptr(bias), ptr(aux), alpha, beta, stream()), "rgnn_gemm")
 
 
@@ -177,7 +182,7 @@ class EdgeMLPFn(torch.autograd.Function):
         with torch.cuda.device(pose.device):
             check(lib().rgnn_edge_mlp1_fwd(dtype_code(a1), ptr(pose), ptr(w1), ptr(b1), ptr(a1), e, hid, stream()), "rgnn_edge_mlp1_fwd")
             _gemm(a1, (0, 0, hid, 1), w2, (0, 0, 1, hid), z, (0, f2, 1), e, f2, hid,
-                  epi=_lib.EPI_BIAS_N | _lib.EPI_SIGMOID, bias=b2)
+                  epi=_lib.EPI_BIAS_N | _lib.EPI_SIGMOID, bias=b2, tag="mlp2_fwd")
         ctx.save_for_backward(pose, w2, a1, z)
         return z
 
@@ -200,11 +205,11 @@ def edge_mlp_param_grads(pose, w2, a1, dzp):
     dev = a1.device
     f32 = dict(dtype=torch.float32, device=dev)
     da1 = torch.empty_like(a1)
-    _gemm(dzp, (0, 0, f2, 1), w2, (0, 0, hid, 1), da1, (0, hid, 1), e, hid, f2, epi=_lib.EPI_RELU_MASK, aux=a1)
+    _gemm(dzp, (0, 0, f2, 1), w2, (0, 0, hid, 1), da1, (0, hid, 1), e, hid, f2, epi=_lib.EPI_RELU_MASK, aux=a1, tag="mlp2_dx")
     dw2 = torch.empty((f2, hid), **f32)
     split = _splits(((f2 + 63) // 64) * ((hid + 63) // 64), max(1, (e + 63) // 64))
     partial = torch.empty((split, f2, hid), **f32) if split > 1 else None
-    _gemm(dzp, (0, 0, 1, f2), a1, (0, 0, hid, 1), dw2, (0, hid, 1), f2, hid, e, split=split, partial=partial)
+    _gemm(dzp, (0, 0, 1, f2), a1, (0, 0, hid, 1), dw2, (0, hid, 1), f2, hid, e, split=split, partial=partial, tag="mlp2_dw")
     db2 = torch.empty((f2,), **f32)
     check(lib().rgnn_reduce_sum(dtype_code(dzp), ptr(dzp), e, f2, f2, 1, 1, 1, ptr(db2), stream()), "rgnn_reduce_sum")
     dw1, db1 = torch.empty((hid, 9), **f32), torch.empty((hid,), **f32)
@@ -237,8 +242,8 @@ class CompressFn(torch.autograd.Function):
                 sb, sc, bt, nn = (0, 0, 1, f), (0, 1, fo), 1, n
             else:         # one [Fo x P] product per node
                 sb, sc, bt, nn = (f * p, 0, p, 1), (fo * p, p, 1), n, p
-            _gemm(wc2, (0, 0, 2 * f, 1), h, sb, y, sc, fo, nn, f, batch=bt, epi=_lib.EPI_BIAS_M, bias=bcf)
-            _gemm(wc2[:, f:], (0, 0, 2 * f, 1), gh, sb, y, sc, fo, nn, f, batch=bt, epi=_lib.EPI_ADD_AUX, aux=y, beta=1.0)
+            _gemm(wc2, (0, 0, 2 * f, 1), h, sb, y, sc, fo, nn, f, batch=bt, epi=_lib.EPI_BIAS_M, bias=bcf, tag="compress_fwd")
+            _gemm(wc2[:, f:], (0, 0, 2 * f, 1), gh, sb, y, sc, fo, nn, f, batch=bt, epi=_lib.EPI_ADD_AUX, aux=y, beta=1.0, tag="compress_fwd")
         ctx.save_for_backward(h, gh, wc2)
         ctx.wshape = tuple(wc.shape)
         return y
@@ -260,10 +265,10 @@ class CompressFn(torch.autograd.Function):
                 sb, sc, bt, nn = (fo * p, 0, p, 1), (f * p, p, 1), n, p
             if ctx.needs_input_grad[0]:
                 dh = torch.empty_like(h)
-                _gemm(wc2, (0, 0, 1, 2 * f), dy, sb, dh, sc, f, nn, fo, batch=bt)
+                _gemm(wc2, (0, 0, 1, 2 * f), dy, sb, dh, sc, f, nn, fo, batch=bt, tag="compress_dx")
             if ctx.needs_input_grad[1]:
                 dgh = torch.empty_like(gh)
-                _gemm(wc2[:, f:], (0, 0, 1, 2 * f), dy, sb, dgh, sc, f, nn, fo, batch=bt)
+                _gemm(wc2[:, f:], (0, 0, 1, 2 * f), dy, sb, dgh, sc, f, nn, fo, batch=bt, tag="compress_dx")
             if ctx.needs_input_grad[2]:
                 dwc = torch.empty((fo, 2 * f), **f32)
                 split = _splits(((fo + 63) // 64) * ((f + 63) // 64), n)
@@ -271,7 +276,7 @@ class CompressFn(torch.autograd.Function):
                 for half, src in ((0, h), (1, gh)):
                     # dWc[o, k2] = sum_v sum_p dy[v,o,p] * src[v,k2,p]: K = P per node, reduced over the N nodes
                     _gemm(dy, (0, fo * p, p, 1), src, (0, f * p, 1, p), dwc[:, half * f:], (0, 2 * f, 1), fo, f, p,
-                          red=n, split=split, partial=partial)
+                          red=n, split=split, partial=partial, tag="compress_dw")
                 dwc = dwc.reshape(ctx.wshape)
             if ctx.needs_input_grad[3]:
                 dbc = torch.empty((fo,), **f32)

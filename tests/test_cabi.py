@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(R):
 
 
 def test_binding_covers_header(R):
-    bound = set(R._lib.SIGNATURES) | {"rgnn_last_error"}
+    bound = set(R._lib.SIGNATURES) | {"rgnn_last_error", "rgnn_launch_count"}
     assert bound == set(header_symbols())
 
 

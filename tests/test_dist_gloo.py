@@ -1,0 +1,77 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the multi-GPU path - graph sharding and the
+bucketed gradient all-reduce.  (Kernels are not involved; the N>1 GPU run is bench.py under torchrun.)"""
+import os
+import socket
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import robot_gnn_b200 as R
+    torch.manual_seed(0)                                   # identical parameters on every rank
+    blk = R.GNNBlock(types.SimpleNamespace(feature_dim=8, compress_gcn=True, multi_gcn=True))
+    sync = R.parallel.GradSync(blk)
+    assert len(sync.buckets) == 2 and sync.buckets[0][0][0].startswith(("gcn2", "conv2"))   # layer 2 reduces first
+    # rank-dependent synthetic gradients, produced through autograd so the hooks fire in backward order
+    gen = torch.Generator().manual_seed(100 + rank)
+    loss = sum((p * torch.randn(p.shape, generator=gen)).sum() for p in blk.parameters())
+    loss.backward()
+    local = {n: p.grad.clone().numpy() for n, p in blk.named_parameters()}
+    sync.finish()
+    out = {n: p.grad.clone().numpy() for n, p in blk.named_parameters()}
+    # second step must work too (state reset)
+    for p in blk.parameters():
+        p.grad = None
+    loss = sum((p * 2.0).sum() for p in blk.parameters())
+    loss.backward()
+    sync.finish()
+    ok2 = all(torch.allclose(p.grad, torch.full_like(p, 2.0)) for p in blk.parameters())
+    lo, hi = R.parallel.shard_range(11, rank, world)
+    q.put((rank, local, out, ok2, (lo, hi)))
+    dist.destroy_process_group()
+
+
+def test_grad_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, l0, o0, ok0, s0), (_, l1, o1, ok1, s1) = res
+    assert ok0 and ok1
+    for n in l0:
+        assert np.allclose(o0[n], (l0[n] + l1[n]) / 2, atol=1e-6) and np.array_equal(o0[n], o1[n]), n
+    assert s0 == (0, 6) and s1 == (6, 11)
+
+
+def test_shard_range_partitions():
+    import robot_gnn_b200 as R
+    for g, w in ((8, 8), (1000, 8), (7, 4), (3, 8)):
+        cuts = [R.parallel.shard_range(g, r, w) for r in range(w)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == g
+        assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
+        assert max(h - l for l, h in cuts) - min(h - l for l, h in cuts) <= 1

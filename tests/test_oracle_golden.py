@@ -128,3 +128,26 @@ def test_graphconv_gcn2_formula_vs_shim_modules():
         got = O.gcn2conv(x2, x0, sb["src"], sb["dst"], m.weight1, m.bias, layer=3, alpha=0.2, lambda_=0.5,
                          weight2=None if project else m.weight2)
         assert nerr(got, ref) < 1e-12
+
+
+@pytest.mark.parametrize("ci", range(len(load_cases("block_cases.npz"))))
+def test_ref_port_matches_golden(ci):
+    """oracle/ref_port.py (the CPU baseline bench.py times) reproduces the unmodified reference's outputs."""
+    from oracle import ref_port
+    c = load_cases("block_cases.npz")[ci]
+    seed, f, k, gN, comp, multi = [int(v) for v in c["cfg"]]
+    t = lambda a: torch.from_numpy(np.asarray(a))
+    blk = ref_port.RefBlock(f, bool(comp), bool(multi))
+    sd = {}
+    for j in range(2 if multi else 1):
+        pre = f"gcn{j + 1}.edge_encoder.layers."
+        sd.update({pre + "0.weight": t(c[f"l{j}_w1"]), pre + "0.bias": t(c[f"l{j}_b1"]), pre + "2.weight": t(c[f"l{j}_w2"]), pre + "2.bias": t(c[f"l{j}_b2"])})
+        if comp:
+            sd.update({f"conv{j + 1}.weight": t(c[f"l{j}_wc"]).reshape(f, 2 * f, 1, 1), f"conv{j + 1}.bias": t(c[f"l{j}_bc"])})
+    blk.load_state_dict(sd, strict=True)
+    g = ref_port.make_graph(c["src"], c["dst"], gN * k, t(c["pose"]))
+    h = t(c["h"]).clone().requires_grad_()
+    y = blk(g, h)
+    assert nerr(y, c["y"]) <= 1e-6
+    y.backward(t(c["dy"]))
+    assert nerr(h.grad, c["dh"]) <= 1e-6
