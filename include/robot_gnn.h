@@ -145,6 +145,32 @@ int rgnn_gemm(int a_dtype, const void* A, int64_t sAz, int64_t sAr, int64_t sAm,
               int64_t M, int64_t N, int64_t K, int64_t batch, int64_t red, int64_t split, float* partial,
               int epi, const float* bias, const void* aux, float alpha, float beta, void* stream);
 
+/* ---- A4/A8 (+A10): the same transforms on the tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM) -------
+ * Throughput path.  Shapes the tiles do not cover return RGNN_E_UNSUPPORTED and the caller uses rgnn_gemm. */
+
+/* fp32 master weights [rows, cols] -> bf16 copy and/or bf16 transpose [cols, rows] (either may be NULL) */
+int rgnn_tc_cast_weights(const float* w, int64_t rows, int64_t cols, void* out_bf16, void* out_t_bf16, void* stream);
+
+/* 1x1 convolution over NCHW robot feature maps with P = 64 pixels, concat-free (models.py:182-184 and its dX):
+ * out[v,m,:] = sum_{k<c0} W[m,k] x0[v,k,:] + sum_{k<c1} W[m,c0+k] x1[v,k,:] (+ bias[m]);  W bf16 [m0+m1, c0+c1];
+ * rows m < m0 land in out0 [nodes, m0, 64], rows >= m0 in out1 [nodes, m1, 64] (x1/out1 optional with c1/m1 = 0). */
+int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const void* x1, int64_t c1,
+                    void* out0, int64_t m0, void* out1, int64_t m1, const float* bias, int64_t nodes, void* stream);
+
+/* weight gradient of the above: dW[m,k] = sum_v sum_p dy[v,m,p] x[v,k,p], x = x0 | x1; dW fp32 (row stride ldw);
+ * partial fp32 [splits, M, c0+c1] scratch; the robots are split across CTAs and summed in a fixed order. */
+int rgnn_tc_conv1x1_wgrad(const void* dy, int64_t M, const void* x0, int64_t c0, const void* x1, int64_t c1,
+                          float* dW, int64_t ldw, float* partial, int64_t splits, int64_t nodes, void* stream);
+
+/* C[M,N] = epi(A[M,K] . B[N,K]^T), bf16 row-major operands; epi = bit-or of RGNN_EPI_BIAS_N | _SIGMOID | _RELU_MASK
+ * (nn.Linear(F,2F)+Sigmoid, models.py:149-150, and dA1 of its autograd). */
+int rgnn_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                    int64_t M, int64_t N, int64_t K, int epi, const float* bias, const void* aux, void* stream);
+
+/* C[M,N] fp32 = A^T . B with A bf16 [K,M], B bf16 [K,N] (dW2 = dZ^T . A1); split over K, partial fp32 [splits,M,N]. */
+int rgnn_tc_gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                    int64_t M, int64_t N, int64_t K, float* partial, int64_t splits, void* stream);
+
 /* dzpre = dz * z * (1 - z)  elementwise over n values (sigmoid backward, models.py:150) */
 int rgnn_sigmoid_grad(int dtype, const void* z, const void* dz, void* dzpre, int64_t n, void* stream);
 

@@ -1,0 +1,599 @@
+// A4/A8 (+A10): the weight transforms of the robot-graph layer as bf16 GEMMs on the 5th-gen tensor cores
+// (tcgen05.mma, fp32 accumulators in TMEM, operands staged by TMA into 128B-swizzled shared memory).
+//
+// Reference ops replaced (file:line under /root/reference):
+//   Conv2d(2F,F,1)(cat(h,g_h))  dgl/model/models.py:164,182-184  -> conv1x1  : Y_v = Wc . [h_v ; g_v] + b      (per robot v)
+//   its autograd                 (training.py:209)                -> conv1x1  : dX_v = Wc^T . dY_v   (two outputs: dh | dagg)
+//                                                                 -> wgrad    : dWc = sum_v dY_v . X_v^T  (split over robots)
+//   nn.Linear(F,2F)+Sigmoid      dgl/model/models.py:149-150      -> gemm_tn  : Z = sigmoid(A1 . W2^T + b2)
+//   its autograd                                                  -> gemm_tn  : dA1 = (dZ . W2) * [A1>0] ;  gemm_nn : dW2 = dZ^T . A1
+//
+// One persistent, warp-specialised kernel (1 CTA / SM, 256 threads):
+//   warp 0   TMA producer   (4-stage ring of {A 128x64, B BNx64} bf16 tiles, mbarrier full/empty)
+//   warp 1   MMA issuer     (one elected lane; 4 x tcgen05.mma 128xBNx16 per stage; tcgen05.commit frees the stage)
+//   warp 2   TMEM allocator (2 x BN fp32 columns = double-buffered accumulator, epilogue overlaps the next tile)
+//   warps 4-7 epilogue      (tcgen05.ld 32x32b.x32 -> bias / sigmoid / relu-mask -> bf16 or fp32 partial stores)
+// NCHW feature maps are consumed where they lie: a [64 ch x 64 px] slab of one robot is exactly one MN-major
+// SWIZZLE_128B operand block (row = channel, 128 B = the 64 contiguous pixels), so the concat of models.py:182 is
+// just "k-blocks 0..F/64 from h, the rest from g_h" (two tensor maps) and is never materialised.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace rgnn {
+namespace tc {
+
+constexpr int BM = 128, BK = 64, NSTAGE = 4;
+constexpr int LOAD_TN = 0, LOAD_CONV = 1, LOAD_WGRAD = 2, LOAD_NN = 3;
+constexpr int EPI_NCHW = 0, EPI_ROW = 1, EPI_PARTIAL = 2;
+
+struct TcParams {
+  int load_mode, epi_mode, epi_flags;
+  int tiles_m, tiles_n, splits;
+  int kblocks;          // k-blocks (of 64) in the full reduction
+  int kb_per_split;     // k-blocks per split (== kblocks when splits == 1)
+  int kb_b0;            // CONV: k-blocks taken from tensor map B0 (the rest from B1)
+  int n_b0;             // WGRAD: output columns [0, n_b0) come from B0 (then B1)
+  int rows_a;           // WGRAD: rows of A per robot (= channels of dY)
+  int rows_b0, rows_b1; // WGRAD: rows per robot of B0 / B1
+  int nodes;            // CONV: robots; output guard
+  int64_t M, N;         // logical output extent (guards)
+  void* out0; void* out1; int m_split;   // rows >= m_split go to out1 (row index - m_split)
+  int64_t ld0, ld1;     // NCHW: elements per robot in out0/out1; ROW/PARTIAL: ld0 = row stride
+  const float* bias; const void* aux;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// shared-memory matrix descriptor: SWIZZLE_128B, version 1 (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // version
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+          const __grid_constant__ CUtensorMap tmB1, const TcParams p) {
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;    // 256 or 512: power of two
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // carve: [tiles (1024-aligned)] [barriers]
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t tiles = smem_u32(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NSTAGE);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * NSTAGE), bar_tempty = smem_u32(bars + 2 * NSTAGE + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int work_total = p.tiles_m * p.tiles_n * p.splits;
+  const bool a_mn = p.load_mode == LOAD_NN;
+  const bool b_mn = p.load_mode == LOAD_CONV || p.load_mode == LOAD_NN;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
+        const int tm = w % p.tiles_m, tn = (w / p.tiles_m) % p.tiles_n, sp = w / (p.tiles_m * p.tiles_n);
+        const int kb0 = sp * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t fb = bar_full + 8 * stage;
+          const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          mbar_expect_tx(fb, STAGE_BYTES);
+          if (p.load_mode == LOAD_TN) {
+            tma_2d(sa, &tmA, fb, kb * BK, tm * BM);
+            tma_2d(sb, &tmB0, fb, kb * BK, tn * BN);
+          } else if (p.load_mode == LOAD_CONV) {
+            tma_2d(sa, &tmA, fb, kb * BK, tm * BM);
+            if (kb < p.kb_b0) tma_3d(sb, &tmB0, fb, 0, kb * BK, tn * (BN / 64));
+            else tma_3d(sb, &tmB1, fb, 0, (kb - p.kb_b0) * BK, tn * (BN / 64));
+          } else if (p.load_mode == LOAD_WGRAD) {   // k-block == robot kb; both operands K-major (pixels contiguous)
+            tma_2d(sa, &tmA, fb, 0, kb * p.rows_a + tm * BM);
+            const int n0 = tn * BN;
+            if (n0 < p.n_b0) tma_2d(sb, &tmB0, fb, 0, kb * p.rows_b0 + n0);
+            else tma_2d(sb, &tmB1, fb, 0, kb * p.rows_b1 + (n0 - p.n_b0));
+          } else {                                   // LOAD_NN: both operands MN-major, 64-wide boxes
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_2d(sa + j * (BK * 128), &tmA, fb, tm * BM + j * 64, kb * BK);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_2d(sb + j * (BK * 128), &tmB0, fb, tn * BN + j * 64, kb * BK);
+          }
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    // instruction descriptor: D fp32, A/B bf16, majors, N>>3, M>>4 (cute::UMMA::InstrDescriptor)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t a_lbo = a_mn ? BK * 128 : 0, b_lbo = b_mn ? BK * 128 : 0;
+    const uint32_t a_kstep = a_mn ? 2048 : 32, b_kstep = b_mn ? 2048 : 32;   // bytes per 16 k
+    int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+    for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
+      const int sp = w / (p.tiles_m * p.tiles_n);
+      const int kb0 = sp * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+      mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + as * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_desc(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = make_desc(sb + k * b_kstep, b_lbo, 1024);
+            umma(tacc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * stage);                 // stage reusable once these MMAs retire
+          if (kb == kb1 - 1) umma_commit(bar_tfull + 8 * as); // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+      if (kb1 <= kb0 && elect_one()) umma_commit(bar_tfull + 8 * as);   // empty split: hand over (epilogue writes zeros)
+      __syncwarp();
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const int ew = warp - 4;                    // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+    const int row = ew * 32 + lane;             // row inside the 128-row tile
+    int as = 0; uint32_t aphase = 0;
+    for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
+      const int tm = w % p.tiles_m, tn = (w / p.tiles_m) % p.tiles_n, sp = w / (p.tiles_m * p.tiles_n);
+      const int kb0 = sp * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+      const bool empty = kb1 <= kb0;
+      mbar_wait(bar_tfull + 8 * as, aphase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(ew * 32) << 16);
+      const int64_t m = (int64_t)tm * BM + row;
+      const float bias_m = (p.bias && (p.epi_flags & RGNN_EPI_BIAS_M) && m < p.M) ? p.bias[m] : 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tacc + c * 32, r);
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = empty ? 0.f : __uint_as_float(r[i]);
+        if (p.epi_mode == EPI_NCHW) {
+          // row m = output channel, columns = (robot, pixel); 32 columns = half a robot's 8x8 map
+          const int node = tn * (BN / 64) + (c >> 1);
+          if (node < p.nodes && m < p.M) {
+            __nv_bfloat16* o;
+            if (m < p.m_split) o = static_cast<__nv_bfloat16*>(p.out0) + (int64_t)node * p.ld0 + m * 64 + (c & 1) * 32;
+            else o = static_cast<__nv_bfloat16*>(p.out1) + (int64_t)node * p.ld1 + (m - p.m_split) * 64 + (c & 1) * 32;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              u.x = pack_bf16(v[8 * q + 0] + bias_m, v[8 * q + 1] + bias_m);
+              u.y = pack_bf16(v[8 * q + 2] + bias_m, v[8 * q + 3] + bias_m);
+              u.z = pack_bf16(v[8 * q + 4] + bias_m, v[8 * q + 5] + bias_m);
+              u.w = pack_bf16(v[8 * q + 6] + bias_m, v[8 * q + 7] + bias_m);
+              reinterpret_cast<uint4*>(o)[q] = u;
+            }
+          }
+        } else if (p.epi_mode == EPI_ROW) {
+          const int64_t n0 = (int64_t)tn * BN + c * 32;
+          if (m < p.M && n0 < p.N) {
+            if (p.epi_flags & RGNN_EPI_BIAS_N) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += p.bias[n0 + i];
+            }
+            if (p.epi_flags & RGNN_EPI_SIGMOID) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 1.0f / (1.0f + __expf(-v[i]));
+            }
+            if (p.epi_flags & RGNN_EPI_RELU_MASK) {
+              const uint4* ax = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.aux) + m * p.ld0 + n0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = ax[q];
+                const uint32_t ws[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                  if (!((ws[j] & 0x7fffu) != 0 && !(ws[j] & 0x8000u))) v[8 * q + 2 * j] = 0.f;
+                  if (!(((ws[j] >> 16) & 0x7fffu) != 0 && !((ws[j] >> 16) & 0x8000u))) v[8 * q + 2 * j + 1] = 0.f;
+                }
+              }
+            }
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out0) + m * p.ld0 + n0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+              u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+              reinterpret_cast<uint4*>(o)[q] = u;
+            }
+          }
+        } else {   // EPI_PARTIAL: fp32 partial tile of split sp
+          const int64_t n0 = (int64_t)tn * BN + c * 32;
+          if (m < p.M && n0 < p.N) {
+            float* o = static_cast<float*>(p.out0) + ((int64_t)sp * p.M + m) * p.ld0 + n0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  // ================================ teardown ================================
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// out[i] = alpha * sum_s partial[s][i]   (fixed order: deterministic)
+__global__ void __launch_bounds__(256) k_sum_partials(const float* __restrict__ part, int splits, int64_t n, float* __restrict__ out,
+                                                      int64_t ld_out, int64_t cols, float alpha) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += part[(int64_t)s * n + i];
+    out[(i / cols) * ld_out + (i % cols)] = alpha * acc;
+  }
+}
+
+// fp32 [R, C] -> bf16 [R, C] and (optionally) its transpose [C, R]: per-step cast of the fp32 master weights
+__global__ void __launch_bounds__(256) k_cast_weights(const float* __restrict__ w, int R, int C, __nv_bfloat16* __restrict__ o,
+                                                      __nv_bfloat16* __restrict__ ot) {
+  __shared__ float t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    const float v = (r < R && c < C) ? w[(int64_t)r * C + c] : 0.f;
+    t[j][tx] = v;
+    if (o && r < R && c < C) o[(int64_t)r * C + c] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  if (ot) {
+    for (int j = ty; j < 32; j += 8) {
+      const int c = c0 + j, r = r0 + tx;
+      if (r < R && c < C) ot[(int64_t)c * R + r] = __float2bfloat16_rn(t[tx][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor map, 128B swizzle.  dims/strides innermost first; strides in BYTES for dims 1..rank-1.
+static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  RGNN_REQUIRE(enc, RGNN_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t d[5]; cuuint64_t s[5]; cuuint32_t b[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RGNN_REQUIRE(r == CUDA_SUCCESS, RGNN_E_ARG, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu)", (int)r, rank,
+               (unsigned long long)dims[0], (unsigned long long)dims[1]);
+  return 0;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const TcParams& p, cudaStream_t st) {
+  constexpr size_t smem = 1024 + (size_t)NSTAGE * (BM * BK * 2 + BN * BK * 2) + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_gemm_tc)");
+    attr_done = true;
+  }
+  const int work = p.tiles_m * p.tiles_n * p.splits;
+  int grid = work < kNumSMs ? work : kNumSMs;
+  if (grid < 1) return 0;
+  k_gemm_tc<BN><<<grid, 256, smem, st>>>(a, b0, b1, p);
+  RGNN_LAUNCH_CHECK("k_gemm_tc");
+  return 0;
+}
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace tc
+}  // namespace rgnn
+
+using namespace rgnn;
+using namespace rgnn::tc;
+
+extern "C" int rgnn_tc_cast_weights(const float* w, int64_t rows, int64_t cols, void* out_bf16, void* out_t_bf16, void* stream) {
+  RGNN_REQUIRE(w && (out_bf16 || out_t_bf16) && rows > 0 && cols > 0 && rows < (1 << 30) && cols < (1 << 30), RGNN_E_ARG,
+               "rgnn_tc_cast_weights: bad arguments");
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  k_cast_weights<<<grid, 256, 0, as_stream(stream)>>>(w, (int)rows, (int)cols, static_cast<__nv_bfloat16*>(out_bf16),
+                                                      static_cast<__nv_bfloat16*>(out_t_bf16));
+  RGNN_LAUNCH_CHECK("k_cast_weights");
+  return 0;
+}
+
+// out[v, m, p] = sum_{k<c0} W[m,k] x0[v,k,p] + sum_{k<c1} W[m,c0+k] x1[v,k,p] (+ bias[m]);  rows m < m0 -> out0 [nodes, m0, 64],
+// rows >= m0 -> out1 [nodes, m1, 64].  All bf16, P = 64 pixels.
+extern "C" int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const void* x1, int64_t c1,
+                               void* out0, int64_t m0, void* out1, int64_t m1, const float* bias, int64_t nodes, void* stream) {
+  RGNN_REQUIRE(W && x0 && out0 && c0 > 0 && m0 > 0 && nodes >= 0 && c1 >= 0 && m1 >= 0, RGNN_E_ARG, "rgnn_tc_conv1x1: bad arguments");
+  RGNN_REQUIRE((c1 == 0 || x1) && (m1 == 0 || out1), RGNN_E_ARG, "rgnn_tc_conv1x1: missing second operand/output");
+  RGNN_REQUIRE(c0 % 64 == 0 && c1 % 64 == 0 && m0 % 128 == 0 && m1 % 128 == 0, RGNN_E_UNSUPPORTED,
+               "rgnn_tc_conv1x1: channels must be multiples of 64 (inputs) / 128 (outputs)");
+  RGNN_REQUIRE(al16(W) && al16(x0) && al16(out0) && (!x1 || al16(x1)) && (!out1 || al16(out1)), RGNN_E_ALIGN, "rgnn_tc_conv1x1: 16-byte alignment");
+  RGNN_REQUIRE(nodes < (1ll << 30), RGNN_E_RANGE, "rgnn_tc_conv1x1: too many robots");
+  if (nodes == 0) return 0;
+  const int64_t K = c0 + c1, M = m0 + m1;
+  constexpr int BN = 256;
+  CUtensorMap ta, tb0, tb1;
+  {
+    const uint64_t d[2] = {(uint64_t)K, (uint64_t)M}, s[1] = {(uint64_t)K * 2};
+    const uint32_t b[2] = {64, 128};
+    int rc = make_map(&ta, W, 2, d, s, b); if (rc) return rc;
+  }
+  {
+    const uint64_t d[3] = {64, (uint64_t)c0, (uint64_t)nodes}, s[2] = {128, (uint64_t)c0 * 128};
+    const uint32_t b[3] = {64, 64, BN / 64};
+    int rc = make_map(&tb0, x0, 3, d, s, b); if (rc) return rc;
+  }
+  if (c1 > 0) {
+    const uint64_t d[3] = {64, (uint64_t)c1, (uint64_t)nodes}, s[2] = {128, (uint64_t)c1 * 128};
+    const uint32_t b[3] = {64, 64, BN / 64};
+    int rc = make_map(&tb1, x1, 3, d, s, b); if (rc) return rc;
+  } else tb1 = tb0;
+  TcParams p = {};
+  p.load_mode = LOAD_CONV; p.epi_mode = EPI_NCHW; p.epi_flags = bias ? RGNN_EPI_BIAS_M : 0;
+  p.tiles_m = (int)(M / 128); p.tiles_n = (int)((nodes + BN / 64 - 1) / (BN / 64)); p.splits = 1;
+  p.kblocks = (int)(K / 64); p.kb_per_split = p.kblocks; p.kb_b0 = (int)(c0 / 64);
+  p.nodes = (int)nodes; p.M = M; p.N = nodes * 64;
+  p.out0 = out0; p.out1 = out1; p.m_split = (int)m0; p.ld0 = m0 * 64; p.ld1 = m1 * 64; p.bias = bias;
+  RGNN_REQUIRE((int64_t)p.tiles_m * p.tiles_n < (1ll << 31), RGNN_E_RANGE, "rgnn_tc_conv1x1: too many tiles");
+  return launch<BN>(ta, tb0, tb1, p, as_stream(stream));
+}
+
+// dW[m, k] = sum_v sum_p dy[v,m,p] * x[v,k,p], x = x0 (k < c0) | x1;  dW fp32 [M, c0+c1] (row stride ldw), partial fp32 [splits, M, c0+c1].
+extern "C" int rgnn_tc_conv1x1_wgrad(const void* dy, int64_t M, const void* x0, int64_t c0, const void* x1, int64_t c1,
+                                     float* dW, int64_t ldw, float* partial, int64_t splits, int64_t nodes, void* stream) {
+  RGNN_REQUIRE(dy && x0 && dW && partial && M > 0 && c0 > 0 && c1 >= 0 && nodes >= 0 && splits >= 1, RGNN_E_ARG, "rgnn_tc_conv1x1_wgrad: bad arguments");
+  RGNN_REQUIRE(c1 == 0 || x1, RGNN_E_ARG, "rgnn_tc_conv1x1_wgrad: missing x1");
+  constexpr int BN = 256;
+  RGNN_REQUIRE(M % 128 == 0 && c0 % BN == 0 && c1 % BN == 0, RGNN_E_UNSUPPORTED, "rgnn_tc_conv1x1_wgrad: channel counts must be multiples of 128 / 256");
+  RGNN_REQUIRE(al16(dy) && al16(x0) && (!x1 || al16(x1)) && al16(partial), RGNN_E_ALIGN, "rgnn_tc_conv1x1_wgrad: 16-byte alignment");
+  RGNN_REQUIRE(nodes * M < (1ll << 31) && nodes * (c0 > c1 ? c0 : c1) < (1ll << 31), RGNN_E_RANGE, "rgnn_tc_conv1x1_wgrad: too many rows for a tensor map coordinate");
+  const int64_t Nn = c0 + c1;
+  cudaStream_t st = as_stream(stream);
+  if (nodes == 0) {
+    cudaError_t e = cudaMemset2DAsync(dW, ldw * 4, 0, Nn * 4, M, st);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "memset dW");
+  }
+  CUtensorMap ta, tb0, tb1;
+  {
+    const uint64_t d[2] = {64, (uint64_t)(nodes * M)}, s[1] = {128};
+    const uint32_t b[2] = {64, 128};
+    int rc = make_map(&ta, dy, 2, d, s, b); if (rc) return rc;
+  }
+  {
+    const uint64_t d[2] = {64, (uint64_t)(nodes * c0)}, s[1] = {128};
+    const uint32_t b[2] = {64, BN};
+    int rc = make_map(&tb0, x0, 2, d, s, b); if (rc) return rc;
+  }
+  if (c1 > 0) {
+    const uint64_t d[2] = {64, (uint64_t)(nodes * c1)}, s[1] = {128};
+    const uint32_t b[2] = {64, BN};
+    int rc = make_map(&tb1, x1, 2, d, s, b); if (rc) return rc;
+  } else tb1 = tb0;
+  if (splits > nodes) splits = nodes;
+  TcParams p = {};
+  p.load_mode = LOAD_WGRAD; p.epi_mode = EPI_PARTIAL;
+  p.tiles_m = (int)(M / 128); p.tiles_n = (int)(Nn / BN); p.splits = (int)splits;
+  p.kblocks = (int)nodes; p.kb_per_split = (int)((nodes + splits - 1) / splits);
+  splits = (nodes + p.kb_per_split - 1) / p.kb_per_split;   // no empty split
+  p.splits = (int)splits;
+  p.n_b0 = (int)c0; p.rows_a = (int)M; p.rows_b0 = (int)c0; p.rows_b1 = (int)c1;
+  p.M = M; p.N = Nn; p.out0 = partial; p.ld0 = Nn;
+  int rc = launch<BN>(ta, tb0, tb1, p, st);
+  if (rc) return rc;
+  const int64_t n = M * Nn;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  k_sum_partials<<<(unsigned)blocks, 256, 0, st>>>(partial, (int)splits, n, dW, ldw, Nn, 1.0f);
+  RGNN_LAUNCH_CHECK("k_sum_partials");
+  return 0;
+}
+
+// C[M,N] = epi(A[M,K] . B[N,K]^T): A, B bf16 K-major (row strides lda, ldb elements); C bf16 row-major (ldc); bias fp32 [N];
+// aux bf16 [M, ldc] for RGNN_EPI_RELU_MASK.  epi: bit-or of RGNN_EPI_BIAS_N | RGNN_EPI_SIGMOID | RGNN_EPI_RELU_MASK.
+extern "C" int rgnn_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                               int64_t M, int64_t N, int64_t K, int epi, const float* bias, const void* aux, void* stream) {
+  RGNN_REQUIRE(A && B && C && M >= 0 && N > 0 && K > 0, RGNN_E_ARG, "rgnn_tc_gemm_tn: bad arguments");
+  RGNN_REQUIRE((epi & ~(RGNN_EPI_BIAS_N | RGNN_EPI_SIGMOID | RGNN_EPI_RELU_MASK)) == 0, RGNN_E_UNSUPPORTED, "rgnn_tc_gemm_tn: unsupported epilogue");
+  RGNN_REQUIRE(!(epi & RGNN_EPI_BIAS_N) || bias, RGNN_E_ARG, "rgnn_tc_gemm_tn: bias missing");
+  RGNN_REQUIRE(!(epi & RGNN_EPI_RELU_MASK) || aux, RGNN_E_ARG, "rgnn_tc_gemm_tn: aux missing");
+  RGNN_REQUIRE(K % 64 == 0 && N % 128 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0, RGNN_E_UNSUPPORTED,
+               "rgnn_tc_gemm_tn: K %% 64, N %% 128 and 16-byte row strides required");
+  RGNN_REQUIRE(al16(A) && al16(B) && al16(C) && (!aux || al16(aux)), RGNN_E_ALIGN, "rgnn_tc_gemm_tn: 16-byte alignment");
+  RGNN_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), RGNN_E_RANGE, "rgnn_tc_gemm_tn: extent too large");
+  if (M == 0) return 0;
+  const bool wide = N % 256 == 0;
+  const int BN = wide ? 256 : 128;
+  CUtensorMap ta, tb;
+  {
+    const uint64_t d[2] = {(uint64_t)K, (uint64_t)M}, s[1] = {(uint64_t)lda * 2};
+    const uint32_t b[2] = {64, 128};
+    int rc = make_map(&ta, A, 2, d, s, b); if (rc) return rc;
+  }
+  {
+    const uint64_t d[2] = {(uint64_t)K, (uint64_t)N}, s[1] = {(uint64_t)ldb * 2};
+    const uint32_t b[2] = {64, (uint32_t)BN};
+    int rc = make_map(&tb, B, 2, d, s, b); if (rc) return rc;
+  }
+  TcParams p = {};
+  p.load_mode = LOAD_TN; p.epi_mode = EPI_ROW; p.epi_flags = epi;
+  p.tiles_m = (int)((M + 127) / 128); p.tiles_n = (int)(N / BN); p.splits = 1;
+  p.kblocks = (int)(K / 64); p.kb_per_split = p.kblocks;
+  p.M = M; p.N = N; p.out0 = C; p.ld0 = ldc; p.bias = bias; p.aux = aux;
+  return wide ? launch<256>(ta, tb, tb, p, as_stream(stream)) : launch<128>(ta, tb, tb, p, as_stream(stream));
+}
+
+// C[M,N] fp32 = A^T . B with A bf16 [K, M] (row stride lda), B bf16 [K, N] (row stride ldb): both operands MN-major.
+// Split over K; partial fp32 [splits, M, N].  (dW2 = dZ^T . A1 of the edge encoder.)
+extern "C" int rgnn_tc_gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                               int64_t M, int64_t N, int64_t K, float* partial, int64_t splits, void* stream) {
+  RGNN_REQUIRE(A && B && C && partial && M > 0 && N > 0 && K >= 0 && splits >= 1, RGNN_E_ARG, "rgnn_tc_gemm_nn: bad arguments");
+  RGNN_REQUIRE(M % 128 == 0 && N % 128 == 0 && lda % 8 == 0 && ldb % 8 == 0, RGNN_E_UNSUPPORTED, "rgnn_tc_gemm_nn: M, N %% 128 and 16-byte row strides required");
+  RGNN_REQUIRE(al16(A) && al16(B) && al16(partial), RGNN_E_ALIGN, "rgnn_tc_gemm_nn: 16-byte alignment");
+  RGNN_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), RGNN_E_RANGE, "rgnn_tc_gemm_nn: extent too large");
+  cudaStream_t st = as_stream(stream);
+  if (K == 0) {
+    cudaError_t e = cudaMemset2DAsync(C, ldc * 4, 0, N * 4, M, st);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "memset C");
+  }
+  const bool wide = N % 256 == 0;
+  const int BN = wide ? 256 : 128;
+  CUtensorMap ta, tb;
+  {
+    const uint64_t d[2] = {(uint64_t)M, (uint64_t)K}, s[1] = {(uint64_t)lda * 2};
+    const uint32_t b[2] = {64, 64};
+    int rc = make_map(&ta, A, 2, d, s, b); if (rc) return rc;
+  }
+  {
+    const uint64_t d[2] = {(uint64_t)N, (uint64_t)K}, s[1] = {(uint64_t)ldb * 2};
+    const uint32_t b[2] = {64, 64};
+    int rc = make_map(&tb, B, 2, d, s, b); if (rc) return rc;
+  }
+  const int64_t kblocks = (K + 63) / 64;
+  if (splits > kblocks) splits = kblocks;
+  TcParams p = {};
+  p.load_mode = LOAD_NN; p.epi_mode = EPI_PARTIAL;
+  p.tiles_m = (int)(M / 128); p.tiles_n = (int)(N / BN); p.splits = (int)splits;
+  p.kblocks = (int)kblocks; p.kb_per_split = (int)((kblocks + splits - 1) / splits);
+  splits = (kblocks + p.kb_per_split - 1) / p.kb_per_split;   // no empty split
+  p.splits = (int)splits;
+  p.M = M; p.N = N; p.out0 = partial; p.ld0 = N;
+  int rc = wide ? launch<256>(ta, tb, tb, p, st) : launch<128>(ta, tb, tb, p, st);
+  if (rc) return rc;
+  const int64_t n = M * N;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  k_sum_partials<<<(unsigned)blocks, 256, 0, st>>>(partial, (int)splits, n, C, ldc, N, 1.0f);
+  RGNN_LAUNCH_CHECK("k_sum_partials");
+  return 0;
+}

@@ -160,6 +160,19 @@ def _gemm(a, sa, b, sb, c, sc, m, n, k, batch=1, red=1, split=1, partial=None, e
                           m, n, k, batch, red, split, ptr(partial), epi, ptr(bias), ptr(aux), alpha, beta, stream()), "rgnn_gemm")
 
 
+def _cast_w(w, transpose=False, both=False):
+    """fp32 master weight [R, C] -> bf16 [R, C] and/or its transpose [C, R] (one small kernel per step)."""
+    r, c = w.shape
+    o = torch.empty((r, c), dtype=torch.bfloat16, device=w.device) if (both or not transpose) else None
+    ot = torch.empty((c, r), dtype=torch.bfloat16, device=w.device) if (both or transpose) else None
+    check(lib().rgnn_tc_cast_weights(ptr(w), r, c, ptr(o), ptr(ot), stream()), "rgnn_tc_cast_weights")
+    return (o, ot) if both else (ot if transpose else o)
+
+
+def _tc_splits(tiles, items):
+    return max(1, min(items, 148 // max(1, tiles)))
+
+
 def _splits(tiles, work_items):
     """Enough split-K slices to fill 148 SMs about twice, at most one per work item."""
     s = max(1, (2 * 148 + tiles - 1) // tiles)
@@ -181,8 +194,14 @@ class EdgeMLPFn(torch.autograd.Function):
         z = torch.empty((e, f2), dtype=out_dtype, device=pose.device)
         with torch.cuda.device(pose.device):
             check(lib().rgnn_edge_mlp1_fwd(dtype_code(a1), ptr(pose), ptr(w1), ptr(b1), ptr(a1), e, hid, stream()), "rgnn_edge_mlp1_fwd")
-            _gemm(a1, (0, 0, hid, 1), w2, (0, 0, 1, hid), z, (0, f2, 1), e, f2, hid,
-                  epi=_lib.EPI_BIAS_N | _lib.EPI_SIGMOID, bias=b2, tag="mlp2_fwd")
+            if _lib.USE_TC and out_dtype == torch.bfloat16 and hid % 64 == 0 and f2 % 128 == 0:
+                w2b = _cast_w(w2)
+                with _lib.timed("mlp2_fwd", 2.0 * e * f2 * hid):
+                    check(lib().rgnn_tc_gemm_tn(ptr(a1), hid, ptr(w2b), hid, ptr(z), f2, e, f2, hid,
+                                                _lib.EPI_BIAS_N | _lib.EPI_SIGMOID, ptr(b2), None, stream()), "rgnn_tc_gemm_tn")
+            else:
+                _gemm(a1, (0, 0, hid, 1), w2, (0, 0, 1, hid), z, (0, f2, 1), e, f2, hid,
+                      epi=_lib.EPI_BIAS_N | _lib.EPI_SIGMOID, bias=b2, tag="mlp2_fwd")
         ctx.save_for_backward(pose, w2, a1, z)
         return z
 
@@ -205,11 +224,22 @@ def edge_mlp_param_grads(pose, w2, a1, dzp):
     dev = a1.device
     f32 = dict(dtype=torch.float32, device=dev)
     da1 = torch.empty_like(a1)
-    _gemm(dzp, (0, 0, f2, 1), w2, (0, 0, hid, 1), da1, (0, hid, 1), e, hid, f2, epi=_lib.EPI_RELU_MASK, aux=a1, tag="mlp2_dx")
     dw2 = torch.empty((f2, hid), **f32)
-    split = _splits(((f2 + 63) // 64) * ((hid + 63) // 64), max(1, (e + 63) // 64))
-    partial = torch.empty((split, f2, hid), **f32) if split > 1 else None
-    _gemm(dzp, (0, 0, 1, f2), a1, (0, 0, hid, 1), dw2, (0, hid, 1), f2, hid, e, split=split, partial=partial, tag="mlp2_dw")
+    if _lib.USE_TC and a1.dtype == torch.bfloat16 and hid % 128 == 0 and f2 % 128 == 0 and e > 0:
+        w2t = _cast_w(w2, transpose=True)                       # [hid, f2], K-major for dA1 = dZ . W2
+        with _lib.timed("mlp2_dx", 2.0 * e * f2 * hid):
+            check(lib().rgnn_tc_gemm_tn(ptr(dzp), f2, ptr(w2t), f2, ptr(da1), hid, e, hid, f2, _lib.EPI_RELU_MASK, None, ptr(a1),
+                                        stream()), "rgnn_tc_gemm_tn")
+        split = _tc_splits((f2 // 128) * (hid // (256 if hid % 256 == 0 else 128)), (e + 63) // 64)
+        partial = torch.empty((split, f2, hid), **f32)
+        with _lib.timed("mlp2_dw", 2.0 * e * f2 * hid):
+            check(lib().rgnn_tc_gemm_nn(ptr(dzp), f2, ptr(a1), hid, ptr(dw2), hid, f2, hid, e, ptr(partial), split, stream()),
+                  "rgnn_tc_gemm_nn")
+    else:
+        _gemm(dzp, (0, 0, f2, 1), w2, (0, 0, hid, 1), da1, (0, hid, 1), e, hid, f2, epi=_lib.EPI_RELU_MASK, aux=a1, tag="mlp2_dx")
+        split = _splits(((f2 + 63) // 64) * ((hid + 63) // 64), max(1, (e + 63) // 64))
+        partial = torch.empty((split, f2, hid), **f32) if split > 1 else None
+        _gemm(dzp, (0, 0, 1, f2), a1, (0, 0, hid, 1), dw2, (0, hid, 1), f2, hid, e, split=split, partial=partial, tag="mlp2_dw")
     db2 = torch.empty((f2,), **f32)
     check(lib().rgnn_reduce_sum(dtype_code(dzp), ptr(dzp), e, f2, f2, 1, 1, 1, ptr(db2), stream()), "rgnn_reduce_sum")
     dw1, db1 = torch.empty((hid, 9), **f32), torch.empty((hid,), **f32)
@@ -237,6 +267,15 @@ class CompressFn(torch.autograd.Function):
             raise ValueError("compress expects h, g_h [N,F,...] and weight [Fo, 2F(,1,1)]")
         bcf = bc.detach().float().contiguous()
         y = torch.empty((n, fo) + tuple(h.shape[2:]), dtype=h.dtype, device=h.device)
+        ctx.tc = bool(_lib.USE_TC and h.dtype == torch.bfloat16 and p == 64 and f % 64 == 0 and fo % 128 == 0 and n > 0)
+        if ctx.tc:
+            with torch.cuda.device(h.device):
+                wb = _cast_w(wc2)
+                with _lib.timed("compress_fwd", 2.0 * fo * 2 * f * n * p):
+                    check(lib().rgnn_tc_conv1x1(ptr(wb), ptr(h), f, ptr(gh), f, ptr(y), fo, None, 0, ptr(bcf), n, stream()), "rgnn_tc_conv1x1")
+            ctx.save_for_backward(h, gh, wc2)
+            ctx.wshape = tuple(wc.shape)
+            return y
         with torch.cuda.device(h.device):
             if p == 1:    # [N,F,1,1] maps: the nodes form the N dimension of one product
                 sb, sc, bt, nn = (0, 0, 1, f), (0, 1, fo), 1, n
@@ -258,18 +297,33 @@ class CompressFn(torch.autograd.Function):
         dev = dy.device
         f32 = dict(dtype=torch.float32, device=dev)
         dh = dgh = dwc = dbc = None
+        tc_dx = ctx.tc and f % 128 == 0 and fo % 64 == 0
+        tc_dw = ctx.tc and f % 256 == 0 and fo % 128 == 0
         with torch.cuda.device(dev):
+            if tc_dx and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+                wt = _cast_w(wc2, transpose=True)               # [2F, Fo] K-major: dX_v = Wc^T . dY_v
+                dh, dgh = torch.empty_like(h), torch.empty_like(gh)
+                with _lib.timed("compress_dx", 2.0 * fo * 2 * f * n * p):
+                    check(lib().rgnn_tc_conv1x1(ptr(wt), ptr(dy), fo, None, 0, ptr(dh), f, ptr(dgh), f, None, n, stream()), "rgnn_tc_conv1x1")
+            if tc_dw and ctx.needs_input_grad[2]:
+                dwc = torch.empty((fo, 2 * f), **f32)
+                split = _tc_splits((fo // 128) * (2 * f // 256), n)
+                partial = torch.empty((split, fo, 2 * f), **f32)
+                with _lib.timed("compress_dw", 2.0 * fo * 2 * f * n * p):
+                    check(lib().rgnn_tc_conv1x1_wgrad(ptr(dy), fo, ptr(h), f, ptr(gh), f, ptr(dwc), 2 * f, ptr(partial), split, n, stream()),
+                          "rgnn_tc_conv1x1_wgrad")
+                dwc = dwc.reshape(ctx.wshape)
             if p == 1:
                 sb, sc, bt, nn = (0, 0, 1, fo), (0, 1, f), 1, n
             else:
                 sb, sc, bt, nn = (fo * p, 0, p, 1), (f * p, p, 1), n, p
-            if ctx.needs_input_grad[0]:
+            if ctx.needs_input_grad[0] and dh is None:
                 dh = torch.empty_like(h)
                 _gemm(wc2, (0, 0, 1, 2 * f), dy, sb, dh, sc, f, nn, fo, batch=bt, tag="compress_dx")
-            if ctx.needs_input_grad[1]:
+            if ctx.needs_input_grad[1] and dgh is None:
                 dgh = torch.empty_like(gh)
                 _gemm(wc2[:, f:], (0, 0, 1, 2 * f), dy, sb, dgh, sc, f, nn, fo, batch=bt, tag="compress_dx")
-            if ctx.needs_input_grad[2]:
+            if ctx.needs_input_grad[2] and dwc is None:
                 dwc = torch.empty((fo, 2 * f), **f32)
                 split = _splits(((fo + 63) // 64) * ((f + 63) // 64), n)
                 partial = torch.empty((split, fo, f), **f32) if split > 1 else None

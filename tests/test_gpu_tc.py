@@ -1,0 +1,116 @@
+"""GPU: the tcgen05 (tensor-core) transforms, called straight through the C ABI, against an fp32 PyTorch reference of
+the same bf16 operands, and against the CUDA-core rgnn_gemm path on whole layers.  bf16 tolerance 2e-2 (north_star);
+the unit products here are far tighter because both sides see identical bf16 inputs (only accumulation order differs)."""
+import types
+
+import pytest
+import torch
+
+from conftest import nerr
+
+pytestmark = pytest.mark.gpu
+
+
+def bf(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (300, 256, 128), (1000, 1024, 512), (77, 384, 192)])
+@pytest.mark.parametrize("epi", ["plain", "bias_sigmoid", "relu_mask"])
+def test_tc_gemm_tn(R, m, n, k, epi):
+    L = R._lib
+    a, b = bf(m, k, seed=1), bf(n, k, seed=2, scale=0.1)
+    c = torch.zeros((m, n), dtype=torch.bfloat16, device="cuda")
+    bias = torch.randn(n, device="cuda")
+    aux = bf(m, n, seed=3)
+    ref = a.float() @ b.float().t()
+    if epi == "plain":
+        flags, pb, pa = 0, None, None
+    elif epi == "bias_sigmoid":
+        flags, pb, pa = L.EPI_BIAS_N | L.EPI_SIGMOID, bias, None
+        ref = torch.sigmoid(ref + bias)
+    else:
+        flags, pb, pa = L.EPI_RELU_MASK, None, aux
+        ref = ref * (aux.float() > 0)
+    L.check(L.lib().rgnn_tc_gemm_tn(L.ptr(a), k, L.ptr(b), k, L.ptr(c), n, m, n, k, flags, L.ptr(pb), L.ptr(pa), L.stream()), "tn")
+    torch.cuda.synchronize()
+    assert nerr(c.float(), ref) <= 6e-3      # bf16 output rounding = 2^-8 relative
+
+
+@pytest.mark.parametrize("m,n,k,splits", [(128, 128, 64, 1), (256, 256, 1000, 3), (1024, 512, 4096, 9), (128, 384, 130, 4)])
+def test_tc_gemm_nn(R, m, n, k, splits):
+    L = R._lib
+    a, b = bf(k, m, seed=4), bf(k, n, seed=5)
+    c = torch.full((m, n), 7.0, device="cuda")
+    part = torch.empty((splits, m, n), device="cuda")
+    L.check(L.lib().rgnn_tc_gemm_nn(L.ptr(a), m, L.ptr(b), n, L.ptr(c), n, m, n, k, L.ptr(part), splits, L.stream()), "nn")
+    torch.cuda.synchronize()
+    assert nerr(c, a.float().t() @ b.float()) <= 1e-5
+
+
+@pytest.mark.parametrize("nodes,c0,c1,m0,m1,bias", [(4, 64, 0, 128, 0, False), (10, 128, 128, 128, 0, True), (7, 256, 0, 128, 256, False),
+                                                     (41, 512, 512, 512, 0, True)])
+def test_tc_conv1x1(R, nodes, c0, c1, m0, m1, bias):
+    L = R._lib
+    w = bf(m0 + m1, c0 + c1, seed=6, scale=0.05)
+    x0, x1 = bf(nodes, c0, 64, seed=7), (bf(nodes, c1, 64, seed=8) if c1 else None)
+    o0 = torch.zeros((nodes, m0, 64), dtype=torch.bfloat16, device="cuda")
+    o1 = torch.zeros((nodes, m1, 64), dtype=torch.bfloat16, device="cuda") if m1 else None
+    b = torch.randn(m0 + m1, device="cuda") if bias else None
+    L.check(L.lib().rgnn_tc_conv1x1(L.ptr(w), L.ptr(x0), c0, L.ptr(x1), c1, L.ptr(o0), m0, L.ptr(o1), m1, L.ptr(b), nodes, L.stream()), "conv")
+    torch.cuda.synchronize()
+    x = torch.cat([x0, x1], 1) if c1 else x0
+    ref = torch.einsum("mk,vkp->vmp", w.float(), x.float())
+    if bias:
+        ref = ref + b.view(1, -1, 1)
+    got = torch.cat([o0, o1], 1) if m1 else o0
+    assert nerr(got.float(), ref) <= 6e-3
+
+
+@pytest.mark.parametrize("nodes,m,c0,c1,splits", [(3, 128, 256, 0, 1), (20, 256, 256, 256, 4), (203, 512, 512, 512, 9)])
+def test_tc_conv1x1_wgrad(R, nodes, m, c0, c1, splits):
+    L = R._lib
+    dy = bf(nodes, m, 64, seed=9)
+    x0, x1 = bf(nodes, c0, 64, seed=10), (bf(nodes, c1, 64, seed=11) if c1 else None)
+    dw = torch.full((m, c0 + c1), 3.0, device="cuda")
+    part = torch.empty((splits, m, c0 + c1), device="cuda")
+    L.check(L.lib().rgnn_tc_conv1x1_wgrad(L.ptr(dy), m, L.ptr(x0), c0, L.ptr(x1), c1, L.ptr(dw), c0 + c1, L.ptr(part), splits, nodes,
+                                          L.stream()), "wgrad")
+    torch.cuda.synchronize()
+    x = torch.cat([x0, x1], 1) if c1 else x0
+    assert nerr(dw, torch.einsum("vmp,vkp->mk", dy.float(), x.float())) <= 1e-5
+
+
+def test_cast_weights(R):
+    L = R._lib
+    w = torch.randn((200, 72), device="cuda")
+    o = torch.empty((200, 72), dtype=torch.bfloat16, device="cuda")
+    ot = torch.empty((72, 200), dtype=torch.bfloat16, device="cuda")
+    L.check(L.lib().rgnn_tc_cast_weights(L.ptr(w), 200, 72, L.ptr(o), L.ptr(ot), L.stream()), "cast")
+    assert torch.equal(o, w.to(torch.bfloat16)) and torch.equal(ot, w.t().contiguous().to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("g_,k,f", [(6, 5, 256), (8, 5, 512)])
+def test_block_tc_matches_cuda_core_path_and_oracle(R, g_, k, f):
+    """Whole 2-layer block in bf16: tensor-core path vs the CUDA-core rgnn_gemm path (same bf16 operands) and vs the fp64 oracle."""
+    from multi_robot_check import check_block, make_block
+    from oracle import gnn_oracle as O
+    errs = check_block(R, O, g_, k, f, torch.bfloat16, 2e-2)
+    assert max(errs.values()) <= 4e-2
+    sb = O.synthetic_batch(g_, k, f, p=64, seed=3)
+    outs = []
+    for use_tc in (True, False):
+        R._lib.USE_TC = use_tc
+        try:
+            blk, _ = make_block(R, O, f, True, True)
+            blk.cuda()
+            g = R.robot_batch(g_, k, device="cuda")
+            h = sb["h"].reshape(g_ * k, f, 8, 8).cuda().bfloat16().requires_grad_()
+            y = blk(g, h, sb["pose"].cuda())
+            y.backward(sb["dy"].reshape(y.shape).cuda().bfloat16())
+            outs.append((y.float(), h.grad.float(), blk.conv1.weight.grad.clone(), blk.gcn1.edge_encoder.layers[2].weight.grad.clone()))
+        finally:
+            R._lib.USE_TC = True
+    for a, b in zip(*outs):
+        assert nerr(a, b) <= 2e-2
