@@ -122,6 +122,17 @@ int rgnn_film_edge_grad(int dtype, const void* x, int64_t ldx, const void* dagg,
                         const int32_t* src32, const int32_t* dst32,
                         void* dz, int64_t num_edges, int64_t feat, int64_t pix, void* stream);
 
+/* ---- A10 fused: dh AND dz of the FiLM-mean aggregation from one shared-memory staging of h and dAgg -----------
+ * dh[u] = addend[u] + sum_{e: src_e = u} gamma_e * w_e * dagg[dst_e];  dz as in rgnn_film_edge_grad.
+ * ptr32 / idx32 / node_offsets32 are the packed arrays rgnn_build_batched_csr wrote.  addend may be NULL or == dh.
+ * Batched-robot-graph path only: returns RGNN_E_UNSUPPORTED when a graph does not fit shared memory or the rows
+ * are not 16-byte addressable (callers then use rgnn_aggregate on the out-CSR + rgnn_film_edge_grad). */
+int rgnn_film_backward(int dtype, const void* h, int64_t ldh, const void* dagg, int64_t lddagg, const void* z,
+                       int fuse_sigmoid_grad, const void* addend, int64_t ldadd, void* dh, int64_t lddh, void* dz,
+                       const float* inv_in_deg, const int32_t* ptr32, const int32_t* idx32, const int32_t* node_offsets32,
+                       int64_t num_graphs, int64_t max_graph_nodes, int64_t max_graph_edges,
+                       int64_t num_nodes, int64_t num_edges, int64_t feat, int64_t pix, void* stream);
+
 /* ---- A4 (+A10): first edge-encoder layer, K = 9 -----------------------------------------
  * a1 = relu(pose W1^T + b1)   (nn.Linear(9,F)+ReLU, dgl/model/models.py:147-148); pose [E,9] fp32
  * (edge.float(), models.py:153); w1 [F,9], b1 [F] fp32 master weights; a1 [E,F] in `dtype`. */

@@ -24,6 +24,7 @@ SIGNATURES = {
     "rgnn_aggregate": [_i32, _vp, _i64, _vp, _i32, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp]
                       + [_i64] * 7 + [_vp],
     "rgnn_film_edge_grad": [_i32, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
+    "rgnn_film_backward": [_i32, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp] + [_i64] * 7 + [_vp],
     "rgnn_edge_mlp1_fwd": [_i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "rgnn_edge_mlp1_bwd": [_i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "rgnn_gemm": [_i32, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i64, _i64, _i64]

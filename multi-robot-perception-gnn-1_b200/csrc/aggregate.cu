@@ -141,8 +141,24 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                : "memory");
 }
 
+// Issue `n` bulk copies of `bytes` each, spread over the lanes of one warp; lane 0 arms the barrier first.
+// src(i) / dst(i) are callables.  Must be called by a full warp.
+template <typename FS, typename FD>
+__device__ __forceinline__ void warp_bulk_rows(uint64_t* bar, int n, uint32_t bytes, FS src, FD dst) {
+  const int lane = threadIdx.x & 31;
+  for (int i = lane; i < n; i += 32) bulk_g2s(dst(i), src(i), bytes, bar);
+}
+
+template <typename T> __device__ __forceinline__ float2 lds_gb(const T* zt, int idx);
+template <> __device__ __forceinline__ float2 lds_gb<float>(const float* zt, int idx) { return *reinterpret_cast<const float2*>(zt + idx); }
+template <> __device__ __forceinline__ float2 lds_gb<__nv_bfloat16>(const __nv_bfloat16* zt, int idx) {
+  const uint32_t w = *reinterpret_cast<const uint32_t*>(zt + idx);
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+
+// zmode: 0 = no FiLM, 1 = gamma/beta read from global, 2 = the graph's z slice [Eg][2*ct] staged in shared memory too
 template <typename T>
-__global__ void __launch_bounds__(256) k_agg_staged(AggParams p, int CT, int maxK, int maxE, int tile_off) {
+__global__ void __launch_bounds__(256) k_agg_staged(AggParams p, int CT, int maxK, int maxE, int tile_off, int zmode) {
   constexpr int VEC = Vec16<T>::N;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -150,6 +166,7 @@ __global__ void __launch_bounds__(256) k_agg_staged(AggParams p, int CT, int max
   int32_t* s_nbr = s_ptr + (maxK + 1);
   int32_t* s_eid = s_nbr + maxE;
   T* tile = reinterpret_cast<T*>(smem + tile_off);
+  T* ztile = tile + (size_t)maxK * CT * p.P;
 
   const T* __restrict__ x = static_cast<const T*>(p.x);
   const T* __restrict__ z = static_cast<const T*>(p.z);
@@ -165,29 +182,36 @@ __global__ void __launch_bounds__(256) k_agg_staged(AggParams p, int CT, int max
   if (K == 0) return;
   const int slice = ct * p.P;                 // elements per node in this tile (contiguous in HBM)
   const uint32_t slice_bytes = (uint32_t)slice * sizeof(T);
+  const int e0 = p.ptr[n0], eg = p.ptr[n0 + K] - e0;   // a batched graph's CSR slice == its edge-id range
+  const uint32_t zrow_bytes = (uint32_t)(2 * ct) * sizeof(T);
 
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, slice_bytes * (uint32_t)K);
-    for (int a = 0; a < K; ++a)
-      bulk_g2s(tile + (size_t)a * slice, x + (int64_t)(n0 + a) * p.ldx + (int64_t)c0 * p.P, slice_bytes, bar);
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) mbar_expect_tx(bar, slice_bytes * (uint32_t)K + (zmode == 2 ? zrow_bytes * (uint32_t)eg : 0u));
+    __syncwarp();
+    warp_bulk_rows(bar, K, slice_bytes,
+                   [&](int a) { return x + (int64_t)(n0 + a) * p.ldx + (int64_t)c0 * p.P; },
+                   [&](int a) { return tile + (size_t)a * slice; });
+    if (zmode == 2)
+      warp_bulk_rows(bar, eg, zrow_bytes,
+                     [&](int i) { return z + (int64_t)(e0 + i) * 2 * p.F + 2 * c0; },
+                     [&](int i) { return ztile + (size_t)i * 2 * ct; });
   }
   // while the copy engine works: this graph's CSR slice -> shared
-  const int e0 = p.ptr[n0], eg = p.ptr[n0 + K] - e0;
   for (int i = threadIdx.x; i <= K; i += blockDim.x) s_ptr[i] = p.ptr[n0 + i] - e0;
-  for (int i = threadIdx.x; i < eg; i += blockDim.x) { s_nbr[i] = p.nbr[e0 + i] - n0; s_eid[i] = p.eid[e0 + i]; }
+  for (int i = threadIdx.x; i < eg; i += blockDim.x) { s_nbr[i] = p.nbr[e0 + i] - n0; s_eid[i] = zmode ? p.eid[e0 + i] - e0 : 0; }
   __syncthreads();
   mbar_wait(bar, 0);
 
-  const bool has_z = z != nullptr, has_ns = p.nbr_scale != nullptr, use_beta = p.use_beta != 0;
+  const bool has_z = zmode != 0, has_ns = p.nbr_scale != nullptr, use_beta = p.use_beta != 0;
   const int nvec = slice / VEC;
   for (int j = threadIdx.x; j < nvec; j += blockDim.x) {
     const int off = j * VEC;
-    const int c = c0 + off / p.P;
+    const int cl = off / p.P;                  // channel inside the tile
     const int64_t goff = (int64_t)c0 * p.P + off;
     for (int a = 0; a < K; ++a) {
       const int i0 = s_ptr[a], i1 = s_ptr[a + 1];
@@ -199,7 +223,8 @@ __global__ void __launch_bounds__(256) k_agg_staged(AggParams p, int CT, int max
         float xv[VEC];
         Vec16<T>::load(tile + (size_t)u * slice + off, xv);
         float2 gb = make_float2(1.f, 0.f);
-        if (has_z) gb = load_gb<T>(z, (int64_t)s_eid[i] * 2 * p.F + 2 * c);
+        if (zmode == 2) gb = lds_gb<T>(ztile, s_eid[i] * 2 * ct + 2 * cl);
+        else if (zmode == 1) gb = load_gb<T>(z, (int64_t)(e0 + s_eid[i]) * 2 * p.F + 2 * (c0 + cl));
         film_acc<VEC>(acc, xv, has_z, gb, use_beta, has_ns ? p.nbr_scale[n0 + u] : 1.f, has_ns);
       }
       const int64_t v = n0 + a;
@@ -214,6 +239,160 @@ __global__ void __launch_bounds__(256) k_agg_staged(AggParams p, int CT, int max
       if (copy_to)
         *reinterpret_cast<uint4*>(copy_to + v * p.ldout + goff) = *reinterpret_cast<const uint4*>(tile + (size_t)a * slice + off);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A10 fused: the whole backward of the FiLM-mean aggregation for one (graph, channel tile) from ONE staging of the
+// h and dAgg tiles:   dh[u]   = addend[u] + sum_{e: src=u} gamma_e * w_dst * dAgg[dst_e]
+//                     dz[e,:] = sigmoid'(z) * w_dst * ( sum_p h[src_e] * dAgg[dst_e] ,  sum_p dAgg[dst_e] )
+// HBM traffic: read h, dAgg, z (+addend) once, write dh, dz once (the reference keeps three [E,F,P] activations alive).
+struct FilmBwdParams {
+  const void* h; int64_t ldh;
+  const void* dagg; int64_t ldd;
+  const void* z;
+  const void* addend; int64_t ldadd;
+  void* dh; int64_t lddh;
+  void* dz;
+  const float* inv_in_deg;
+  const int32_t *in_ptr, *in_src, *in_eid, *out_ptr, *out_dst, *out_eid, *noff;
+  int F, P, fuse_sig;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_film_bwd_staged(FilmBwdParams p, int CT, int maxK, int maxE, int tile_off) {
+  constexpr int VEC = Vec16<T>::N;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  int32_t* s_iptr = reinterpret_cast<int32_t*>(smem + 16);
+  int32_t* s_optr = s_iptr + (maxK + 1);
+  int32_t* s_isrc = s_optr + (maxK + 1);
+  int32_t* s_ieid = s_isrc + maxE;
+  int32_t* s_odst = s_ieid + maxE;
+  int32_t* s_oeid = s_odst + maxE;
+  float* s_w = reinterpret_cast<float*>(s_oeid + maxE);
+  T* htile = reinterpret_cast<T*>(smem + tile_off);
+  T* dtile = htile + (size_t)maxK * CT * p.P;
+  T* ztile = dtile + (size_t)maxK * CT * p.P;
+  T* dztile = ztile + (size_t)maxE * 2 * CT;
+
+  const T* __restrict__ h = static_cast<const T*>(p.h);
+  const T* __restrict__ dagg = static_cast<const T*>(p.dagg);
+  const T* __restrict__ z = static_cast<const T*>(p.z);
+  const T* __restrict__ addend = static_cast<const T*>(p.addend);
+  T* __restrict__ dh = static_cast<T*>(p.dh);
+  T* __restrict__ dz = static_cast<T*>(p.dz);
+
+  const int tiles_c = (p.F + CT - 1) / CT;
+  const int64_t g = blockIdx.x / tiles_c;
+  const int c0 = (int)(blockIdx.x % tiles_c) * CT;
+  const int ct = min(CT, p.F - c0);
+  const int n0 = p.noff[g], K = p.noff[g + 1] - n0;
+  if (K == 0) return;
+  const int slice = ct * p.P;
+  const uint32_t slice_bytes = (uint32_t)slice * sizeof(T);
+  const int e0 = p.in_ptr[n0], eg = p.in_ptr[n0 + K] - e0;
+  const uint32_t zrow_bytes = (uint32_t)(2 * ct) * sizeof(T);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) mbar_expect_tx(bar, 2u * slice_bytes * (uint32_t)K + zrow_bytes * (uint32_t)eg);
+    __syncwarp();
+    warp_bulk_rows(bar, K, slice_bytes,
+                   [&](int a) { return h + (int64_t)(n0 + a) * p.ldh + (int64_t)c0 * p.P; },
+                   [&](int a) { return htile + (size_t)a * slice; });
+    warp_bulk_rows(bar, K, slice_bytes,
+                   [&](int a) { return dagg + (int64_t)(n0 + a) * p.ldd + (int64_t)c0 * p.P; },
+                   [&](int a) { return dtile + (size_t)a * slice; });
+    warp_bulk_rows(bar, eg, zrow_bytes,
+                   [&](int i) { return z + (int64_t)(e0 + i) * 2 * p.F + 2 * c0; },
+                   [&](int i) { return ztile + (size_t)i * 2 * ct; });
+  }
+  for (int i = threadIdx.x; i <= K; i += blockDim.x) { s_iptr[i] = p.in_ptr[n0 + i] - e0; s_optr[i] = p.out_ptr[n0 + i] - e0; }
+  for (int i = threadIdx.x; i < K; i += blockDim.x) s_w[i] = p.inv_in_deg[n0 + i];
+  for (int i = threadIdx.x; i < eg; i += blockDim.x) {
+    s_isrc[i] = p.in_src[e0 + i] - n0; s_ieid[i] = p.in_eid[e0 + i] - e0;
+    s_odst[i] = p.out_dst[e0 + i] - n0; s_oeid[i] = p.out_eid[e0 + i] - e0;
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+
+  const int lpc = p.P / VEC;                  // lanes sharing one channel (power of two <= 32, host-checked)
+  const int nvec = slice / VEC;
+  const int nvec_pad = (nvec + 31) & ~31;     // whole warps iterate together (shuffles)
+  for (int j = threadIdx.x; j < nvec_pad; j += blockDim.x) {
+    const bool live = j < nvec;
+    const int off = live ? j * VEC : 0;
+    const int cl = off / p.P;
+    const int64_t goff = (int64_t)c0 * p.P + off;
+    // ---- dh: transposed gather over the out-edges of every source u
+    if (live) {
+      for (int u = 0; u < K; ++u) {
+        float acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        for (int i = s_optr[u]; i < s_optr[u + 1]; ++i) {
+          const int v = s_odst[i];
+          float dv[VEC];
+          Vec16<T>::load(dtile + (size_t)v * slice + off, dv);
+          const float gw = lds_gb<T>(ztile, s_oeid[i] * 2 * ct + 2 * cl).x * s_w[v];
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[q] = fmaf(gw, dv[q], acc[q]);
+        }
+        const int64_t gu = n0 + u;
+        if (addend) {
+          float av[VEC];
+          Vec16<T>::load(addend + gu * p.ldadd + goff, av);
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[q] += av[q];
+        }
+        Vec16<T>::store(dh + gu * p.lddh + goff, acc);
+      }
+    }
+    // ---- dz: per destination keep dAgg in registers, dot with every in-neighbour's h; lane-group reduction over pixels
+    for (int a = 0; a < K; ++a) {
+      float dv[VEC];
+      float sd = 0.f;
+      if (live) {
+        Vec16<T>::load(dtile + (size_t)a * slice + off, dv);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) sd += dv[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) dv[q] = 0.f;
+      }
+      for (int o = lpc >> 1; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+      const float wa = s_w[a];
+      for (int i = s_iptr[a]; i < s_iptr[a + 1]; ++i) {
+        float sxd = 0.f;
+        if (live) {
+          float hv[VEC];
+          Vec16<T>::load(htile + (size_t)s_isrc[i] * slice + off, hv);
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) sxd = fmaf(hv[q], dv[q], sxd);
+        }
+        for (int o = lpc >> 1; o > 0; o >>= 1) sxd += __shfl_xor_sync(0xffffffffu, sxd, o);
+        if (live && (j % lpc) == 0) {
+          const int zi = s_ieid[i] * 2 * ct + 2 * cl;
+          const float2 gb = lds_gb<T>(ztile, zi);
+          float dg = sxd * wa, db = sd * wa;
+          if (p.fuse_sig) { dg *= gb.x * (1.f - gb.x); db *= gb.y * (1.f - gb.y); }
+          if constexpr (sizeof(T) == 4) *reinterpret_cast<float2*>(dztile + zi) = make_float2(dg, db);
+          else *reinterpret_cast<__nv_bfloat162*>(dztile + zi) = __floats2bfloat162_rn(dg, db);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- dz tile -> global, 16-byte coalesced rows
+  const int zvec_row = (2 * ct) / VEC;
+  for (int t = threadIdx.x; t < eg * zvec_row; t += blockDim.x) {
+    const int e = t / zvec_row, q = t % zvec_row;
+    *reinterpret_cast<uint4*>(dz + (int64_t)(e0 + e) * 2 * p.F + 2 * c0 + q * VEC) = *reinterpret_cast<const uint4*>(dztile + (size_t)e * 2 * ct + q * VEC);
   }
 }
 
@@ -314,19 +493,30 @@ extern "C" int rgnn_aggregate(int dtype, const void* x, int64_t ldx, const void*
     const int idx_bytes = (int)(((maxK + 1 + 2 * (int64_t)maxE) * 4 + 15) / 16 * 16);
     const int tile_off = ((16 + idx_bytes) + 127) / 128 * 128;
     const int64_t budget = 44 * 1024 - tile_off;           // ~5 CTAs / SM
-    int64_t CT = budget > 0 ? budget / (maxK * row_bytes_per_ch) : 0;
-    if (CT > F) CT = F;
-    // bulk copies need 16-byte multiples: ct*P*es % 16 == 0 for every tile incl. the tail
-    while (CT > 0 && ((CT * row_bytes_per_ch) % 16 != 0 || ((F % CT) * row_bytes_per_ch) % 16 != 0)) --CT;
+    // gamma/beta slice in shared memory as well when its rows are 16-byte addressable
+    const int zalign = 8 / es;                               // CT multiple making 2*CT*es a 16-byte multiple
+    const bool z_stage_ok = z && aligned16(z) && (2 * F * es) % 16 == 0 && F % zalign == 0;
+    int zmode = z ? (z_stage_ok ? 2 : 1) : 0;
+    int64_t CT = 0;
+    for (int attempt = 0; attempt < 2 && CT < 1; ++attempt) {
+      const int64_t per_ch = maxK * row_bytes_per_ch + (zmode == 2 ? (int64_t)maxE * 2 * es : 0);
+      CT = budget > 0 ? budget / per_ch : 0;
+      if (CT > F) CT = F;
+      if (zmode == 2) CT -= CT % zalign;
+      // bulk copies need 16-byte multiples: ct*P*es % 16 == 0 for every tile incl. the tail
+      while (CT > 0 && ((CT * row_bytes_per_ch) % 16 != 0 || ((F % CT) * row_bytes_per_ch) % 16 != 0 ||
+                        (zmode == 2 && (F % CT) % zalign != 0))) CT -= (zmode == 2 ? zalign : 1);
+      if (CT < 1 && zmode == 2) zmode = 1;                   // retry without staging z
+    }
     if (CT >= 1 && (int64_t)CT * P >= vec) {
       const int64_t tiles_c = (F + CT - 1) / CT;
       const int64_t blocks = G * tiles_c;
       if (blocks < (1ll << 31)) {
-        const size_t smem = (size_t)tile_off + (size_t)maxK * CT * row_bytes_per_ch;
+        const size_t smem = (size_t)tile_off + (size_t)maxK * CT * row_bytes_per_ch + (zmode == 2 ? (size_t)maxE * 2 * CT * es : 0);
         if (dtype == RGNN_F32) {
-          k_agg_staged<float><<<(unsigned)blocks, 256, smem, st>>>(p, (int)CT, maxK, maxE, tile_off);
+          k_agg_staged<float><<<(unsigned)blocks, 256, smem, st>>>(p, (int)CT, maxK, maxE, tile_off, zmode);
         } else {
-          k_agg_staged<__nv_bfloat16><<<(unsigned)blocks, 256, smem, st>>>(p, (int)CT, maxK, maxE, tile_off);
+          k_agg_staged<__nv_bfloat16><<<(unsigned)blocks, 256, smem, st>>>(p, (int)CT, maxK, maxE, tile_off, zmode);
         }
         RGNN_LAUNCH_CHECK("k_agg_staged");
         return 0;
@@ -371,5 +561,61 @@ extern "C" int rgnn_film_edge_grad(int dtype, const void* x, int64_t ldx, const 
   else { if (vec_ok) LAUNCH(__nv_bfloat16, 8); else LAUNCH(__nv_bfloat16, 1); }
 #undef LAUNCH
   RGNN_LAUNCH_CHECK("k_film_edge_grad");
+  return 0;
+}
+
+// Fused backward of the FiLM-mean aggregation (A10) for batched robot graphs.  Returns RGNN_E_UNSUPPORTED when the
+// batch does not fit the staged kernel (caller then uses rgnn_aggregate on the out-CSR + rgnn_film_edge_grad).
+extern "C" int rgnn_film_backward(int dtype, const void* h, int64_t ldh, const void* dagg, int64_t lddagg, const void* z,
+                                  int fuse_sigmoid_grad, const void* addend, int64_t ldadd, void* dh, int64_t lddh, void* dz,
+                                  const float* inv_in_deg, const int32_t* ptr32, const int32_t* idx32, const int32_t* noff32,
+                                  int64_t G, int64_t max_graph_nodes, int64_t max_graph_edges,
+                                  int64_t N, int64_t E, int64_t F, int64_t P, void* stream) {
+  RGNN_REQUIRE(dtype == RGNN_F32 || dtype == RGNN_BF16, RGNN_E_ARG, "rgnn_film_backward: bad dtype %d", dtype);
+  RGNN_REQUIRE(N >= 0 && E >= 0 && G >= 0 && F > 0 && P > 0, RGNN_E_ARG, "rgnn_film_backward: bad sizes");
+  if (N == 0) return 0;
+  RGNN_REQUIRE(h && dagg && z && dh && dz && inv_in_deg && ptr32 && idx32 && noff32, RGNN_E_ARG, "rgnn_film_backward: null pointer");
+  const int es = dtype == RGNN_F32 ? 4 : 2;
+  const int vec = 16 / es;
+  const int maxK = (int)max_graph_nodes, maxE = (int)max_graph_edges;
+  const int64_t lpc = P / vec;
+  const bool ok = G > 0 && maxK > 0 && maxK < 4096 && maxE < (1 << 20) && P % vec == 0 && lpc >= 1 && lpc <= 32 && (lpc & (lpc - 1)) == 0 &&
+                  aligned16(h) && aligned16(dagg) && aligned16(z) && aligned16(dh) && aligned16(dz) && (!addend || aligned16(addend)) &&
+                  ldh % vec == 0 && lddagg % vec == 0 && lddh % vec == 0 && (!addend || ldadd % vec == 0) &&
+                  (2 * F * es) % 16 == 0 && F % (8 / es) == 0 && F * P < (1ll << 31);
+  RGNN_REQUIRE(ok, RGNN_E_UNSUPPORTED, "rgnn_film_backward: shape/alignment not covered by the staged kernel");
+  const int zalign = 8 / es;
+  const int64_t row_bytes_per_ch = P * es;
+  const int idx_bytes = (int)(((2 * (maxK + 1) + 4 * (int64_t)maxE + maxK) * 4 + 15) / 16 * 16);
+  const int tile_off = ((16 + idx_bytes) + 127) / 128 * 128;
+  const int64_t budget = 56 * 1024 - tile_off;             // 4 CTAs / SM
+  const int64_t per_ch = 2 * maxK * row_bytes_per_ch + (int64_t)maxE * 4 * es;
+  int64_t CT = budget > 0 ? budget / per_ch : 0;
+  if (CT > F) CT = F;
+  CT -= CT % zalign;
+  while (CT > 0 && ((CT * row_bytes_per_ch) % 16 != 0 || ((F % CT) * row_bytes_per_ch) % 16 != 0 || (F % CT) % zalign != 0)) CT -= zalign;
+  RGNN_REQUIRE(CT >= 1, RGNN_E_UNSUPPORTED, "rgnn_film_backward: a graph's tile does not fit shared memory");
+  const int64_t tiles_c = (F + CT - 1) / CT;
+  const int64_t blocks = G * tiles_c;
+  RGNN_REQUIRE(blocks < (1ll << 31), RGNN_E_RANGE, "rgnn_film_backward: grid too large");
+  FilmBwdParams p;
+  p.h = h; p.ldh = ldh; p.dagg = dagg; p.ldd = lddagg; p.z = z; p.addend = addend; p.ldadd = ldadd; p.dh = dh; p.lddh = lddh; p.dz = dz;
+  p.inv_in_deg = inv_in_deg;
+  p.in_ptr = ptr32; p.out_ptr = ptr32 + (N + 1);
+  p.in_src = idx32; p.in_eid = idx32 + E; p.out_dst = idx32 + 2 * E; p.out_eid = idx32 + 3 * E;
+  p.noff = noff32; p.F = (int)F; p.P = (int)P; p.fuse_sig = fuse_sigmoid_grad;
+  const size_t smem = (size_t)tile_off + 2 * (size_t)maxK * CT * row_bytes_per_ch + (size_t)maxE * 4 * CT * es;
+  cudaStream_t st = as_stream(stream);
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[dtype]) {
+    cudaError_t e = dtype == RGNN_F32
+        ? cudaFuncSetAttribute(k_film_bwd_staged<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)
+        : cudaFuncSetAttribute(k_film_bwd_staged<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_film_bwd_staged)");
+    attr_done[dtype] = true;
+  }
+  if (dtype == RGNN_F32) k_film_bwd_staged<float><<<(unsigned)blocks, 256, smem, st>>>(p, (int)CT, maxK, maxE, tile_off);
+  else k_film_bwd_staged<__nv_bfloat16><<<(unsigned)blocks, 256, smem, st>>>(p, (int)CT, maxK, maxE, tile_off);
+  RGNN_LAUNCH_CHECK("k_film_bwd_staged");
   return 0;
 }

@@ -163,6 +163,39 @@ __global__ void __launch_bounds__(256) k_reduce_sum(const T* __restrict__ x, int
   }
 }
 
+// NCHW bias gradient at full bandwidth: x [outer, len, inner] contiguous, inner % VEC == 0.  Thread = one 16-byte vector of
+// the (len*inner) row, streams its chunk of `outer`; the inner/VEC lanes of a channel combine by shuffle; one atomic per channel.
+template <typename T>
+__global__ void __launch_bounds__(256) k_reduce_rows_vec(const T* __restrict__ x, int64_t outer, int64_t len, int inner,
+                                                         float* __restrict__ out, int64_t chunk) {
+  constexpr int VEC = Vec16<T>::N;
+  const int64_t row_vecs = len * inner / VEC;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lpc = inner / VEC;
+  const int64_t i0 = (int64_t)blockIdx.y * chunk, i1 = min(outer, i0 + chunk);
+  float acc = 0.f;
+  if (t < row_vecs) {
+    const T* px = x + t * VEC;
+    const int64_t stride = len * inner;
+    int64_t i = i0;
+    for (; i + 4 <= i1; i += 4) {       // 4 independent 16-byte loads in flight
+      float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
+      Vec16<T>::load(px + i * stride, v0); Vec16<T>::load(px + (i + 1) * stride, v1);
+      Vec16<T>::load(px + (i + 2) * stride, v2); Vec16<T>::load(px + (i + 3) * stride, v3);
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) acc += (v0[q] + v1[q]) + (v2[q] + v3[q]);
+    }
+    for (; i < i1; ++i) {
+      float v0[VEC];
+      Vec16<T>::load(px + i * stride, v0);
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) acc += v0[q];
+    }
+  }
+  for (int o = min(lpc, 32) >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (t < row_vecs && (lpc >= 32 ? (threadIdx.x & 31) == 0 : (t % lpc) == 0)) atomicAdd(out + (t * VEC) / inner, acc);
+}
+
 }  // namespace rgnn
 
 using namespace rgnn;
@@ -285,6 +318,26 @@ extern "C" int rgnn_reduce_sum(int dtype, const void* x, int64_t outer, int64_t 
   if (e != cudaSuccess) return cuda_fail(e, "memset reduce out");
   if (outer == 0 || inner == 0) return 0;
   RGNN_REQUIRE(x, RGNN_E_ARG, "rgnn_reduce_sum: null x");
+  {  // contiguous [outer, len, inner] with 16-byte vectors inside a channel: the streaming kernel
+    const int es = dtype == RGNN_F32 ? 4 : 2, vec = 16 / es;
+    const int64_t lpc = inner / vec;
+    if (s_inner == 1 && s_j == inner && s_outer == len * inner && inner % vec == 0 && (lpc & (lpc - 1)) == 0 &&
+        (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && inner < (1 << 20)) {
+      const int64_t row_vecs = len * inner / vec;
+      const int64_t bx = (row_vecs + 255) / 256;
+      int64_t chunks = (8 * kNumSMs + bx - 1) / bx;
+      if (chunks > outer) chunks = outer;
+      if (chunks > 65535) chunks = 65535;
+      const int64_t chunk = (outer + chunks - 1) / chunks;
+      chunks = (outer + chunk - 1) / chunk;
+      RGNN_REQUIRE(bx < (1ll << 31), RGNN_E_RANGE, "rgnn_reduce_sum: too long");
+      dim3 grid((unsigned)bx, (unsigned)chunks);
+      if (dtype == RGNN_F32) k_reduce_rows_vec<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), outer, len, (int)inner, out, chunk);
+      else k_reduce_rows_vec<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), outer, len, (int)inner, out, chunk);
+      RGNN_LAUNCH_CHECK("k_reduce_rows_vec");
+      return 0;
+    }
+  }
   const bool jfast = (s_j == 1 || inner == 1);
   const int64_t bx = jfast ? (len + 255) / 256 : (len + 7) / 8;
   int64_t chunks = (8 * kNumSMs + bx - 1) / bx;

@@ -78,6 +78,9 @@ class AggregateFn(torch.autograd.Function):
         dout = dout.contiguous()
         dx = dz = None
         with torch.cuda.device(dout.device):
+            if z is not None and ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:
+                dx, dz = _film_backward(ix, x, dout, z, None, False)
+                return dx, dz, None, None, None, None
             if ctx.needs_input_grad[0]:
                 back_nbr = {"mean": ix.inv_in_deg, "scale": dst_scale}.get(ctx.post)
                 dx = torch.empty_like(x)
@@ -126,14 +129,12 @@ class FilmMeanCatFn(torch.autograd.Function):
         dagg = dout.view(-1)[f * p:]          # second channel half, node stride 2FP
         dh = dz = None
         with torch.cuda.device(dout.device):
-            if ctx.needs_input_grad[0]:
+            if z is not None and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+                dh, dz = _film_backward(ix, h, dagg, z, dout, False, ldd=2 * f * p, ldadd=2 * f * p, dh=torch.empty_like(h))
+            elif ctx.needs_input_grad[0]:
                 dh = torch.empty_like(h)
-                _aggregate(ix, dagg, z, False, ix.inv_in_deg, _lib.POST_NONE, None, dout, dh, None, True,
+                _aggregate(ix, dagg, None, False, ix.inv_in_deg, _lib.POST_NONE, None, dout, dh, None, True,
                            ldx=2 * f * p, ldadd=2 * f * p, shape=(f, p))
-            if z is not None and ctx.needs_input_grad[1]:
-                dz = torch.empty_like(z)
-                check(lib().rgnn_film_edge_grad(dtype_code(h), ptr(h), f * p, ptr(dagg), 2 * f * p, ptr(z), 0, ptr(ix.inv_in_deg),
-                                                ptr(ix.src32), ptr(ix.dst32), ptr(dz), ix.E, f, p, stream()), "rgnn_film_edge_grad")
         return dh, dz, None
 
 
@@ -179,29 +180,34 @@ def _splits(tiles, work_items):
     return max(1, min(s, work_items))
 
 
+def _edge_mlp_forward(pose, w1, b1, w2, b2, out_dtype):
+    _lib.require_cuda(pose, w1, b1, w2, b2)
+    pose = pose.float().contiguous()          # edge.float(), models.py:153
+    e, hid, f2 = pose.shape[0], w1.shape[0], w2.shape[0]
+    if pose.shape[1] != 9 or w1.shape != (hid, 9) or w2.shape != (f2, hid) or f2 % 2:
+        raise ValueError("edge encoder expects pose [E,9], W1 [H,9], W2 [2F,H]")
+    w1, b1, w2, b2 = (t.detach().float().contiguous() for t in (w1, b1, w2, b2))
+    a1 = torch.empty((e, hid), dtype=out_dtype, device=pose.device)
+    z = torch.empty((e, f2), dtype=out_dtype, device=pose.device)
+    with torch.cuda.device(pose.device):
+        check(lib().rgnn_edge_mlp1_fwd(dtype_code(a1), ptr(pose), ptr(w1), ptr(b1), ptr(a1), e, hid, stream()), "rgnn_edge_mlp1_fwd")
+        if _lib.USE_TC and out_dtype == torch.bfloat16 and hid % 64 == 0 and f2 % 128 == 0:
+            w2b = _cast_w(w2)
+            with _lib.timed("mlp2_fwd", 2.0 * e * f2 * hid):
+                check(lib().rgnn_tc_gemm_tn(ptr(a1), hid, ptr(w2b), hid, ptr(z), f2, e, f2, hid,
+                                            _lib.EPI_BIAS_N | _lib.EPI_SIGMOID, ptr(b2), None, stream()), "rgnn_tc_gemm_tn")
+        else:
+            _gemm(a1, (0, 0, hid, 1), w2, (0, 0, 1, hid), z, (0, f2, 1), e, f2, hid,
+                  epi=_lib.EPI_BIAS_N | _lib.EPI_SIGMOID, bias=b2, tag="mlp2_fwd")
+    return pose, w2, a1, z
+
+
 class EdgeMLPFn(torch.autograd.Function):
     """z = sigmoid(relu(pose W1^T + b1) W2^T + b2)  - edge_encoder.layers (models.py:146-151); [E, 2F]."""
 
     @staticmethod
     def forward(ctx, pose, w1, b1, w2, b2, out_dtype):
-        _lib.require_cuda(pose, w1, b1, w2, b2)
-        pose = pose.float().contiguous()          # edge.float(), models.py:153
-        e, hid, f2 = pose.shape[0], w1.shape[0], w2.shape[0]
-        if pose.shape[1] != 9 or w1.shape != (hid, 9) or w2.shape != (f2, hid) or f2 % 2:
-            raise ValueError("edge encoder expects pose [E,9], W1 [H,9], W2 [2F,H]")
-        w1, b1, w2, b2 = (t.detach().float().contiguous() for t in (w1, b1, w2, b2))
-        a1 = torch.empty((e, hid), dtype=out_dtype, device=pose.device)
-        z = torch.empty((e, f2), dtype=out_dtype, device=pose.device)
-        with torch.cuda.device(pose.device):
-            check(lib().rgnn_edge_mlp1_fwd(dtype_code(a1), ptr(pose), ptr(w1), ptr(b1), ptr(a1), e, hid, stream()), "rgnn_edge_mlp1_fwd")
-            if _lib.USE_TC and out_dtype == torch.bfloat16 and hid % 64 == 0 and f2 % 128 == 0:
-                w2b = _cast_w(w2)
-                with _lib.timed("mlp2_fwd", 2.0 * e * f2 * hid):
-                    check(lib().rgnn_tc_gemm_tn(ptr(a1), hid, ptr(w2b), hid, ptr(z), f2, e, f2, hid,
-                                                _lib.EPI_BIAS_N | _lib.EPI_SIGMOID, ptr(b2), None, stream()), "rgnn_tc_gemm_tn")
-            else:
-                _gemm(a1, (0, 0, hid, 1), w2, (0, 0, 1, hid), z, (0, f2, 1), e, f2, hid,
-                      epi=_lib.EPI_BIAS_N | _lib.EPI_SIGMOID, bias=b2, tag="mlp2_fwd")
+        pose, w2, a1, z = _edge_mlp_forward(pose, w1, b1, w2, b2, out_dtype)
         ctx.save_for_backward(pose, w2, a1, z)
         return z
 
@@ -251,38 +257,89 @@ def edge_mlp(pose, w1, b1, w2, b2, out_dtype=torch.float32):
     return EdgeMLPFn.apply(pose, w1, b1, w2, b2, out_dtype)
 
 
-class CompressFn(torch.autograd.Function):
-    """y = Conv2d(2F, F, 1)(cat(h, g_h))  - dgl/model/models.py:182-184 - without materialising the concat:
-    y_v = Wc[:, :F] h_v + Wc[:, F:] g_v + bc per node (a [F x 2F] . [2F x P] product per robot)."""
-
-    @staticmethod
-    def forward(ctx, h, gh, wc, bc):
-        _lib.require_cuda(h, gh, wc, bc)
-        h, gh = h.contiguous(), gh.contiguous()
-        n, f = h.shape[0], h.shape[1]
-        _, p = _row_shape(h)
-        wc2 = wc.detach().float().reshape(wc.shape[0], -1).contiguous()
-        fo = wc2.shape[0]
-        if wc2.shape[1] != 2 * f or gh.shape != h.shape or h.dtype != gh.dtype:
-            raise ValueError("compress expects h, g_h [N,F,...] and weight [Fo, 2F(,1,1)]")
-        bcf = bc.detach().float().contiguous()
-        y = torch.empty((n, fo) + tuple(h.shape[2:]), dtype=h.dtype, device=h.device)
-        ctx.tc = bool(_lib.USE_TC and h.dtype == torch.bfloat16 and p == 64 and f % 64 == 0 and fo % 128 == 0 and n > 0)
-        if ctx.tc:
-            with torch.cuda.device(h.device):
-                wb = _cast_w(wc2)
-                with _lib.timed("compress_fwd", 2.0 * fo * 2 * f * n * p):
-                    check(lib().rgnn_tc_conv1x1(ptr(wb), ptr(h), f, ptr(gh), f, ptr(y), fo, None, 0, ptr(bcf), n, stream()), "rgnn_tc_conv1x1")
-            ctx.save_for_backward(h, gh, wc2)
-            ctx.wshape = tuple(wc.shape)
-            return y
-        with torch.cuda.device(h.device):
+def _compress_forward(h, gh, wc, bc):
+    """-> (y, wc2 fp32 [Fo, 2F], used_tensor_cores)."""
+    _lib.require_cuda(h, gh, wc, bc)
+    n, f = h.shape[0], h.shape[1]
+    _, p = _row_shape(h)
+    wc2 = wc.detach().float().reshape(wc.shape[0], -1).contiguous()
+    fo = wc2.shape[0]
+    if wc2.shape[1] != 2 * f or gh.shape != h.shape or h.dtype != gh.dtype:
+        raise ValueError("compress expects h, g_h [N,F,...] and weight [Fo, 2F(,1,1)]")
+    bcf = bc.detach().float().contiguous()
+    y = torch.empty((n, fo) + tuple(h.shape[2:]), dtype=h.dtype, device=h.device)
+    tc = bool(_lib.USE_TC and h.dtype == torch.bfloat16 and p == 64 and f % 64 == 0 and fo % 128 == 0 and n > 0)
+    with torch.cuda.device(h.device):
+        if tc:
+            wb = _cast_w(wc2)
+            with _lib.timed("compress_fwd", 2.0 * fo * 2 * f * n * p):
+                check(lib().rgnn_tc_conv1x1(ptr(wb), ptr(h), f, ptr(gh), f, ptr(y), fo, None, 0, ptr(bcf), n, stream()), "rgnn_tc_conv1x1")
+        else:
             if p == 1:    # [N,F,1,1] maps: the nodes form the N dimension of one product
                 sb, sc, bt, nn = (0, 0, 1, f), (0, 1, fo), 1, n
             else:         # one [Fo x P] product per node
                 sb, sc, bt, nn = (f * p, 0, p, 1), (fo * p, p, 1), n, p
             _gemm(wc2, (0, 0, 2 * f, 1), h, sb, y, sc, fo, nn, f, batch=bt, epi=_lib.EPI_BIAS_M, bias=bcf, tag="compress_fwd")
             _gemm(wc2[:, f:], (0, 0, 2 * f, 1), gh, sb, y, sc, fo, nn, f, batch=bt, epi=_lib.EPI_ADD_AUX, aux=y, beta=1.0, tag="compress_fwd")
+    return y, wc2, tc
+
+
+def _compress_backward(dy, h, gh, wc2, tc, need_dh, need_dgh, need_dw, need_db):
+    """Autograd of the concat + 1x1 conv: dh (direct), dg_h, dWc [Fo, 2F] fp32, dbc [Fo] fp32."""
+    n, f = h.shape[0], h.shape[1]
+    _, p = _row_shape(h)
+    fo = wc2.shape[0]
+    dev = dy.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    dh = dgh = dwc = dbc = None
+    tc_dx = tc and f % 128 == 0 and fo % 64 == 0
+    tc_dw = tc and f % 256 == 0 and fo % 128 == 0
+    with torch.cuda.device(dev):
+        if tc_dx and (need_dh or need_dgh):
+            wt = _cast_w(wc2, transpose=True)               # [2F, Fo] K-major: dX_v = Wc^T . dY_v
+            dh, dgh = torch.empty_like(h), torch.empty_like(gh)
+            with _lib.timed("compress_dx", 2.0 * fo * 2 * f * n * p):
+                check(lib().rgnn_tc_conv1x1(ptr(wt), ptr(dy), fo, None, 0, ptr(dh), f, ptr(dgh), f, None, n, stream()), "rgnn_tc_conv1x1")
+        if tc_dw and need_dw:
+            dwc = torch.empty((fo, 2 * f), **f32)
+            split = _tc_splits((fo // 128) * (2 * f // 256), n)
+            partial = torch.empty((split, fo, 2 * f), **f32)
+            with _lib.timed("compress_dw", 2.0 * fo * 2 * f * n * p):
+                check(lib().rgnn_tc_conv1x1_wgrad(ptr(dy), fo, ptr(h), f, ptr(gh), f, ptr(dwc), 2 * f, ptr(partial), split, n, stream()),
+                      "rgnn_tc_conv1x1_wgrad")
+        if p == 1:
+            sb, sc, bt, nn = (0, 0, 1, fo), (0, 1, f), 1, n
+        else:
+            sb, sc, bt, nn = (fo * p, 0, p, 1), (f * p, p, 1), n, p
+        if need_dh and dh is None:
+            dh = torch.empty_like(h)
+            _gemm(wc2, (0, 0, 1, 2 * f), dy, sb, dh, sc, f, nn, fo, batch=bt, tag="compress_dx")
+        if need_dgh and dgh is None:
+            dgh = torch.empty_like(gh)
+            _gemm(wc2[:, f:], (0, 0, 1, 2 * f), dy, sb, dgh, sc, f, nn, fo, batch=bt, tag="compress_dx")
+        if need_dw and dwc is None:
+            dwc = torch.empty((fo, 2 * f), **f32)
+            split = _splits(((fo + 63) // 64) * ((f + 63) // 64), n)
+            partial = torch.empty((split, fo, f), **f32) if split > 1 else None
+            for half, src in ((0, h), (1, gh)):
+                # dWc[o, k2] = sum_v sum_p dy[v,o,p] * src[v,k2,p]: K = P per node, reduced over the N nodes
+                _gemm(dy, (0, fo * p, p, 1), src, (0, f * p, 1, p), dwc[:, half * f:], (0, 2 * f, 1), fo, f, p,
+                      red=n, split=split, partial=partial, tag="compress_dw")
+        if need_db:
+            dbc = torch.empty((fo,), **f32)
+            with _lib.timed("bias_grad", dy.element_size() * float(dy.numel())):
+                check(lib().rgnn_reduce_sum(dtype_code(dy), ptr(dy), n, fo * p, fo, p, p, 1, ptr(dbc), stream()), "rgnn_reduce_sum")
+    return dh, dgh, dwc, dbc
+
+
+class CompressFn(torch.autograd.Function):
+    """y = Conv2d(2F, F, 1)(cat(h, g_h))  - dgl/model/models.py:182-184 - without materialising the concat:
+    y_v = Wc[:, :F] h_v + Wc[:, F:] g_v + bc per node (a [F x 2F] . [2F x P] product per robot)."""
+
+    @staticmethod
+    def forward(ctx, h, gh, wc, bc):
+        h, gh = h.contiguous(), gh.contiguous()
+        y, wc2, ctx.tc = _compress_forward(h, gh, wc, bc)
         ctx.save_for_backward(h, gh, wc2)
         ctx.wshape = tuple(wc.shape)
         return y
@@ -290,52 +347,78 @@ class CompressFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         h, gh, wc2 = ctx.saved_tensors
-        dy = dy.contiguous()
-        n, f = h.shape[0], h.shape[1]
-        _, p = _row_shape(h)
-        fo = wc2.shape[0]
-        dev = dy.device
-        f32 = dict(dtype=torch.float32, device=dev)
-        dh = dgh = dwc = dbc = None
-        tc_dx = ctx.tc and f % 128 == 0 and fo % 64 == 0
-        tc_dw = ctx.tc and f % 256 == 0 and fo % 128 == 0
-        with torch.cuda.device(dev):
-            if tc_dx and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
-                wt = _cast_w(wc2, transpose=True)               # [2F, Fo] K-major: dX_v = Wc^T . dY_v
-                dh, dgh = torch.empty_like(h), torch.empty_like(gh)
-                with _lib.timed("compress_dx", 2.0 * fo * 2 * f * n * p):
-                    check(lib().rgnn_tc_conv1x1(ptr(wt), ptr(dy), fo, None, 0, ptr(dh), f, ptr(dgh), f, None, n, stream()), "rgnn_tc_conv1x1")
-            if tc_dw and ctx.needs_input_grad[2]:
-                dwc = torch.empty((fo, 2 * f), **f32)
-                split = _tc_splits((fo // 128) * (2 * f // 256), n)
-                partial = torch.empty((split, fo, 2 * f), **f32)
-                with _lib.timed("compress_dw", 2.0 * fo * 2 * f * n * p):
-                    check(lib().rgnn_tc_conv1x1_wgrad(ptr(dy), fo, ptr(h), f, ptr(gh), f, ptr(dwc), 2 * f, ptr(partial), split, n, stream()),
-                          "rgnn_tc_conv1x1_wgrad")
-                dwc = dwc.reshape(ctx.wshape)
-            if p == 1:
-                sb, sc, bt, nn = (0, 0, 1, fo), (0, 1, f), 1, n
-            else:
-                sb, sc, bt, nn = (fo * p, 0, p, 1), (f * p, p, 1), n, p
-            if ctx.needs_input_grad[0] and dh is None:
-                dh = torch.empty_like(h)
-                _gemm(wc2, (0, 0, 1, 2 * f), dy, sb, dh, sc, f, nn, fo, batch=bt, tag="compress_dx")
-            if ctx.needs_input_grad[1] and dgh is None:
-                dgh = torch.empty_like(gh)
-                _gemm(wc2[:, f:], (0, 0, 1, 2 * f), dy, sb, dgh, sc, f, nn, fo, batch=bt, tag="compress_dx")
-            if ctx.needs_input_grad[2] and dwc is None:
-                dwc = torch.empty((fo, 2 * f), **f32)
-                split = _splits(((fo + 63) // 64) * ((f + 63) // 64), n)
-                partial = torch.empty((split, fo, f), **f32) if split > 1 else None
-                for half, src in ((0, h), (1, gh)):
-                    # dWc[o, k2] = sum_v sum_p dy[v,o,p] * src[v,k2,p]: K = P per node, reduced over the N nodes
-                    _gemm(dy, (0, fo * p, p, 1), src, (0, f * p, 1, p), dwc[:, half * f:], (0, 2 * f, 1), fo, f, p,
-                          red=n, split=split, partial=partial, tag="compress_dw")
-                dwc = dwc.reshape(ctx.wshape)
-            if ctx.needs_input_grad[3]:
-                dbc = torch.empty((fo,), **f32)
-                check(lib().rgnn_reduce_sum(dtype_code(dy), ptr(dy), n, fo * p, fo, p, p, 1, ptr(dbc), stream()), "rgnn_reduce_sum")
-        return dh, dgh, dwc, dbc
+        dh, dgh, dwc, dbc = _compress_backward(dy.contiguous(), h, gh, wc2, ctx.tc, *ctx.needs_input_grad)
+        return dh, dgh, (dwc.reshape(ctx.wshape) if dwc is not None else None), dbc
+
+
+def _film_backward(ix, h, dagg, z, addend, fuse_sig, ldd=None, ldadd=None, dh=None):
+    """dh (= addend + transposed FiLM gather of dagg) and dz; one fused staged kernel when the batch allows, else two.
+    dagg / addend may be channel-halves of a wider buffer (node strides ldd / ldadd); dh defaults to in-place on addend."""
+    f, p = _row_shape(h)
+    ldd = f * p if ldd is None else ldd
+    ldadd = f * p if ldadd is None else ldadd
+    if dh is None:
+        dh = addend if addend is not None else torch.empty_like(h)
+    dz = torch.empty_like(z)
+    nbytes = h.element_size() * (ix.N * f * p * (3 + (addend is not None)) + 2 * ix.E * 2 * f)
+    with _lib.timed("film_backward", nbytes):
+        rc = lib().rgnn_film_backward(dtype_code(h), ptr(h), f * p, ptr(dagg), ldd, ptr(z), int(fuse_sig), ptr(addend), ldadd,
+                                      ptr(dh), f * p, ptr(dz), ptr(ix.inv_in_deg), ptr(ix.ptr32), ptr(ix.idx32), ptr(ix.noff32),
+                                      ix.G, ix.max_nodes, ix.max_edges, ix.N, ix.E, f, p, stream())
+    if rc == -4:      # RGNN_E_UNSUPPORTED: general graphs / ragged rows -> the two global-gather kernels
+        _aggregate(ix, dagg, z, False, ix.inv_in_deg, _lib.POST_NONE, None, addend, dh, None, True, ldx=ldd, ldadd=ldadd, shape=(f, p))
+        check(lib().rgnn_film_edge_grad(dtype_code(h), ptr(h), f * p, ptr(dagg), ldd, ptr(z), int(fuse_sig), ptr(ix.inv_in_deg),
+                                        ptr(ix.src32), ptr(ix.dst32), ptr(dz), ix.E, f, p, stream()), "rgnn_film_edge_grad")
+    else:
+        check(rc, "rgnn_film_backward")
+    return dh, dz
+
+
+class GNNLayerFn(torch.autograd.Function):
+    """One whole layer of the reference's GNN slice as a single autograd node (dgl/model/models.py:181-184 / :186-189):
+        z = edge_encoder(pose);  g_h = FiLM-mean(h, z);  y = Conv2d(2F,F,1)(cat(h, g_h)).
+    Fusing the node lets the backward (i) add the direct and the aggregated parts of dh inside the aggregation kernel,
+    (ii) apply the sigmoid derivative where dgamma/dbeta are produced, (iii) keep every intermediate in its kernel dtype."""
+
+    @staticmethod
+    def forward(ctx, h, pose, w1, b1, w2, b2, wc, bc, g):
+        ix = g.index()
+        _lib.require_cuda(h, pose)
+        h = h.contiguous()
+        if h.shape[0] != ix.N:
+            raise ValueError(f"feature rows ({h.shape[0]}) != graph nodes ({ix.N})")
+        if pose.shape[0] != ix.E:
+            raise ValueError(f"pose rows ({pose.shape[0]}) != graph edges ({ix.E})")
+        pose, w2f, a1, z = _edge_mlp_forward(pose, w1, b1, w2, b2, h.dtype)
+        if z.shape[1] != 2 * h.shape[1]:
+            raise ValueError("edge encoder width does not match the feature maps")
+        gh = torch.empty_like(h)
+        with torch.cuda.device(h.device):
+            _aggregate(ix, h, z, True, None, _lib.POST_MEAN, None, None, gh, None, False)
+        y, wc2, ctx.tc = _compress_forward(h, gh, wc, bc)
+        ctx.g, ctx.wshape = g, tuple(wc.shape)
+        ctx.save_for_backward(h, pose, w2f, a1, z, gh, wc2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, pose, w2f, a1, z, gh, wc2 = ctx.saved_tensors
+        ix = ctx.g.index()
+        need = ctx.needs_input_grad
+        need_edge = any(need[2:6])
+        dh_direct, dgh, dwc, dbc = _compress_backward(dy.contiguous(), h, gh, wc2, ctx.tc, need[0], need[0] or need_edge, need[6], need[7])
+        dh = dw1 = db1 = dw2 = db2 = None
+        with torch.cuda.device(dy.device):
+            if need[0] or need_edge:
+                dh, dzp = _film_backward(ix, h, dgh, z, dh_direct, True)
+                if need_edge:
+                    dw1, db1, dw2, db2 = edge_mlp_param_grads(pose, w2f, a1, dzp)
+        return (dh if need[0] else None, None, dw1, db1, dw2, db2,
+                dwc.reshape(ctx.wshape) if dwc is not None else None, dbc, None)
+
+
+def gnn_layer(g, h, pose, w1, b1, w2, b2, wc, bc):
+    return GNNLayerFn.apply(h, pose, w1, b1, w2, b2, wc, bc, g)
 
 
 def compress(h, gh, wc, bc):
