@@ -87,6 +87,13 @@ int rgnn_build_batched_csr(const int64_t* src, const int64_t* dst, int64_t num_n
                            int64_t* out_ptr, int64_t* out_dst, int64_t* out_eid,
                            int32_t* ptr32, int32_t* idx32, float* norm, int32_t* status, void* stream);
 
+/* ---- A1: topology check -------------------------------------------------------------------------------------
+ * ORs 2 into *status (device int32) unless src/dst (global ids, [E]) are exactly num_graphs complete directed
+ * `robots`-node graphs without self loops in the reference's edge order: eid(i->j) = i*(K-1) + (j<i ? j : j-1)
+ * (dgl/dataloader.py:88-95).  Validates the complete_k fast path of rgnn_aggregate / rgnn_film_backward. */
+int rgnn_check_complete(const int64_t* src, const int64_t* dst, int64_t num_graphs, int64_t robots, int64_t num_edges,
+                        int32_t* status, void* stream);
+
 /* ---- A5/A6 (+A10, A11): fused gather -> FiLM / normalise -> sum|mean ----------------------
  * out[v,c,p] = post_v( sum_{i in [ptr[v],ptr[v+1])} ( gamma(eid_i,c) * nbr_scale[nbr_i] * x[nbr_i,c,p]
  *                                                    + beta(eid_i,c) ) ) + addend[v,c,p]
@@ -102,14 +109,17 @@ int rgnn_build_batched_csr(const int64_t* src, const int64_t* dst, int64_t num_n
  *   (dgl/model/models.py:182) for free.
  *   ptr32 [N+1], nbr32 [E], eid32 [E]: the in-CSR (forward) or out-CSR (backward).
  *   node_offsets32 [G+1] or NULL: batch layout enabling the shared-memory staged path; max_graph_nodes /
- *   max_graph_edges: host-known maxima over the batch (0 = unknown -> generic path). */
+ *   max_graph_edges: host-known maxima over the batch (0 = unknown -> generic path).
+ *   complete_k: K if the caller vouches that the batch is G complete directed K-robot graphs without self loops in the
+ *   reference's src-major edge order (dgl/dataloader.py:88-95; see rgnn_check_complete), else 0.  2 <= K <= 8 selects
+ *   a register-tiled kernel with the topology compiled in. */
 int rgnn_aggregate(int dtype, const void* x, int64_t ldx, const void* z, int use_beta,
                    const float* nbr_scale, int post, const float* dst_scale,
                    const void* addend, int64_t ldadd,
                    void* out, int64_t ldout, void* copy_x_to,
                    const int32_t* ptr32, const int32_t* nbr32, const int32_t* eid32,
                    const int32_t* node_offsets32, int64_t num_graphs,
-                   int64_t max_graph_nodes, int64_t max_graph_edges,
+                   int64_t max_graph_nodes, int64_t max_graph_edges, int64_t complete_k,
                    int64_t num_nodes, int64_t num_edges, int64_t feat, int64_t pix, void* stream);
 
 /* ---- A10: per-edge FiLM gradients with the sigmoid derivative fused ----------------------
@@ -130,7 +140,7 @@ int rgnn_film_edge_grad(int dtype, const void* x, int64_t ldx, const void* dagg,
 int rgnn_film_backward(int dtype, const void* h, int64_t ldh, const void* dagg, int64_t lddagg, const void* z,
                        int fuse_sigmoid_grad, const void* addend, int64_t ldadd, void* dh, int64_t lddh, void* dz,
                        const float* inv_in_deg, const int32_t* ptr32, const int32_t* idx32, const int32_t* node_offsets32,
-                       int64_t num_graphs, int64_t max_graph_nodes, int64_t max_graph_edges,
+                       int64_t num_graphs, int64_t max_graph_nodes, int64_t max_graph_edges, int64_t complete_k,
                        int64_t num_nodes, int64_t num_edges, int64_t feat, int64_t pix, void* stream);
 
 /* ---- A4 (+A10): first edge-encoder layer, K = 9 -----------------------------------------

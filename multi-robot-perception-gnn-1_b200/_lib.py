@@ -22,9 +22,10 @@ SIGNATURES = {
     "rgnn_batch_graphs": [_vp] * 4 + [_i64] * 2 + [_vp] * 5,
     "rgnn_build_batched_csr": [_vp, _vp, _i64, _i64, _vp, _vp, _i64] + [_vp] * 13,
     "rgnn_aggregate": [_i32, _vp, _i64, _vp, _i32, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp]
-                      + [_i64] * 7 + [_vp],
+                      + [_i64] * 8 + [_vp],
+    "rgnn_check_complete": [_vp, _vp, _i64, _i64, _i64, _vp, _vp],
     "rgnn_film_edge_grad": [_i32, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
-    "rgnn_film_backward": [_i32, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp] + [_i64] * 7 + [_vp],
+    "rgnn_film_backward": [_i32, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp] + [_i64] * 8 + [_vp],
     "rgnn_edge_mlp1_fwd": [_i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "rgnn_edge_mlp1_bwd": [_i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "rgnn_gemm": [_i32, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i64, _i64, _i64]

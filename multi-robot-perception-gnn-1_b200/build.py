@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librobotgnn.so")
-SOURCES = ["api.cu", "csr.cu", "aggregate.cu", "edge_mlp.cu", "gemm_simt.cu", "gemm_tc.cu"]
+SOURCES = ["api.cu", "csr.cu", "aggregate.cu", "film_complete.cu", "edge_mlp.cu", "gemm_simt.cu", "gemm_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

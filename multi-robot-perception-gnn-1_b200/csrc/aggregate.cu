@@ -449,13 +449,20 @@ __global__ void __launch_bounds__(256) k_film_edge_grad(const T* __restrict__ x,
 
 using namespace rgnn;
 
+namespace rgnn {
+int film_fwd_complete(int dtype, int K, const void* x, int64_t ldx, const void* z, void* out, int64_t ldout, void* copy_to,
+                      int64_t G, int64_t F, int64_t P, cudaStream_t st);
+int film_bwd_complete(int dtype, int K, const void* h, int64_t ldh, const void* dagg, int64_t ldd, const void* z, const void* addend,
+                      int64_t ldadd, void* dh, int64_t lddh, void* dz, int64_t G, int64_t F, int64_t P, int fuse_sig, cudaStream_t st);
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 extern "C" int rgnn_aggregate(int dtype, const void* x, int64_t ldx, const void* z, int use_beta,
                               const float* nbr_scale, int post, const float* dst_scale,
                               const void* addend, int64_t ldadd, void* out, int64_t ldout, void* copy_x_to,
                               const int32_t* ptr32, const int32_t* nbr32, const int32_t* eid32,
-                              const int32_t* noff32, int64_t G, int64_t max_graph_nodes, int64_t max_graph_edges,
+                              const int32_t* noff32, int64_t G, int64_t max_graph_nodes, int64_t max_graph_edges, int64_t complete_k,
                               int64_t N, int64_t E, int64_t F, int64_t P, void* stream) {
   RGNN_REQUIRE(dtype == RGNN_F32 || dtype == RGNN_BF16, RGNN_E_ARG, "rgnn_aggregate: bad dtype %d", dtype);
   RGNN_REQUIRE(N >= 0 && E >= 0 && F > 0 && P > 0, RGNN_E_ARG, "rgnn_aggregate: bad sizes N=%lld E=%lld F=%lld P=%lld",
@@ -485,6 +492,11 @@ extern "C" int rgnn_aggregate(int dtype, const void* x, int64_t ldx, const void*
     else k_agg_generic<__nv_bfloat16, 1><<<(unsigned)blocks, 256, 0, st>>>(p);
     RGNN_LAUNCH_CHECK("k_agg_generic<1>");
     return 0;
+  }
+  // ---- complete K-robot graphs (the reference's topology): register-tiled kernel, no CSR walk
+  if (complete_k >= 2 && complete_k <= 8 && post == RGNN_POST_MEAN && !nbr_scale && !addend && N == G * complete_k &&
+      E == G * complete_k * (complete_k - 1) && (!z || (reinterpret_cast<uintptr_t>(z) & (2 * es - 1)) == 0) && use_beta) {
+    return film_fwd_complete(dtype, (int)complete_k, x, ldx, z, out, ldout, copy_x_to, G, F, P, st);
   }
   // ---- staged path: needs the batch layout and every graph's tile + CSR slice to fit shared memory
   const int maxK = (int)max_graph_nodes, maxE = (int)max_graph_edges;
@@ -569,7 +581,7 @@ extern "C" int rgnn_film_edge_grad(int dtype, const void* x, int64_t ldx, const 
 extern "C" int rgnn_film_backward(int dtype, const void* h, int64_t ldh, const void* dagg, int64_t lddagg, const void* z,
                                   int fuse_sigmoid_grad, const void* addend, int64_t ldadd, void* dh, int64_t lddh, void* dz,
                                   const float* inv_in_deg, const int32_t* ptr32, const int32_t* idx32, const int32_t* noff32,
-                                  int64_t G, int64_t max_graph_nodes, int64_t max_graph_edges,
+                                  int64_t G, int64_t max_graph_nodes, int64_t max_graph_edges, int64_t complete_k,
                                   int64_t N, int64_t E, int64_t F, int64_t P, void* stream) {
   RGNN_REQUIRE(dtype == RGNN_F32 || dtype == RGNN_BF16, RGNN_E_ARG, "rgnn_film_backward: bad dtype %d", dtype);
   RGNN_REQUIRE(N >= 0 && E >= 0 && G >= 0 && F > 0 && P > 0, RGNN_E_ARG, "rgnn_film_backward: bad sizes");
@@ -584,6 +596,9 @@ extern "C" int rgnn_film_backward(int dtype, const void* h, int64_t ldh, const v
                   ldh % vec == 0 && lddagg % vec == 0 && lddh % vec == 0 && (!addend || ldadd % vec == 0) &&
                   (2 * F * es) % 16 == 0 && F % (8 / es) == 0 && F * P < (1ll << 31);
   RGNN_REQUIRE(ok, RGNN_E_UNSUPPORTED, "rgnn_film_backward: shape/alignment not covered by the staged kernel");
+  if (complete_k >= 2 && complete_k <= 8 && N == G * complete_k && E == G * complete_k * (complete_k - 1))
+    return film_bwd_complete(dtype, (int)complete_k, h, ldh, dagg, lddagg, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sigmoid_grad,
+                             as_stream(stream));
   const int zalign = 8 / es;
   const int64_t row_bytes_per_ch = P * es;
   const int idx_bytes = (int)(((2 * (maxK + 1) + 4 * (int64_t)maxE + maxK) * 4 + 15) / 16 * 16);

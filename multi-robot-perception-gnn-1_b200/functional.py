@@ -38,7 +38,7 @@ def _aggregate(ix, x, z, use_beta, nbr_scale, post, dst_scale, addend, out, copy
                                ptr(dst_scale), ptr(addend), row if ldadd is None else ldadd, ptr(out),
                                row if ldout is None else ldout, ptr(copy_to),
                                ptr(ptr32), ptr(nbr), ptr(eid), ptr(ix.noff32), ix.G, ix.max_nodes, ix.max_edges,
-                               ix.N, ix.E, f, p, stream()), "rgnn_aggregate")
+                               0 if transposed else ix.complete_k, ix.N, ix.E, f, p, stream()), "rgnn_aggregate")
     return out
 
 
@@ -364,7 +364,7 @@ def _film_backward(ix, h, dagg, z, addend, fuse_sig, ldd=None, ldadd=None, dh=No
     with _lib.timed("film_backward", nbytes):
         rc = lib().rgnn_film_backward(dtype_code(h), ptr(h), f * p, ptr(dagg), ldd, ptr(z), int(fuse_sig), ptr(addend), ldadd,
                                       ptr(dh), f * p, ptr(dz), ptr(ix.inv_in_deg), ptr(ix.ptr32), ptr(ix.idx32), ptr(ix.noff32),
-                                      ix.G, ix.max_nodes, ix.max_edges, ix.N, ix.E, f, p, stream())
+                                      ix.G, ix.max_nodes, ix.max_edges, ix.complete_k, ix.N, ix.E, f, p, stream())
     if rc == -4:      # RGNN_E_UNSUPPORTED: general graphs / ragged rows -> the two global-gather kernels
         _aggregate(ix, dagg, z, False, ix.inv_in_deg, _lib.POST_NONE, None, addend, dh, None, True, ldx=ldd, ldadd=ldadd, shape=(f, p))
         check(lib().rgnn_film_edge_grad(dtype_code(h), ptr(h), f * p, ptr(dagg), ldd, ptr(z), int(fuse_sig), ptr(ix.inv_in_deg),

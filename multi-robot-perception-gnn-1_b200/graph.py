@@ -22,7 +22,7 @@ class RobotGraph:
     CSR index are produced on the device on first use and cached.
     """
 
-    def __init__(self, local_src, local_dst, batch_num_nodes, batch_num_edges):
+    def __init__(self, local_src, local_dst, batch_num_nodes, batch_num_edges, complete_k=0):
         self._lsrc = local_src.to(torch.int64).reshape(-1)
         self._ldst = local_dst.to(torch.int64).reshape(-1)
         self._bnn = [int(v) for v in batch_num_nodes]
@@ -31,6 +31,10 @@ class RobotGraph:
             raise ValueError("edge arrays do not match batch_num_edges")
         self._n, self._e = sum(self._bnn), sum(self._bne)
         self.ndata, self.edata = {}, {}
+        # K if every graph is the reference's complete K-robot topology in its edge order (dataloader.py:88-95), else 0.
+        # Established on the host where the edge lists are host data (graph(), robot_batch()); a claim on device data
+        # is verified on the device by rgnn_check_complete and reported by validate().
+        self.complete_k = int(complete_k) if complete_k and all(n == complete_k for n in self._bnn) else 0
         self._global = None   # (src, dst, node_offsets, edge_offsets) on self.device
         self._index = None
 
@@ -98,7 +102,7 @@ class RobotGraph:
             src, dst, noff, eoff = self._globals()
             n, e, g = self._n, self._e, len(self._bnn)
             i64 = lambda k: torch.empty(k, dtype=torch.int64, device=dev)
-            ix = SimpleNamespace(N=n, E=e, G=g, max_nodes=max(self._bnn, default=0), max_edges=max(self._bne, default=0),
+            ix = SimpleNamespace(N=n, E=e, G=g, complete_k=self.complete_k if 2 <= self.complete_k <= 8 else 0, max_nodes=max(self._bnn, default=0), max_edges=max(self._bne, default=0),
                                  src=src, dst=dst, node_offsets=noff, edge_offsets=eoff,
                                  in_deg=i64(n), out_deg=i64(n), in_ptr=i64(n + 1), in_src=i64(e), in_eid=i64(e),
                                  out_ptr=i64(n + 1), out_dst=i64(e), out_eid=i64(e),
@@ -113,6 +117,9 @@ class RobotGraph:
                     _lib.ptr(ix.out_ptr), _lib.ptr(ix.out_dst), _lib.ptr(ix.out_eid),
                     _lib.ptr(ix.ptr32), _lib.ptr(ix.idx32), _lib.ptr(ix.norm), _lib.ptr(ix.status), _lib.stream()),
                     "rgnn_build_batched_csr")
+                if ix.complete_k:
+                    _lib.check(_lib.lib().rgnn_check_complete(_lib.ptr(src), _lib.ptr(dst), g, ix.complete_k, e, _lib.ptr(ix.status),
+                                                              _lib.stream()), "rgnn_check_complete")
             ix.in_ptr32, ix.out_ptr32 = ix.ptr32[: n + 1], ix.ptr32[n + 1: 2 * (n + 1)]
             ix.noff32 = ix.ptr32[2 * (n + 1):]
             ix.in_src32, ix.in_eid32 = ix.idx32[0:e], ix.idx32[e: 2 * e]
@@ -124,8 +131,11 @@ class RobotGraph:
 
     def validate(self):
         """Host-synchronising check that no edge leaves its graph (DGL raises at construction time)."""
-        if int(self.index().status.item()) != 0:
+        st = int(self.index().status.item())
+        if st & 1:
             raise ValueError("an edge references a node outside its graph")
+        if st & 2:
+            raise ValueError("graph was declared complete_k but its edge list is not the reference's complete-graph enumeration")
         return self
 
     def in_degrees(self):
@@ -141,7 +151,7 @@ class RobotGraph:
         if device == self.device:
             return self
         g = RobotGraph(self._lsrc.to(device, non_blocking=non_blocking), self._ldst.to(device, non_blocking=non_blocking),
-                       self._bnn, self._bne)
+                       self._bnn, self._bne, self.complete_k)
         g.ndata = {k: v.to(device, non_blocking=non_blocking) for k, v in self.ndata.items()}
         g.edata = {k: v.to(device, non_blocking=non_blocking) for k, v in self.edata.items()}
         return g
@@ -205,7 +215,17 @@ def graph(data, num_nodes=None, device=None, **_):
         num_nodes = int(max(src.max().item(), dst.max().item())) + 1 if src.numel() else 0
     elif src.numel() and not src.is_cuda and int(max(src.max().item(), dst.max().item())) >= num_nodes:
         raise ValueError("edge endpoint >= num_nodes")
-    return RobotGraph(src, dst, [num_nodes], [src.numel()])
+    return RobotGraph(src, dst, [num_nodes], [src.numel()], _host_complete_k(src, dst, num_nodes))
+
+
+def _host_complete_k(src, dst, k):
+    """K if the (host) edge list is the reference's complete-graph enumeration, else 0.  Device lists are not inspected."""
+    if src.is_cuda or k < 2 or src.numel() != k * (k - 1):
+        return 0
+    ii = torch.arange(k).repeat_interleave(k)
+    jj = torch.arange(k).repeat(k)
+    keep = ii != jj
+    return k if torch.equal(src, ii[keep]) and torch.equal(dst, jj[keep]) else 0
 
 
 def batch(graphs):
@@ -219,7 +239,8 @@ def batch(graphs):
         if set(g.ndata) != keys_n or set(g.edata) != keys_e:
             raise ValueError("all graphs must carry the same ndata/edata keys")
     bg = RobotGraph(torch.cat([g._lsrc for g in graphs]), torch.cat([g._ldst for g in graphs]),
-                    [n for g in graphs for n in g._bnn], [e for g in graphs for e in g._bne])
+                    [n for g in graphs for n in g._bnn], [e for g in graphs for e in g._bne],
+                    graphs[0].complete_k if all(g.complete_k == graphs[0].complete_k for g in graphs) else 0)
     for k in graphs[0].ndata:
         bg.ndata[k] = torch.cat([g.ndata[k] for g in graphs], 0)
     for k in graphs[0].edata:
@@ -237,5 +258,5 @@ def robot_batch(num_graphs, num_robots, device=None):
     s, d = ii[keep].to(torch.int64), jj[keep].to(torch.int64)
     g = RobotGraph(s.repeat(num_graphs).to(device) if device else s.repeat(num_graphs),
                    d.repeat(num_graphs).to(device) if device else d.repeat(num_graphs),
-                   [k] * num_graphs, [k * (k - 1)] * num_graphs)
+                   [k] * num_graphs, [k * (k - 1)] * num_graphs, complete_k=k)
     return g

@@ -227,22 +227,52 @@ def test_block_vs_oracle(R, dtype, tol, g_, k, f, comp, multi):
             assert nerr(conv.bias.grad, l["bc"].grad) <= gtol
 
 
-def test_staged_and_generic_paths_agree(R):
-    """The shared-memory staged kernel and the global gather kernel must produce identical bits."""
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("k,f", [(5, 48), (3, 64), (8, 32)])
+def test_three_aggregation_paths_agree(R, dtype, k, f):
+    """complete-graph register kernel, shared-memory staged kernel and global gather kernel: forward bits identical in fp32
+    (all keep the reference's rounding order), backward within tolerance; bf16 within 2e-2 of the fp64 oracle."""
     from oracle import gnn_oracle as O
-    sb = O.synthetic_batch(7, 5, 48, p=64, seed=9)
-    g = R.robot_batch(7, 5, device="cuda")
-    h = sb["h"].cuda()
-    z = torch.rand((g.num_edges(), 96), generator=torch.Generator().manual_seed(1)).cuda()
-    a = R.film_mean(g, h, z)
-    ix = g.index()
-    keep = ix.max_nodes
-    ix.max_nodes = 0            # disables the staged path
-    b = R.film_mean(g, h, z)
-    ix.max_nodes = keep
-    assert torch.equal(a, b)
-    ref = O.film_mean(sb["h"], z.cpu(), sb["src"], sb["dst"])
-    assert torch.equal(a.cpu(), ref)
+    gN = 7
+    sb = O.synthetic_batch(gN, k, f, p=64, seed=9)
+    z32 = torch.rand((gN * k * (k - 1), 2 * f), generator=torch.Generator().manual_seed(1))
+    dout32 = torch.randn((gN * k, f, 64), generator=torch.Generator().manual_seed(2))
+    res = []
+    for mode in ("complete", "staged", "generic"):
+        g = R.robot_batch(gN, k, device="cuda")
+        ix = g.index()
+        assert ix.complete_k == k
+        if mode != "complete":
+            ix.complete_k = 0
+        if mode == "generic":
+            ix.max_nodes = 0
+        h = sb["h"].cuda().to(dtype).requires_grad_()
+        z = z32.cuda().to(dtype).requires_grad_()
+        a = R.film_mean(g, h, z)
+        a.backward(dout32.cuda().to(dtype))
+        res.append((a.detach().float(), h.grad.float(), z.grad.float()))
+    ho, zo = sb["h"].double().requires_grad_(), z32.double().requires_grad_()
+    ref = O.film_mean(ho, zo, sb["src"], sb["dst"])
+    ref.backward(dout32.double())
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    for a, dh, dz in res:
+        if dtype == torch.float32:
+            assert torch.equal(a, res[0][0])
+            assert torch.equal(a.cpu(), O.film_mean(sb["h"], z32, sb["src"], sb["dst"]))       # bit-exact vs the fp32 oracle
+        assert nerr(a, ref) <= tol and nerr(dh, ho.grad) <= tol and nerr(dz, zo.grad) <= tol
+
+
+def test_false_completeness_claim_is_caught(R):
+    s = torch.tensor([0, 1, 0, 2, 1, 2]).cuda()     # a 3-robot graph whose edges are NOT in the reference enumeration
+    d = torch.tensor([1, 0, 2, 0, 2, 1]).cuda()
+    g = R.RobotGraph(s, d, [3], [6], complete_k=3)
+    with pytest.raises(ValueError, match="complete"):
+        g.validate()
+    ok = R.robot_batch(4, 3, device="cuda")
+    ok.validate()
+    host = R.graph(([0, 0, 1, 1, 2, 2], [1, 2, 0, 2, 0, 1]))       # host lists: detected on the host
+    assert host.complete_k == 3 and R.graph(([0, 1], [1, 2])).complete_k == 0
+    assert R.batch([host, host]).complete_k == 3
 
 
 def test_copy_u_mean_variant(R):
