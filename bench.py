@@ -25,6 +25,7 @@ import torch  # noqa: E402
 
 F_DIM, K_ROBOTS, PIX = 512, 5, 64
 METRIC = "gnn_layer_fwd_bwd_robot_graphs_per_sec"
+MEM_KERNELS = ("aggregate", "film_", "bias_grad")      # HBM-bound kernel families (the rest are tensor-pipe GEMMs)
 
 
 def parse():
@@ -247,13 +248,13 @@ def main():
     by_time = sorted(prof.items(), key=lambda kv: -kv[1]["ms_total"])
     kernels = {}
     for name, d in prof.items():
-        is_mem = name.startswith(("aggregate", "film_edge"))
+        is_mem = name.startswith(MEM_KERNELS)
         ach = d["work_total"] / (d["ms_total"] * 1e-3) / (1e9 if is_mem else 1e12) if d["ms_total"] > 0 else 0.0
         kernels[name] = {"calls": d["calls"], "ms_avg": round(d["ms_avg"], 4), "share": round(d["ms_total"] / ms_total, 4),
                          "achieved": round(ach, 2), "unit": "GB/s" if is_mem else "TFLOP/s",
                          "frac": round(ach / (hbm_peak if is_mem else tc_peak), 4)}
     top, topd = by_time[0]
-    top_mem = top.startswith(("aggregate", "film_edge"))
+    top_mem = top.startswith(MEM_KERNELS)
     roofline = {"kernel": top, "bound": "hbm" if top_mem else "tensor", "achieved": kernels[top]["achieved"],
                 "peak": hbm_peak if top_mem else tc_peak, "unit": kernels[top]["unit"], "frac": kernels[top]["frac"],
                 "traffic": None, "peak_source": peak_src, "ms_avg_per_launch": kernels[top]["ms_avg"]}

@@ -596,9 +596,11 @@ extern "C" int rgnn_film_backward(int dtype, const void* h, int64_t ldh, const v
                   ldh % vec == 0 && lddagg % vec == 0 && lddh % vec == 0 && (!addend || ldadd % vec == 0) &&
                   (2 * F * es) % 16 == 0 && F % (8 / es) == 0 && F * P < (1ll << 31);
   RGNN_REQUIRE(ok, RGNN_E_UNSUPPORTED, "rgnn_film_backward: shape/alignment not covered by the staged kernel");
-  if (complete_k >= 2 && complete_k <= 8 && N == G * complete_k && E == G * complete_k * (complete_k - 1))
-    return film_bwd_complete(dtype, (int)complete_k, h, ldh, dagg, lddagg, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sigmoid_grad,
-                             as_stream(stream));
+  if (complete_k >= 2 && complete_k <= 8 && N == G * complete_k && E == G * complete_k * (complete_k - 1)) {
+    const int rc = film_bwd_complete(dtype, (int)complete_k, h, ldh, dagg, lddagg, z, addend, ldadd, dh, lddh, dz, G, F, P,
+                                     fuse_sigmoid_grad, as_stream(stream));
+    if (rc != RGNN_E_UNSUPPORTED) return rc;
+  }
   const int zalign = 8 / es;
   const int64_t row_bytes_per_ch = P * es;
   const int idx_bytes = (int)(((2 * (maxK + 1) + 4 * (int64_t)maxE + maxK) * 4 + 15) / 16 * 16);

@@ -74,19 +74,50 @@ __global__ void __launch_bounds__(256) k_film_fwd_complete(const T* __restrict__
   }
 }
 
+// Reduce-scatter of NV per-lane partial sums over the LPC lanes that share a channel: after log2(LPC) steps lane l holds the
+// fully reduced values with ids  i + sum_s bit_s(l) * (NVP >> (s+1)),  i < NVP/LPC.  NVP/2 + NVP/4 + ... shuffles instead of
+// NV*log2(LPC), every step's shuffles independent of each other (latency hidden by ILP, not by occupancy).
+template <int NVP, int LPC>
+__device__ __forceinline__ void reduce_scatter(float (&a)[NVP], int l) {
+  static_assert(NVP % LPC == 0, "pad the value count to a multiple of the lane group");
+  if constexpr (LPC > 1) {
+    constexpr int H = NVP / 2;
+    const bool up = (l & (LPC / 2)) != 0;
+    float b[H];
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      const float send = up ? a[i] : a[i + H];
+      const float keep = up ? a[i + H] : a[i];
+      b[i] = keep + __shfl_xor_sync(0xffffffffu, send, LPC / 2);
+    }
+    reduce_scatter<H, LPC / 2>(b, l);
+#pragma unroll
+    for (int i = 0; i < H / (LPC / 2); ++i) a[i] = b[i];
+  }
+}
+template <int NVP, int LPC> __device__ __forceinline__ int scattered_id(int i, int l) {
+  int id = i, h = NVP / 2;
+#pragma unroll
+  for (int o = LPC / 2; o > 0; o >>= 1) { if (l & o) id += h; h >>= 1; }
+  return id;
+}
+
 // dh[u] = addend[u] + w * sum_{a != u} gamma[e(u,a)] * dagg[a];  dz[e(u,a)] = sig' * w * (sum_p h[u] dagg[a], sum_p dagg[a]);  w = 1/(K-1)
-template <typename T, int K>
+// LPC = P / VEC lanes share one channel (compile time).
+template <typename T, int K, int LPC>
 __global__ void __launch_bounds__(256) k_film_bwd_complete(const T* __restrict__ h, int64_t ldh, const T* __restrict__ dagg, int64_t ldd,
                                                            const T* __restrict__ z, const T* addend, int64_t ldadd,
                                                            T* dh, int64_t lddh, T* __restrict__ dz,
                                                            int64_t G, int F, int P, int fuse_sig) {
   constexpr int VEC = Vec16<T>::N;
-  const int lpc = P / VEC;                       // lanes sharing one channel: power of two <= 32 (host-checked)
-  const int64_t row_vecs = (int64_t)F * lpc;
+  constexpr int NE = K * (K - 1);
+  constexpr int NVP = (NE + LPC - 1) / LPC * LPC;
+  const int64_t row_vecs = (int64_t)F * LPC;
   const int64_t total = G * row_vecs;
   const float w = 1.0f / (K - 1);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t rounds = (total + stride - 1) / stride;
+  const int l = threadIdx.x % LPC;
   for (int64_t r = 0; r < rounds; ++r) {         // whole warps iterate together (shuffles below)
     const int64_t t = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < total;
@@ -94,7 +125,8 @@ __global__ void __launch_bounds__(256) k_film_bwd_complete(const T* __restrict__
     const int64_t g = tt / row_vecs;
     const int64_t off = (tt - g * row_vecs) * VEC;
     const int c = (int)(off / P);
-    const int64_t n0 = g * K, e0 = g * (K * (K - 1));
+    const int64_t n0 = g * K, e0 = g * NE;
+    const T* zc = z + e0 * 2 * F + 2 * c;
     float hv[K][VEC], dv[K][VEC];
 #pragma unroll
     for (int u = 0; u < K; ++u) {
@@ -104,16 +136,7 @@ __global__ void __launch_bounds__(256) k_film_bwd_complete(const T* __restrict__
         for (int q = 0; q < VEC; ++q) { hv[u][q] = 0.f; dv[u][q] = 0.f; }
       }
     }
-    float sd[K];
-#pragma unroll
-    for (int a = 0; a < K; ++a) {
-      float s = 0.f;
-#pragma unroll
-      for (int q = 0; q < VEC; ++q) s += dv[a][q];
-      for (int o = lpc >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      sd[a] = s;
-    }
-    const bool leader = live && (t % lpc) == 0;
+    // ---- dh: needs every gamma of the graph for this channel (the LPC lanes of a channel read the same 4/8 bytes: broadcast)
 #pragma unroll
     for (int u = 0; u < K; ++u) {
       float acc[VEC];
@@ -122,17 +145,9 @@ __global__ void __launch_bounds__(256) k_film_bwd_complete(const T* __restrict__
 #pragma unroll
       for (int a = 0; a < K; ++a) {
         if (a == u) continue;
-        const int64_t zi = (e0 + edge_id(K, u, a)) * 2 * F + 2 * c;
-        const float2 gb = live ? ldg_pair<T>(z + zi) : make_float2(0.f, 0.f);
-        float sxd = 0.f;
+        const float gam = live ? ldg_pair<T>(zc + (int64_t)edge_id(K, u, a) * 2 * F).x : 0.f;
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) { acc[q] = fmaf(gb.x, dv[a][q], acc[q]); sxd = fmaf(hv[u][q], dv[a][q], sxd); }
-        for (int o = lpc >> 1; o > 0; o >>= 1) sxd += __shfl_xor_sync(0xffffffffu, sxd, o);
-        if (leader) {
-          float dg = sxd * w, db = sd[a] * w;
-          if (fuse_sig) { dg *= gb.x * (1.f - gb.x); db *= gb.y * (1.f - gb.y); }
-          st_pair<T>(dz + zi, dg, db);
-        }
+        for (int q = 0; q < VEC; ++q) acc[q] = fmaf(gam, dv[a][q], acc[q]);
       }
       if (live) {
         if (addend) {
@@ -145,6 +160,54 @@ __global__ void __launch_bounds__(256) k_film_bwd_complete(const T* __restrict__
           for (int q = 0; q < VEC; ++q) acc[q] *= w;
         }
         Vec16<T>::store(dh + (n0 + u) * lddh + off, acc);
+      }
+    }
+    // ---- dz: per-lane partial pixel sums, then one reduce-scatter over the lane group
+    float sd[K];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) s += dv[a][q];
+      sd[a] = s;
+    }
+#pragma unroll
+    for (int o = LPC / 2; o > 0; o >>= 1) {      // all-reduce of the K destination sums (independent chains)
+#pragma unroll
+      for (int a = 0; a < K; ++a) sd[a] += __shfl_xor_sync(0xffffffffu, sd[a], o);
+    }
+    float pg[NVP];
+#pragma unroll
+    for (int e = 0; e < NVP; ++e) pg[e] = 0.f;
+#pragma unroll
+    for (int u = 0; u < K; ++u)
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+        if (a == u) continue;
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) s = fmaf(hv[u][q], dv[a][q], s);
+        pg[edge_id(K, u, a)] = s;
+      }
+    reduce_scatter<NVP, LPC>(pg, l);
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < NVP / LPC; ++i) {
+        const int e = scattered_id<NVP, LPC>(i, l);
+        if (e < NE) {
+          const int u = e / (K - 1), jj = e % (K - 1);
+          const int a = jj < u ? jj : jj + 1;
+          float sda = sd[0];
+#pragma unroll
+          for (int q = 1; q < K; ++q) sda = (a == q) ? sd[q] : sda;
+          const int64_t zi = (int64_t)e * 2 * F;
+          float dg = pg[i] * w, db = sda * w;
+          if (fuse_sig) {
+            const float2 gb = ldg_pair<T>(zc + zi);
+            dg *= gb.x * (1.f - gb.x); db *= gb.y * (1.f - gb.y);
+          }
+          st_pair<T>(dz + e0 * 2 * F + 2 * c + zi, dg, db);
+        }
       }
     }
   }
@@ -164,18 +227,32 @@ static int launch_fwd(int K, const T* x, int64_t ldx, const T* z, T* out, int64_
   return 0;
 }
 
-template <typename T>
-static int launch_bwd(int K, const T* h, int64_t ldh, const T* dagg, int64_t ldd, const T* z, const T* addend, int64_t ldadd, T* dh,
-                      int64_t lddh, T* dz, int64_t G, int F, int P, int fuse_sig, cudaStream_t st) {
+template <typename T, int LPC>
+static int launch_bwd_lpc(int K, const T* h, int64_t ldh, const T* dagg, int64_t ldd, const T* z, const T* addend, int64_t ldadd, T* dh,
+                          int64_t lddh, T* dz, int64_t G, int F, int P, int fuse_sig, cudaStream_t st) {
   const int64_t total = G * ((int64_t)F * P / Vec16<T>::N);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
   if (blocks < 1) return 0;
-#define RGNN_CASE(KK) case KK: k_film_bwd_complete<T, KK><<<(unsigned)blocks, 256, 0, st>>>(h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sig); break;
+#define RGNN_CASE(KK) case KK: k_film_bwd_complete<T, KK, LPC><<<(unsigned)blocks, 256, 0, st>>>(h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sig); break;
   switch (K) { RGNN_CASE(2) RGNN_CASE(3) RGNN_CASE(4) RGNN_CASE(5) RGNN_CASE(6) RGNN_CASE(7) RGNN_CASE(8) default: return RGNN_E_UNSUPPORTED; }
 #undef RGNN_CASE
   RGNN_LAUNCH_CHECK("k_film_bwd_complete");
   return 0;
+}
+
+// lane-group sizes with the topology compiled in: P/VEC in {1, 2, 4, 8, 16} (P = 64: 8 for bf16, 16 for fp32); others -> staged kernel
+template <typename T>
+static int launch_bwd(int K, const T* h, int64_t ldh, const T* dagg, int64_t ldd, const T* z, const T* addend, int64_t ldadd, T* dh,
+                      int64_t lddh, T* dz, int64_t G, int F, int P, int fuse_sig, cudaStream_t st) {
+  switch (P / Vec16<T>::N) {
+    case 1: return launch_bwd_lpc<T, 1>(K, h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sig, st);
+    case 2: return launch_bwd_lpc<T, 2>(K, h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sig, st);
+    case 4: return launch_bwd_lpc<T, 4>(K, h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sig, st);
+    case 8: return launch_bwd_lpc<T, 8>(K, h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sig, st);
+    case 16: return launch_bwd_lpc<T, 16>(K, h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sig, st);
+    default: return RGNN_E_UNSUPPORTED;
+  }
 }
 
 // Entry points used by rgnn_aggregate / rgnn_film_backward (aggregate.cu) when the caller vouches for the topology.

@@ -112,7 +112,7 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -122,8 +122,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -132,14 +136,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
-          const __grid_constant__ CUtensorMap tmB1, const TcParams p) {
+          const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmO0,
+          const __grid_constant__ CUtensorMap tmO1, const TcParams p) {
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;    // 256 or 512: power of two
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: [tiles (1024-aligned)] [barriers]
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t tiles = smem_u32(smem);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
+  constexpr uint32_t OUT_STAGE_BYTES = 128 * 128;      // one robot's [128 ch x 64 px] bf16 output slab
+  const uint32_t out_stage = tiles + NSTAGE * STAGE_BYTES;   // 2 slabs, 1024-aligned (TMA-store staging, NCHW epilogue)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES + 2 * OUT_STAGE_BYTES);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NSTAGE);
   const uint32_t bar_tfull = smem_u32(bars + 2 * NSTAGE), bar_tempty = smem_u32(bars + 2 * NSTAGE + 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
@@ -149,6 +156,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
+    if (p.epi_mode == EPI_NCHW) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO0) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO1) : "memory");
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
@@ -251,31 +262,50 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(ew * 32) << 16);
       const int64_t m = (int64_t)tm * BM + row;
       const float bias_m = (p.bias && (p.epi_flags & RGNN_EPI_BIAS_M) && m < p.M) ? p.bias[m] : 0.f;
+      if (p.epi_mode == EPI_NCHW) {
+        // row m = output channel, columns = (robot, pixel).  Per robot: 128 ch x 64 px bf16 = one contiguous 16 KB slab of the
+        // NCHW tensor -> staged in shared memory (128B-swizzled rows, conflict-free 16-byte stores) and written by ONE TMA store.
+        const bool second = m >= p.m_split;
+        const int row0 = tm * BM - (second ? p.m_split : 0);            // first channel of this tile inside its output tensor
+        const int rows_per_node = second ? (int)(p.ld1 / 64) : (int)(p.ld0 / 64);
+#pragma unroll 1
+        for (int j = 0; j < BN / 64; ++j) {
+          const int node = tn * (BN / 64) + j;
+          const uint32_t stg = out_stage + (j & 1) * OUT_STAGE_BYTES;
+          if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // slab j-2 fully read
+          epi_bar_sync();
+          uint32_t r0[32], r1[32];
+          tmem_ld32_issue(tacc + (2 * j) * 32, r0);
+          tmem_ld32_issue(tacc + (2 * j + 1) * 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t* r = q < 4 ? r0 : r1;
+            const int b = (q & 3) * 8;
+            uint32_t w0 = pack_bf16(__uint_as_float(r[b + 0]) + bias_m, __uint_as_float(r[b + 1]) + bias_m);
+            uint32_t w1 = pack_bf16(__uint_as_float(r[b + 2]) + bias_m, __uint_as_float(r[b + 3]) + bias_m);
+            uint32_t w2 = pack_bf16(__uint_as_float(r[b + 4]) + bias_m, __uint_as_float(r[b + 5]) + bias_m);
+            uint32_t w3 = pack_bf16(__uint_as_float(r[b + 6]) + bias_m, __uint_as_float(r[b + 7]) + bias_m);
+            const uint32_t addr = stg + row * 128 + ((q ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          epi_bar_sync();
+          if (ew == 0 && lane == 0) {
+            if (node < p.nodes) tma_store_2d(second ? &tmO1 : &tmO0, stg, 0, node * rows_per_node + row0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
-        tmem_ld32(tacc + c * 32, r);
+        tmem_ld32_issue(tacc + c * 32, r);
+        tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = empty ? 0.f : __uint_as_float(r[i]);
-        if (p.epi_mode == EPI_NCHW) {
-          // row m = output channel, columns = (robot, pixel); 32 columns = half a robot's 8x8 map
-          const int node = tn * (BN / 64) + (c >> 1);
-          if (node < p.nodes && m < p.M) {
-            __nv_bfloat16* o;
-            if (m < p.m_split) o = static_cast<__nv_bfloat16*>(p.out0) + (int64_t)node * p.ld0 + m * 64 + (c & 1) * 32;
-            else o = static_cast<__nv_bfloat16*>(p.out1) + (int64_t)node * p.ld1 + (m - p.m_split) * 64 + (c & 1) * 32;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 u;
-              u.x = pack_bf16(v[8 * q + 0] + bias_m, v[8 * q + 1] + bias_m);
-              u.y = pack_bf16(v[8 * q + 2] + bias_m, v[8 * q + 3] + bias_m);
-              u.z = pack_bf16(v[8 * q + 4] + bias_m, v[8 * q + 5] + bias_m);
-              u.w = pack_bf16(v[8 * q + 6] + bias_m, v[8 * q + 7] + bias_m);
-              reinterpret_cast<uint4*>(o)[q] = u;
-            }
-          }
-        } else if (p.epi_mode == EPI_ROW) {
+        if (p.epi_mode == EPI_ROW) {
           const int64_t n0 = (int64_t)tn * BN + c * 32;
           if (m < p.M && n0 < p.N) {
             if (p.epi_flags & RGNN_EPI_BIAS_N) {
@@ -318,11 +348,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
         }
       }
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive its readers
   }
   // ================================ teardown ================================
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -396,8 +428,9 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
 }
 
 template <int BN>
-static int launch(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const TcParams& p, cudaStream_t st) {
-  constexpr size_t smem = 1024 + (size_t)NSTAGE * (BM * BK * 2 + BN * BK * 2) + 256;
+static int launch(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const TcParams& p, cudaStream_t st,
+                  const CUtensorMap* o0 = nullptr, const CUtensorMap* o1 = nullptr) {
+  constexpr size_t smem = 1024 + (size_t)NSTAGE * (BM * BK * 2 + BN * BK * 2) + 2 * 128 * 128 + 256;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -407,7 +440,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap
   const int work = p.tiles_m * p.tiles_n * p.splits;
   int grid = work < kNumSMs ? work : kNumSMs;
   if (grid < 1) return 0;
-  k_gemm_tc<BN><<<grid, 256, smem, st>>>(a, b0, b1, p);
+  k_gemm_tc<BN><<<grid, 256, smem, st>>>(a, b0, b1, o0 ? *o0 : a, o1 ? *o1 : (o0 ? *o0 : a), p);
   RGNN_LAUNCH_CHECK("k_gemm_tc");
   return 0;
 }
@@ -466,7 +499,19 @@ extern "C" int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const 
   p.nodes = (int)nodes; p.M = M; p.N = nodes * 64;
   p.out0 = out0; p.out1 = out1; p.m_split = (int)m0; p.ld0 = m0 * 64; p.ld1 = m1 * 64; p.bias = bias;
   RGNN_REQUIRE((int64_t)p.tiles_m * p.tiles_n < (1ll << 31), RGNN_E_RANGE, "rgnn_tc_conv1x1: too many tiles");
-  return launch<BN>(ta, tb0, tb1, p, as_stream(stream));
+  RGNN_REQUIRE(nodes * (m0 > m1 ? m0 : m1) < (1ll << 31), RGNN_E_RANGE, "rgnn_tc_conv1x1: too many output rows for a tensor map coordinate");
+  CUtensorMap to0, to1;
+  {
+    const uint64_t d[2] = {64, (uint64_t)(nodes * m0)}, s[1] = {128};
+    const uint32_t b[2] = {64, 128};
+    int rc = make_map(&to0, out0, 2, d, s, b); if (rc) return rc;
+  }
+  if (m1 > 0) {
+    const uint64_t d[2] = {64, (uint64_t)(nodes * m1)}, s[1] = {128};
+    const uint32_t b[2] = {64, 128};
+    int rc = make_map(&to1, out1, 2, d, s, b); if (rc) return rc;
+  } else to1 = to0;
+  return launch<BN>(ta, tb0, tb1, p, as_stream(stream), &to0, &to1);
 }
 
 // dW[m, k] = sum_v sum_p dy[v,m,p] * x[v,k,p], x = x0 (k < c0) | x1;  dW fp32 [M, c0+c1] (row stride ldw), partial fp32 [splits, M, c0+c1].

@@ -35,7 +35,7 @@ def test_version_and_arch(R):
 
 def test_argument_validation_without_gpu(R):
     l = R._lib.lib()
-    rc = l.rgnn_aggregate(7, None, 0, None, 0, None, 0, None, None, 0, None, 0, None, None, None, None, None, 0, 0, 0, 1, 0, 1, 1, None)
+    rc = l.rgnn_aggregate(7, None, 0, None, 0, None, 0, None, None, 0, None, 0, None, None, None, None, None, 0, 0, 0, 0, 1, 0, 1, 1, None)
     assert rc == -1 and b"dtype" in l.rgnn_last_error()
     rc = l.rgnn_gemm(0, None, 0, 0, 0, 0, 0, None, 0, 0, 0, 0, 0, None, 0, 0, 0, 4, 4, 4, 1, 1, 1, None, 0, None, None, 1.0, 0.0, None)
     assert rc == -1
