@@ -104,11 +104,13 @@ template <int NVP, int LPC> __device__ __forceinline__ int scattered_id(int i, i
 
 // dh[u] = addend[u] + w * sum_{a != u} gamma[e(u,a)] * dagg[a];  dz[e(u,a)] = sig' * w * (sum_p h[u] dagg[a], sum_p dagg[a]);  w = 1/(K-1)
 // LPC = P / VEC lanes share one channel (compile time).
+// Software-pipelined over the grid-stride loop: the 3K 16-byte vectors of iteration r+1 are in flight (packed, 12K registers)
+// while iteration r computes, so HBM latency is covered by the loop itself rather than by occupancy (1 CTA of 8 warps / SM).
 template <typename T, int K, int LPC>
-__global__ void __launch_bounds__(256) k_film_bwd_complete(const T* __restrict__ h, int64_t ldh, const T* __restrict__ dagg, int64_t ldd,
-                                                           const T* __restrict__ z, const T* addend, int64_t ldadd,
-                                                           T* dh, int64_t lddh, T* __restrict__ dz,
-                                                           int64_t G, int F, int P, int fuse_sig) {
+__global__ void __launch_bounds__(256, 1) k_film_bwd_complete(const T* __restrict__ h, int64_t ldh, const T* __restrict__ dagg, int64_t ldd,
+                                                              const T* __restrict__ z, const T* addend, int64_t ldadd,
+                                                              T* dh, int64_t lddh, T* __restrict__ dz,
+                                                              int64_t G, int F, int P, int fuse_sig) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int NE = K * (K - 1);
   constexpr int NVP = (NE + LPC - 1) / LPC * LPC;
@@ -118,25 +120,49 @@ __global__ void __launch_bounds__(256) k_film_bwd_complete(const T* __restrict__
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t rounds = (total + stride - 1) / stride;
   const int l = threadIdx.x % LPC;
+  const bool has_add = addend != nullptr;
+
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint4 nh[K], nd[K], na[K];
+  bool nlive = t < total;
+  int64_t ng = 0, noff = 0;
+  auto fetch = [&]() {
+    ng = t / row_vecs;
+    noff = (t - ng * row_vecs) * VEC;
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      nh[u] = *reinterpret_cast<const uint4*>(h + (ng * K + u) * ldh + noff);
+      nd[u] = *reinterpret_cast<const uint4*>(dagg + (ng * K + u) * ldd + noff);
+      if (has_add) na[u] = *reinterpret_cast<const uint4*>(addend + (ng * K + u) * ldadd + noff);
+    }
+  };
+#pragma unroll
+  for (int u = 0; u < K; ++u) { nh[u] = make_uint4(0, 0, 0, 0); nd[u] = nh[u]; na[u] = nh[u]; }
+  if (nlive) fetch();
+
   for (int64_t r = 0; r < rounds; ++r) {         // whole warps iterate together (shuffles below)
-    const int64_t t = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = t < total;
-    const int64_t tt = live ? t : 0;
-    const int64_t g = tt / row_vecs;
-    const int64_t off = (tt - g * row_vecs) * VEC;
+    const bool live = nlive;
+    const int64_t g = ng, off = noff;
     const int c = (int)(off / P);
     const int64_t n0 = g * K, e0 = g * NE;
     const T* zc = z + e0 * 2 * F + 2 * c;
     float hv[K][VEC], dv[K][VEC];
+    uint4 ca[K];
 #pragma unroll
-    for (int u = 0; u < K; ++u) {
-      if (live) { Vec16<T>::load(h + (n0 + u) * ldh + off, hv[u]); Vec16<T>::load(dagg + (n0 + u) * ldd + off, dv[u]); }
-      else {
+    for (int u = 0; u < K; ++u) { Vec16<T>::unpack(nh[u], hv[u]); Vec16<T>::unpack(nd[u], dv[u]); ca[u] = na[u]; }
+    // gamma of every edge of the graph for this channel (the LPC lanes of a channel read the same bytes: broadcast)
+    float gam[NE];
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) { hv[u][q] = 0.f; dv[u][q] = 0.f; }
-      }
+    for (int e = 0; e < NE; ++e) gam[e] = live ? ldg_pair<T>(zc + (int64_t)e * 2 * F).x : 0.f;
+    // ---- prefetch the next iteration
+    t += stride;
+    nlive = t < total;
+    if (nlive) fetch();
+    else {
+#pragma unroll
+      for (int u = 0; u < K; ++u) { nh[u] = make_uint4(0, 0, 0, 0); nd[u] = nh[u]; }
     }
-    // ---- dh: needs every gamma of the graph for this channel (the LPC lanes of a channel read the same 4/8 bytes: broadcast)
+    // ---- dh
 #pragma unroll
     for (int u = 0; u < K; ++u) {
       float acc[VEC];
@@ -145,14 +171,13 @@ __global__ void __launch_bounds__(256) k_film_bwd_complete(const T* __restrict__
 #pragma unroll
       for (int a = 0; a < K; ++a) {
         if (a == u) continue;
-        const float gam = live ? ldg_pair<T>(zc + (int64_t)edge_id(K, u, a) * 2 * F).x : 0.f;
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) acc[q] = fmaf(gam, dv[a][q], acc[q]);
+        for (int q = 0; q < VEC; ++q) acc[q] = fmaf(gam[edge_id(K, u, a)], dv[a][q], acc[q]);
       }
       if (live) {
-        if (addend) {
+        if (has_add) {
           float av[VEC];
-          Vec16<T>::load(addend + (n0 + u) * ldadd + off, av);
+          Vec16<T>::unpack(ca[u], av);
 #pragma unroll
           for (int q = 0; q < VEC; ++q) acc[q] = fmaf(acc[q], w, av[q]);
         } else {
@@ -232,7 +257,7 @@ static int launch_bwd_lpc(int K, const T* h, int64_t ldh, const T* dagg, int64_t
                           int64_t lddh, T* dz, int64_t G, int F, int P, int fuse_sig, cudaStream_t st) {
   const int64_t total = G * ((int64_t)F * P / Vec16<T>::N);
   int64_t blocks = (total + 255) / 256;
-  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  if (blocks > kNumSMs) blocks = kNumSMs;        // persistent: one pipelined CTA per SM
   if (blocks < 1) return 0;
 #define RGNN_CASE(KK) case KK: k_film_bwd_complete<T, KK, LPC><<<(unsigned)blocks, 256, 0, st>>>(h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sig); break;
   switch (K) { RGNN_CASE(2) RGNN_CASE(3) RGNN_CASE(4) RGNN_CASE(5) RGNN_CASE(6) RGNN_CASE(7) RGNN_CASE(8) default: return RGNN_E_UNSUPPORTED; }
