@@ -26,51 +26,65 @@ template <> __device__ __forceinline__ void st_pair<__nv_bfloat16>(__nv_bfloat16
 
 __host__ __device__ constexpr int edge_id(int K, int u, int a) { return u * (K - 1) + (a < u ? a : a - 1); }
 
+// Software-pipelined like the backward below: the K vectors of iteration r+1 are in flight while iteration r computes.
 template <typename T, int K, bool HAS_Z>
-__global__ void __launch_bounds__(256) k_film_fwd_complete(const T* __restrict__ x, int64_t ldx, const T* __restrict__ z,
-                                                           T* __restrict__ out, int64_t ldout, T* __restrict__ copy_to,
-                                                           int64_t G, int F, int P) {
+__global__ void __launch_bounds__(256, (K <= 5 ? 2 : 1)) k_film_fwd_complete(const T* __restrict__ x, int64_t ldx, const T* __restrict__ z,
+                                                              T* __restrict__ out, int64_t ldout, T* __restrict__ copy_to,
+                                                              int64_t G, int F, int P) {
   constexpr int VEC = Vec16<T>::N;
   constexpr bool EXACT = sizeof(T) == 4;       // fp32: reference rounding order; bf16: fused multiply-add
   const int64_t row_vecs = (int64_t)F * P / VEC;
   const int64_t total = G * row_vecs;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t g = t / row_vecs;
-    const int64_t off = (t - g * row_vecs) * VEC;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  uint4 nx[K];
+  int64_t ng = t / row_vecs, noff = (t - ng * row_vecs) * VEC;
+#pragma unroll
+  for (int u = 0; u < K; ++u) nx[u] = *reinterpret_cast<const uint4*>(x + (ng * K + u) * ldx + noff);
+  while (true) {
+    const int64_t g = ng, off = noff;
     const int c = (int)(off / P);
     const int64_t n0 = g * K, e0 = g * (K * (K - 1));
+    uint4 cx[K];
+#pragma unroll
+    for (int u = 0; u < K; ++u) cx[u] = nx[u];
+    const T* zc = z + e0 * 2 * F + 2 * c;
+    t += stride;
+    const bool more = t < total;
+    if (more) {
+      ng = t / row_vecs; noff = (t - ng * row_vecs) * VEC;
+#pragma unroll
+      for (int u = 0; u < K; ++u) nx[u] = *reinterpret_cast<const uint4*>(x + (ng * K + u) * ldx + noff);
+    }
     float xv[K][VEC];
 #pragma unroll
-    for (int u = 0; u < K; ++u) Vec16<T>::load(x + (n0 + u) * ldx + off, xv[u]);
+    for (int u = 0; u < K; ++u) Vec16<T>::unpack(cx[u], xv[u]);
     if (copy_to) {
 #pragma unroll
-      for (int u = 0; u < K; ++u) Vec16<T>::store(copy_to + (n0 + u) * ldout + off, xv[u]);
+      for (int u = 0; u < K; ++u) *reinterpret_cast<uint4*>(copy_to + (n0 + u) * ldout + off) = cx[u];
     }
 #pragma unroll
     for (int a = 0; a < K; ++a) {
-      float2 gb[K];
-      if (HAS_Z) {
-#pragma unroll
-        for (int u = 0; u < K; ++u)
-          if (u != a) gb[u] = ldg_pair<T>(z + (e0 + edge_id(K, u, a)) * 2 * F + 2 * c);
-      }
       float acc[VEC];
 #pragma unroll
       for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
 #pragma unroll
       for (int u = 0; u < K; ++u) {      // ascending u == ascending edge id among the in-edges of a
         if (u == a) continue;
+        const float2 p2 = HAS_Z ? ldg_pair<T>(zc + (int64_t)edge_id(K, u, a) * 2 * F) : make_float2(1.f, 0.f);
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
           if (!HAS_Z) acc[q] = __fadd_rn(acc[q], xv[u][q]);
-          else if (EXACT) acc[q] = __fadd_rn(acc[q], __fadd_rn(__fmul_rn(gb[u].x, xv[u][q]), gb[u].y));
-          else acc[q] += fmaf(gb[u].x, xv[u][q], gb[u].y);
+          else if (EXACT) acc[q] = __fadd_rn(acc[q], __fadd_rn(__fmul_rn(p2.x, xv[u][q]), p2.y));
+          else acc[q] += fmaf(p2.x, xv[u][q], p2.y);
         }
       }
 #pragma unroll
       for (int q = 0; q < VEC; ++q) acc[q] = EXACT ? __fdiv_rn(acc[q], (float)(K - 1)) : acc[q] * (1.0f / (K - 1));
       Vec16<T>::store(out + (n0 + a) * ldout + off, acc);
     }
+    if (!more) break;
   }
 }
 
@@ -243,7 +257,8 @@ static int launch_fwd(int K, const T* x, int64_t ldx, const T* z, T* out, int64_
                       cudaStream_t st) {
   const int64_t total = G * ((int64_t)F * P / Vec16<T>::N);
   int64_t blocks = (total + 255) / 256;
-  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  const int64_t resident = (K <= 5 ? 2 : 1) * kNumSMs;   // persistent: pipelined CTAs, as many as stay resident
+  if (blocks > resident) blocks = resident;
   if (blocks < 1) return 0;
 #define RGNN_CASE(KK) case KK: k_film_fwd_complete<T, KK, HAS_Z><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, z, out, ldout, copy_to, G, F, P); break;
   switch (K) { RGNN_CASE(2) RGNN_CASE(3) RGNN_CASE(4) RGNN_CASE(5) RGNN_CASE(6) RGNN_CASE(7) RGNN_CASE(8) default: return RGNN_E_UNSUPPORTED; }

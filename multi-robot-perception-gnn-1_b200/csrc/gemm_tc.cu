@@ -156,7 +156,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
-    if (p.epi_mode == EPI_NCHW) {
+    if (p.epi_mode != EPI_PARTIAL) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO0) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO1) : "memory");
     }
@@ -262,10 +262,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(ew * 32) << 16);
       const int64_t m = (int64_t)tm * BM + row;
       const float bias_m = (p.bias && (p.epi_flags & RGNN_EPI_BIAS_M) && m < p.M) ? p.bias[m] : 0.f;
-      if (p.epi_mode == EPI_NCHW) {
-        // row m = output channel, columns = (robot, pixel).  Per robot: 128 ch x 64 px bf16 = one contiguous 16 KB slab of the
-        // NCHW tensor -> staged in shared memory (128B-swizzled rows, conflict-free 16-byte stores) and written by ONE TMA store.
-        const bool second = m >= p.m_split;
+      if (p.epi_mode == EPI_NCHW || p.epi_mode == EPI_ROW) {
+        // bf16 outputs leave through shared memory: each 128-row x 64-column (128 B) slab is staged with the 128B swizzle
+        // (conflict-free 16-byte stores) and written by ONE TMA store - full 128 B lines, rows beyond M clipped by the map.
+        //   NCHW: row = output channel, slab j = robot j of the tile: the slab is a contiguous 16 KB piece of [N, F, 8, 8].
+        //   ROW : row = output row, slab j = columns [64 j, 64 j + 64) of a row-major matrix.
+        const bool nchw = p.epi_mode == EPI_NCHW;
+        const bool second = nchw && m >= p.m_split;
         const int row0 = tm * BM - (second ? p.m_split : 0);            // first channel of this tile inside its output tensor
         const int rows_per_node = second ? (int)(p.ld1 / 64) : (int)(p.ld0 / 64);
 #pragma unroll 1
@@ -278,21 +281,43 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           tmem_ld32_issue(tacc + (2 * j) * 32, r0);
           tmem_ld32_issue(tacc + (2 * j + 1) * 32, r1);
           tmem_ld_wait();
+          const int64_t n0 = (int64_t)tn * BN + j * 64;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const uint32_t* r = q < 4 ? r0 : r1;
             const int b = (q & 3) * 8;
-            uint32_t w0 = pack_bf16(__uint_as_float(r[b + 0]) + bias_m, __uint_as_float(r[b + 1]) + bias_m);
-            uint32_t w1 = pack_bf16(__uint_as_float(r[b + 2]) + bias_m, __uint_as_float(r[b + 3]) + bias_m);
-            uint32_t w2 = pack_bf16(__uint_as_float(r[b + 4]) + bias_m, __uint_as_float(r[b + 5]) + bias_m);
-            uint32_t w3 = pack_bf16(__uint_as_float(r[b + 6]) + bias_m, __uint_as_float(r[b + 7]) + bias_m);
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[b + i]) + bias_m;
+            if (!nchw) {
+              if (p.epi_flags & RGNN_EPI_BIAS_N) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + q * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + q * 8 + 4));
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (p.epi_flags & RGNN_EPI_SIGMOID) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __fdividef(1.0f, 1.0f + __expf(-v[i]));
+              }
+              if ((p.epi_flags & RGNN_EPI_RELU_MASK) && m < p.M) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.aux) + m * p.ld0 + n0 + q * 8));
+                const uint32_t ws[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {     // bf16 > 0  <=>  sign clear and magnitude non-zero
+                  if (!((ws[i] & 0x7fffu) != 0 && !(ws[i] & 0x8000u))) v[2 * i] = 0.f;
+                  if (!(((ws[i] >> 16) & 0x7fffu) != 0 && !((ws[i] >> 16) & 0x8000u))) v[2 * i + 1] = 0.f;
+                }
+              }
+            }
+            const uint32_t w0 = pack_bf16(v[0], v[1]), w1 = pack_bf16(v[2], v[3]), w2 = pack_bf16(v[4], v[5]), w3 = pack_bf16(v[6], v[7]);
             const uint32_t addr = stg + row * 128 + ((q ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           epi_bar_sync();
           if (ew == 0 && lane == 0) {
-            if (node < p.nodes) tma_store_2d(second ? &tmO1 : &tmO0, stg, 0, node * rows_per_node + row0);
+            if (nchw) { if (node < p.nodes) tma_store_2d(second ? &tmO1 : &tmO0, stg, 0, node * rows_per_node + row0); }
+            else if (n0 < p.N) tma_store_2d(&tmO0, stg, (int)n0, tm * BM);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
@@ -305,41 +330,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = empty ? 0.f : __uint_as_float(r[i]);
-        if (p.epi_mode == EPI_ROW) {
-          const int64_t n0 = (int64_t)tn * BN + c * 32;
-          if (m < p.M && n0 < p.N) {
-            if (p.epi_flags & RGNN_EPI_BIAS_N) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] += p.bias[n0 + i];
-            }
-            if (p.epi_flags & RGNN_EPI_SIGMOID) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = 1.0f / (1.0f + __expf(-v[i]));
-            }
-            if (p.epi_flags & RGNN_EPI_RELU_MASK) {
-              const uint4* ax = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.aux) + m * p.ld0 + n0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 u = ax[q];
-                const uint32_t ws[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                  if (!((ws[j] & 0x7fffu) != 0 && !(ws[j] & 0x8000u))) v[8 * q + 2 * j] = 0.f;
-                  if (!(((ws[j] >> 16) & 0x7fffu) != 0 && !((ws[j] >> 16) & 0x8000u))) v[8 * q + 2 * j + 1] = 0.f;
-                }
-              }
-            }
-            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out0) + m * p.ld0 + n0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 u;
-              u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
-              u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
-              reinterpret_cast<uint4*>(o)[q] = u;
-            }
-          }
-        } else {   // EPI_PARTIAL: fp32 partial tile of split sp
+        {
           const int64_t n0 = (int64_t)tn * BN + c * 32;
           if (m < p.M && n0 < p.N) {
             float* o = static_cast<float*>(p.out0) + ((int64_t)sp * p.M + m) * p.ld0 + n0;
@@ -595,7 +586,14 @@ extern "C" int rgnn_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_
   p.tiles_m = (int)((M + 127) / 128); p.tiles_n = (int)(N / BN); p.splits = 1;
   p.kblocks = (int)(K / 64); p.kb_per_split = p.kblocks;
   p.M = M; p.N = N; p.out0 = C; p.ld0 = ldc; p.bias = bias; p.aux = aux;
-  return wide ? launch<256>(ta, tb, tb, p, as_stream(stream)) : launch<128>(ta, tb, tb, p, as_stream(stream));
+  RGNN_REQUIRE(!bias || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0, RGNN_E_ALIGN, "rgnn_tc_gemm_tn: bias must be 16-byte aligned");
+  CUtensorMap to;
+  {
+    const uint64_t d[2] = {(uint64_t)N, (uint64_t)M}, s[1] = {(uint64_t)ldc * 2};
+    const uint32_t b[2] = {64, 128};
+    int rc = make_map(&to, C, 2, d, s, b); if (rc) return rc;
+  }
+  return wide ? launch<256>(ta, tb, tb, p, as_stream(stream), &to, &to) : launch<128>(ta, tb, tb, p, as_stream(stream), &to, &to);
 }
 
 // C[M,N] fp32 = A^T . B with A bf16 [K, M] (row stride lda), B bf16 [K, N] (row stride ldb): both operands MN-major.
