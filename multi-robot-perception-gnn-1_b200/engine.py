@@ -1,0 +1,75 @@
+"""Host-buffer front end of the GNN block: the call a user with HOST tensors makes.
+
+`HostPipeline.step(h, pose, dy, y_out, dh_out)` runs fwd+bwd of a GNNBlock over a batch that lives in pinned host memory
+and returns the block output and the input gradient to pinned host memory.  Robot graphs are independent, so the batch is
+cut into chunks of whole graphs and the three phases are overlapped on three CUDA streams:
+
+    copy-in stream :  H2D of chunk i+1 (h, pose, dy)          |  PCIe is full duplex: in and out copies run concurrently
+    compute stream :  fwd + bwd of chunk i (librobotgnn)      |  parameter gradients accumulate across chunks (sum)
+    copy-out stream:  D2H of chunk i-1 (y, dh)                |
+
+The reference has no counterpart (its loop moves a whole DGL batch with data.to('cuda:0'), dgl/training.py:183, and keeps
+everything else on the device); this exists so that end-to-end throughput with host-resident data is bounded by the PCIe
+link, not by serialising copies and kernels.
+"""
+import torch
+
+from .graph import robot_batch
+
+
+class HostPipeline:
+    def __init__(self, block, num_graphs, robots, feat, dtype=torch.bfloat16, device="cuda", chunks=8, slots=3, hw=(8, 8)):
+        if num_graphs % chunks:
+            raise ValueError("num_graphs must be a multiple of chunks")
+        self.block, self.G, self.K, self.F, self.dtype = block, num_graphs, robots, feat, dtype
+        self.dev = torch.device(device)
+        self.chunks, self.slots = chunks, slots
+        self.gc = num_graphs // chunks
+        self.nc, self.ec = self.gc * robots, self.gc * robots * (robots - 1)
+        self.hw = hw
+        self.graph = robot_batch(self.gc, robots, device=self.dev)
+        self.graph.index()
+        mk = lambda *s, dt=dtype: torch.empty(s, dtype=dt, device=self.dev)
+        self.h_d = [mk(self.nc, feat, *hw) for _ in range(slots)]
+        self.dy_d = [mk(self.nc, feat, *hw) for _ in range(slots)]
+        self.pose_d = [mk(self.ec, 9, dt=torch.float32) for _ in range(slots)]
+        self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
+        self.h2d_bytes = num_graphs * robots * feat * hw[0] * hw[1] * 2 * self.h_d[0].element_size() + num_graphs * robots * (robots - 1) * 36
+        self.d2h_bytes = num_graphs * robots * feat * hw[0] * hw[1] * 2 * self.h_d[0].element_size()
+
+    def step(self, h, pose, dy, y_out, dh_out):
+        """h, dy, y_out, dh_out: pinned host [N, F, 8, 8]; pose: pinned host [E, 9] fp32.  Parameter .grad holds the sum over
+        the whole batch on return (after the caller synchronises, e.g. torch.cuda.current_stream().synchronize())."""
+        cur = torch.cuda.current_stream(self.dev)
+        for s in (self.s_in, self.s_comp, self.s_out):
+            s.wait_stream(cur)
+        for p in self.block.parameters():
+            p.grad = None
+        ev_comp = [None] * self.chunks
+        for i in range(self.chunks):
+            sl = i % self.slots
+            n0, n1, e0, e1 = i * self.nc, (i + 1) * self.nc, i * self.ec, (i + 1) * self.ec
+            with torch.cuda.stream(self.s_in):
+                if i >= self.slots:
+                    self.s_in.wait_event(ev_comp[i - self.slots])      # the slot's previous consumer is done
+                self.h_d[sl].copy_(h[n0:n1], non_blocking=True)
+                self.dy_d[sl].copy_(dy[n0:n1], non_blocking=True)
+                self.pose_d[sl].copy_(pose[e0:e1], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self.s_in)
+            with torch.cuda.stream(self.s_comp):
+                self.s_comp.wait_event(ev_in)
+                hd = self.h_d[sl].detach().requires_grad_()
+                y = self.block(self.graph, hd, self.pose_d[sl])
+                y.backward(self.dy_d[sl])
+                ev_comp[i] = torch.cuda.Event()
+                ev_comp[i].record(self.s_comp)
+                yd, dhd = y.detach(), hd.grad
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ev_comp[i])
+                yd.record_stream(self.s_out)
+                dhd.record_stream(self.s_out)
+                y_out[n0:n1].copy_(yd, non_blocking=True)
+                dh_out[n0:n1].copy_(dhd, non_blocking=True)
+        cur.wait_stream(self.s_out)
+        cur.wait_stream(self.s_comp)

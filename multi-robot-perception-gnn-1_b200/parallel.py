@@ -41,7 +41,8 @@ class GradSync:
         self._work = [None] * len(self.buckets)
         self._pending = [0] * len(self.buckets)
         self._hooks = []
-        self._side = None
+        self.overlap = True      # False: hooks stay quiet (e.g. gradients accumulated over several backward passes); finish() reduces
+
         for bi, b in enumerate(self.buckets):
             for _, p in b:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
@@ -53,6 +54,8 @@ class GradSync:
 
     def _make_hook(self, bi):
         def hook(_param):
+            if not self.overlap:
+                return
             self._pending[bi] -= 1
             if self._pending[bi] == 0:
                 self._launch(bi)
