@@ -196,6 +196,36 @@ __global__ void __launch_bounds__(256) k_reduce_rows_vec(const T* __restrict__ x
   if (t < row_vecs && (lpc >= 32 ? (threadIdx.x & 31) == 0 : (t % lpc) == 0)) atomicAdd(out + (t * VEC) / inner, acc);
 }
 
+// column sums of a row-major [rows, cols] matrix (bias gradient of nn.Linear): thread = 16-byte vector of columns,
+// streams its chunk of rows with 4 loads in flight, VEC atomics at the end.
+template <typename T>
+__global__ void __launch_bounds__(256) k_reduce_cols_vec(const T* __restrict__ x, int64_t rows, int64_t cols, float* __restrict__ out, int64_t chunk) {
+  constexpr int VEC = Vec16<T>::N;
+  const int64_t cv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cv * VEC >= cols) return;
+  const int64_t i0 = (int64_t)blockIdx.y * chunk, i1 = min(rows, i0 + chunk);
+  float acc[VEC];
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
+  const T* px = x + cv * VEC;
+  int64_t i = i0;
+  for (; i + 4 <= i1; i += 4) {
+    float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
+    Vec16<T>::load(px + i * cols, v0); Vec16<T>::load(px + (i + 1) * cols, v1);
+    Vec16<T>::load(px + (i + 2) * cols, v2); Vec16<T>::load(px + (i + 3) * cols, v3);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) acc[q] += (v0[q] + v1[q]) + (v2[q] + v3[q]);
+  }
+  for (; i < i1; ++i) {
+    float v0[VEC];
+    Vec16<T>::load(px + i * cols, v0);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) acc[q] += v0[q];
+  }
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) atomicAdd(out + cv * VEC + q, acc[q]);
+}
+
 }  // namespace rgnn
 
 using namespace rgnn;
@@ -335,6 +365,25 @@ extern "C" int rgnn_reduce_sum(int dtype, const void* x, int64_t outer, int64_t 
       if (dtype == RGNN_F32) k_reduce_rows_vec<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), outer, len, (int)inner, out, chunk);
       else k_reduce_rows_vec<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), outer, len, (int)inner, out, chunk);
       RGNN_LAUNCH_CHECK("k_reduce_rows_vec");
+      return 0;
+    }
+  }
+  {  // contiguous row-major [outer, len] column sums with 16-byte vectors
+    const int es = dtype == RGNN_F32 ? 4 : 2, vec = 16 / es;
+    if (inner == 1 && s_j == 1 && s_outer == len && len % vec == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+      const int64_t cvs = len / vec;
+      const int threads = 64;                      // few columns, many rows: small blocks, many row chunks
+      const int64_t bx = (cvs + threads - 1) / threads;
+      int64_t chunks = (16 * kNumSMs + bx - 1) / bx;
+      if (chunks > (outer + 15) / 16) chunks = (outer + 15) / 16;
+      if (chunks > 65535) chunks = 65535;
+      if (chunks < 1) chunks = 1;
+      const int64_t chunk = (outer + chunks - 1) / chunks;
+      chunks = (outer + chunk - 1) / chunk;
+      dim3 grid((unsigned)bx, (unsigned)chunks);
+      if (dtype == RGNN_F32) k_reduce_cols_vec<float><<<grid, threads, 0, st>>>(static_cast<const float*>(x), outer, len, out, chunk);
+      else k_reduce_cols_vec<__nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), outer, len, out, chunk);
+      RGNN_LAUNCH_CHECK("k_reduce_cols_vec");
       return 0;
     }
   }
