@@ -17,6 +17,7 @@
 // SWIZZLE_128B operand block (row = channel, 128 B = the 64 contiguous pixels), so the concat of models.py:182 is
 // just "k-blocks 0..F/64 from h, the rest from g_h" (two tensor maps) and is never materialised.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace rgnn {
@@ -77,6 +78,30 @@ __device__ __forceinline__ void tma_3d(uint32_t dst, const CUtensorMap* map, uin
                "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -133,7 +158,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BN>
+// CL = 2: the two CTAs of a cluster work on the two M-tiles that share one B tile (same tn); each loads HALF of the B tile
+// and TMA-multicasts it into both CTAs' shared memory, cutting L2->SM operand traffic per CTA from 48 KB to 32 KB per
+// k-block.  Every stage's empty barrier then collects the tcgen05.commit of BOTH CTAs (multicast commit) before either
+// producer may overwrite the stage.  The MMAs themselves stay cta_group::1 (each CTA owns its accumulator).
+template <int BN, int CL>
 __global__ void __launch_bounds__(256, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
           const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmO0,
@@ -152,6 +181,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0) : "memory");
@@ -162,7 +193,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -172,10 +203,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();       // the peer's barriers exist before any multicast / remote arrive targets them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  const int work_total = p.tiles_m * p.tiles_n * p.splits;
+  const int tiles_mc = (p.tiles_m + CL - 1) / CL;     // M-tile groups: the CTAs of a cluster take consecutive M-tiles
+  const int work_total = tiles_mc * p.tiles_n * p.splits;
+  const int w_first = blockIdx.x / CL, w_step = gridDim.x / CL;
   const bool a_mn = p.load_mode == LOAD_NN;
   const bool b_mn = p.load_mode == LOAD_CONV || p.load_mode == LOAD_NN;
 
@@ -183,31 +217,49 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // ================================ TMA producer ================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
-        const int tm = w % p.tiles_m, tn = (w / p.tiles_m) % p.tiles_n, sp = w / (p.tiles_m * p.tiles_n);
+      for (int w = w_first; w < work_total; w += w_step) {
+        const int tm = (w % tiles_mc) * CL + crank, tn = (w / tiles_mc) % p.tiles_n, sp = w / (tiles_mc * p.tiles_n);
         const int kb0 = sp * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t fb = bar_full + 8 * stage;
           const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
           mbar_expect_tx(fb, STAGE_BYTES);
+          // A: this CTA's own 128 rows.  B: tensor maps carry HALF-tile boxes; a lone CTA fetches both halves, a cluster CTA
+          // fetches half `crank` and multicasts it to every CTA of the cluster.
+          constexpr uint32_t HALF_B = B_BYTES / 2;
+          const int h0 = CL > 1 ? crank : 0, h1 = CL > 1 ? crank + 1 : 2;
           if (p.load_mode == LOAD_TN) {
             tma_2d(sa, &tmA, fb, kb * BK, tm * BM);
-            tma_2d(sb, &tmB0, fb, kb * BK, tn * BN);
+            for (int hb = h0; hb < h1; ++hb) {
+              if (CL > 1) tma_2d_mc(sb + hb * HALF_B, &tmB0, fb, kb * BK, tn * BN + hb * (BN / 2), MC_MASK);
+              else tma_2d(sb + hb * HALF_B, &tmB0, fb, kb * BK, tn * BN + hb * (BN / 2));
+            }
           } else if (p.load_mode == LOAD_CONV) {
             tma_2d(sa, &tmA, fb, kb * BK, tm * BM);
-            if (kb < p.kb_b0) tma_3d(sb, &tmB0, fb, 0, kb * BK, tn * (BN / 64));
-            else tma_3d(sb, &tmB1, fb, 0, (kb - p.kb_b0) * BK, tn * (BN / 64));
+            const CUtensorMap* mb = kb < p.kb_b0 ? &tmB0 : &tmB1;
+            const int kc = (kb < p.kb_b0 ? kb : kb - p.kb_b0) * BK;
+            for (int hb = h0; hb < h1; ++hb) {
+              if (CL > 1) tma_3d_mc(sb + hb * HALF_B, mb, fb, 0, kc, tn * (BN / 64) + hb * (BN / 128), MC_MASK);
+              else tma_3d(sb + hb * HALF_B, mb, fb, 0, kc, tn * (BN / 64) + hb * (BN / 128));
+            }
           } else if (p.load_mode == LOAD_WGRAD) {   // k-block == robot kb; both operands K-major (pixels contiguous)
             tma_2d(sa, &tmA, fb, 0, kb * p.rows_a + tm * BM);
             const int n0 = tn * BN;
-            if (n0 < p.n_b0) tma_2d(sb, &tmB0, fb, 0, kb * p.rows_b0 + n0);
-            else tma_2d(sb, &tmB1, fb, 0, kb * p.rows_b1 + (n0 - p.n_b0));
+            const CUtensorMap* mb = n0 < p.n_b0 ? &tmB0 : &tmB1;
+            const int rowb = n0 < p.n_b0 ? kb * p.rows_b0 + n0 : kb * p.rows_b1 + (n0 - p.n_b0);
+            for (int hb = h0; hb < h1; ++hb) {
+              if (CL > 1) tma_2d_mc(sb + hb * HALF_B, mb, fb, 0, rowb + hb * (BN / 2), MC_MASK);
+              else tma_2d(sb + hb * HALF_B, mb, fb, 0, rowb + hb * (BN / 2));
+            }
           } else {                                   // LOAD_NN: both operands MN-major, 64-wide boxes
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_2d(sa + j * (BK * 128), &tmA, fb, tm * BM + j * 64, kb * BK);
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_2d(sb + j * (BK * 128), &tmB0, fb, tn * BN + j * 64, kb * BK);
+            for (int hb = h0; hb < h1; ++hb)
+              for (int j = hb * (BN / 128); j < (hb + 1) * (BN / 128); ++j) {
+                if (CL > 1) tma_2d_mc(sb + j * (BK * 128), &tmB0, fb, tn * BN + j * 64, kb * BK, MC_MASK);
+                else tma_2d(sb + j * (BK * 128), &tmB0, fb, tn * BN + j * 64, kb * BK);
+              }
           }
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
@@ -221,8 +273,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t a_lbo = a_mn ? BK * 128 : 0, b_lbo = b_mn ? BK * 128 : 0;
     const uint32_t a_kstep = a_mn ? 2048 : 32, b_kstep = b_mn ? 2048 : 32;   // bytes per 16 k
     int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
-    for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
-      const int sp = w / (p.tiles_m * p.tiles_n);
+    for (int w = w_first; w < work_total; w += w_step) {
+      const int sp = w / (tiles_mc * p.tiles_n);
       const int kb0 = sp * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
       mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -238,7 +290,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint64_t db = make_desc(sb + k * b_kstep, b_lbo, 1024);
             umma(tacc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(bar_empty + 8 * stage);                 // stage reusable once these MMAs retire
+          if (CL > 1) umma_commit_mc(bar_empty + 8 * stage, MC_MASK);   // both CTAs' producers wait for both consumers
+          else umma_commit(bar_empty + 8 * stage);            // stage reusable once these MMAs retire
           if (kb == kb1 - 1) umma_commit(bar_tfull + 8 * as); // accumulator complete
         }
         __syncwarp();
@@ -253,8 +306,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int ew = warp - 4;                    // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
     const int row = ew * 32 + lane;             // row inside the 128-row tile
     int as = 0; uint32_t aphase = 0;
-    for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
-      const int tm = w % p.tiles_m, tn = (w / p.tiles_m) % p.tiles_n, sp = w / (p.tiles_m * p.tiles_n);
+    for (int w = w_first; w < work_total; w += w_step) {
+      const int tm = (w % tiles_mc) * CL + crank, tn = (w / tiles_mc) % p.tiles_n, sp = w / (tiles_mc * p.tiles_n);
       const int kb0 = sp * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
       const bool empty = kb1 <= kb0;
       mbar_wait(bar_tfull + 8 * as, aphase);
@@ -316,7 +369,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           epi_bar_sync();
           if (ew == 0 && lane == 0) {
-            if (nchw) { if (node < p.nodes) tma_store_2d(second ? &tmO1 : &tmO0, stg, 0, node * rows_per_node + row0); }
+            if (nchw) { if (node < p.nodes && (int64_t)tm * BM < p.M) tma_store_2d(second ? &tmO1 : &tmO0, stg, 0, node * rows_per_node + row0); }
             else if (n0 < p.N) tma_store_2d(&tmO0, stg, (int)n0, tm * BM);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -350,6 +403,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // ================================ teardown ================================
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();       // nobody leaves while a peer may still multicast into it or signal its barriers
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -418,22 +472,46 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
   return 0;
 }
 
-template <int BN>
-static int launch(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const TcParams& p, cudaStream_t st,
-                  const CUtensorMap* o0 = nullptr, const CUtensorMap* o1 = nullptr) {
+static int g_cluster = -1;    // RGNN_TC_CLUSTER=1 disables the 2-CTA multicast clusters (debug / A-B comparison)
+
+template <int BN, int CL>
+static int launch_cl(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const TcParams& p, cudaStream_t st,
+                     const CUtensorMap* o0, const CUtensorMap* o1) {
   constexpr size_t smem = 1024 + (size_t)NSTAGE * (BM * BK * 2 + BN * BK * 2) + 2 * 128 * 128 + 256;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_gemm_tc)");
     attr_done = true;
   }
-  const int work = p.tiles_m * p.tiles_n * p.splits;
-  int grid = work < kNumSMs ? work : kNumSMs;
-  if (grid < 1) return 0;
-  k_gemm_tc<BN><<<grid, 256, smem, st>>>(a, b0, b1, o0 ? *o0 : a, o1 ? *o1 : (o0 ? *o0 : a), p);
-  RGNN_LAUNCH_CHECK("k_gemm_tc");
+  const int64_t work = (int64_t)((p.tiles_m + CL - 1) / CL) * p.tiles_n * p.splits;
+  int64_t groups = work < kNumSMs / CL ? work : kNumSMs / CL;
+  if (groups < 1) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(groups * CL));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  count_launch();
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, CL>, a, b0, b1, o0 ? *o0 : a, o1 ? *o1 : (o0 ? *o0 : a), p);
+  if (e != cudaSuccess) return cuda_fail(e, "k_gemm_tc launch");
   return 0;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const TcParams& p, cudaStream_t st,
+                  const CUtensorMap* o0 = nullptr, const CUtensorMap* o1 = nullptr) {
+  if (g_cluster < 0) {
+    const char* e = getenv("RGNN_TC_CLUSTER");
+    g_cluster = (e && e[0] == '1') ? 1 : 2;
+  }
+  // clusters only pay when there are at least two M-tiles to pair up
+  if (g_cluster == 2 && p.tiles_m >= 2) return launch_cl<BN, 2>(a, b0, b1, p, st, o0, o1);
+  return launch_cl<BN, 1>(a, b0, b1, p, st, o0, o1);
 }
 
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -475,12 +553,12 @@ extern "C" int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const 
   }
   {
     const uint64_t d[3] = {64, (uint64_t)c0, (uint64_t)nodes}, s[2] = {128, (uint64_t)c0 * 128};
-    const uint32_t b[3] = {64, 64, BN / 64};
+    const uint32_t b[3] = {64, 64, BN / 128};        // half of the tile's robots per box (see k_gemm_tc, CL)
     int rc = make_map(&tb0, x0, 3, d, s, b); if (rc) return rc;
   }
   if (c1 > 0) {
     const uint64_t d[3] = {64, (uint64_t)c1, (uint64_t)nodes}, s[2] = {128, (uint64_t)c1 * 128};
-    const uint32_t b[3] = {64, 64, BN / 64};
+    const uint32_t b[3] = {64, 64, BN / 128};
     int rc = make_map(&tb1, x1, 3, d, s, b); if (rc) return rc;
   } else tb1 = tb0;
   TcParams p = {};
@@ -528,12 +606,12 @@ extern "C" int rgnn_tc_conv1x1_wgrad(const void* dy, int64_t M, const void* x0, 
   }
   {
     const uint64_t d[2] = {64, (uint64_t)(nodes * c0)}, s[1] = {128};
-    const uint32_t b[2] = {64, BN};
+    const uint32_t b[2] = {64, BN / 2};
     int rc = make_map(&tb0, x0, 2, d, s, b); if (rc) return rc;
   }
   if (c1 > 0) {
     const uint64_t d[2] = {64, (uint64_t)(nodes * c1)}, s[1] = {128};
-    const uint32_t b[2] = {64, BN};
+    const uint32_t b[2] = {64, BN / 2};
     int rc = make_map(&tb1, x1, 2, d, s, b); if (rc) return rc;
   } else tb1 = tb0;
   if (splits > nodes) splits = nodes;
@@ -578,7 +656,7 @@ extern "C" int rgnn_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_
   }
   {
     const uint64_t d[2] = {(uint64_t)K, (uint64_t)N}, s[1] = {(uint64_t)ldb * 2};
-    const uint32_t b[2] = {64, (uint32_t)BN};
+    const uint32_t b[2] = {64, (uint32_t)BN / 2};
     int rc = make_map(&tb, B, 2, d, s, b); if (rc) return rc;
   }
   TcParams p = {};
