@@ -27,35 +27,49 @@ template <> __device__ __forceinline__ void st_pair<__nv_bfloat16>(__nv_bfloat16
 __host__ __device__ constexpr int edge_id(int K, int u, int a) { return u * (K - 1) + (a < u ? a : a - 1); }
 
 // Software-pipelined like the backward below: the K vectors of iteration r+1 are in flight while iteration r computes.
+// The kernel is instruction-issue sensitive (ncu: ~55% issue utilisation at 4 TB/s), so the loop carries (graph, offset)
+// incrementally instead of dividing, walks z with pointer bumps, and in bf16 folds the K-1 betas into one add per output.
 template <typename T, int K, bool HAS_Z>
 __global__ void __launch_bounds__(256, (K <= 5 ? 2 : 1)) k_film_fwd_complete(const T* __restrict__ x, int64_t ldx, const T* __restrict__ z,
-                                                              T* __restrict__ out, int64_t ldout, T* __restrict__ copy_to,
-                                                              int64_t G, int F, int P) {
+                                                                             T* __restrict__ out, int64_t ldout, T* __restrict__ copy_to,
+                                                                             int64_t G, int F, int P) {
   constexpr int VEC = Vec16<T>::N;
+  constexpr int NE = K * (K - 1);
   constexpr bool EXACT = sizeof(T) == 4;       // fp32: reference rounding order; bf16: fused multiply-add
-  const int64_t row_vecs = (int64_t)F * P / VEC;
-  const int64_t total = G * row_vecs;
+  const int row_vecs = (int)((int64_t)F * P / VEC);
+  const int64_t total = G * (int64_t)row_vecs;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t dg = stride / row_vecs;
+  const int dj = (int)(stride - dg * row_vecs);
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
+  int64_t ng = t / row_vecs;
+  int nj = (int)(t - ng * row_vecs);
+  const int64_t zrow = 2 * (int64_t)F;
   uint4 nx[K];
-  int64_t ng = t / row_vecs, noff = (t - ng * row_vecs) * VEC;
 #pragma unroll
-  for (int u = 0; u < K; ++u) nx[u] = *reinterpret_cast<const uint4*>(x + (ng * K + u) * ldx + noff);
+  for (int u = 0; u < K; ++u) nx[u] = *reinterpret_cast<const uint4*>(x + (ng * K + u) * ldx + (int64_t)nj * VEC);
   while (true) {
-    const int64_t g = ng, off = noff;
-    const int c = (int)(off / P);
-    const int64_t n0 = g * K, e0 = g * (K * (K - 1));
+    const int64_t g = ng;
+    const int off = nj * VEC;
+    const int c = off / P;
+    const int64_t n0 = g * K;
     uint4 cx[K];
 #pragma unroll
     for (int u = 0; u < K; ++u) cx[u] = nx[u];
-    const T* zc = z + e0 * 2 * F + 2 * c;
+    float2 gb[NE];
+    if (HAS_Z) {
+      const T* zp = z + g * NE * zrow + 2 * c;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) { gb[e] = ldg_pair<T>(zp); zp += zrow; }
+    }
     t += stride;
     const bool more = t < total;
     if (more) {
-      ng = t / row_vecs; noff = (t - ng * row_vecs) * VEC;
+      ng += dg; nj += dj;
+      if (nj >= row_vecs) { nj -= row_vecs; ++ng; }
 #pragma unroll
-      for (int u = 0; u < K; ++u) nx[u] = *reinterpret_cast<const uint4*>(x + (ng * K + u) * ldx + noff);
+      for (int u = 0; u < K; ++u) nx[u] = *reinterpret_cast<const uint4*>(x + (ng * K + u) * ldx + (int64_t)nj * VEC);
     }
     float xv[K][VEC];
 #pragma unroll
@@ -69,19 +83,21 @@ __global__ void __launch_bounds__(256, (K <= 5 ? 2 : 1)) k_film_fwd_complete(con
       float acc[VEC];
 #pragma unroll
       for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
+      float bsum = 0.f;
 #pragma unroll
       for (int u = 0; u < K; ++u) {      // ascending u == ascending edge id among the in-edges of a
         if (u == a) continue;
-        const float2 p2 = HAS_Z ? ldg_pair<T>(zc + (int64_t)edge_id(K, u, a) * 2 * F) : make_float2(1.f, 0.f);
+        const float2 p2 = HAS_Z ? gb[edge_id(K, u, a)] : make_float2(1.f, 0.f);
+        if (HAS_Z && !EXACT) bsum += p2.y;
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
           if (!HAS_Z) acc[q] = __fadd_rn(acc[q], xv[u][q]);
           else if (EXACT) acc[q] = __fadd_rn(acc[q], __fadd_rn(__fmul_rn(p2.x, xv[u][q]), p2.y));
-          else acc[q] += fmaf(p2.x, xv[u][q], p2.y);
+          else acc[q] = fmaf(p2.x, xv[u][q], acc[q]);
         }
       }
 #pragma unroll
-      for (int q = 0; q < VEC; ++q) acc[q] = EXACT ? __fdiv_rn(acc[q], (float)(K - 1)) : acc[q] * (1.0f / (K - 1));
+      for (int q = 0; q < VEC; ++q) acc[q] = EXACT ? __fdiv_rn(acc[q], (float)(K - 1)) : (acc[q] + bsum) * (1.0f / (K - 1));
       Vec16<T>::store(out + (n0 + a) * ldout + off, acc);
     }
     if (!more) break;
@@ -128,21 +144,33 @@ __global__ void __launch_bounds__(256, 1) k_film_bwd_complete(const T* __restric
   constexpr int VEC = Vec16<T>::N;
   constexpr int NE = K * (K - 1);
   constexpr int NVP = (NE + LPC - 1) / LPC * LPC;
-  const int64_t row_vecs = (int64_t)F * LPC;
-  const int64_t total = G * row_vecs;
+  const int row_vecs = F * LPC;
+  const int64_t total = G * (int64_t)row_vecs;
   const float w = 1.0f / (K - 1);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t rounds = (total + stride - 1) / stride;
+  const int64_t dgs = stride / row_vecs;
+  const int djs = (int)(stride - dgs * row_vecs);
   const int l = threadIdx.x % LPC;
   const bool has_add = addend != nullptr;
+  const int64_t zrow = 2 * (int64_t)F;
+  // the edges this lane finishes after the reduce-scatter (loop invariant): id, destination, z row offset
+  int my_e[NVP / LPC], my_a[NVP / LPC];
+#pragma unroll
+  for (int i = 0; i < NVP / LPC; ++i) {
+    const int e = scattered_id<NVP, LPC>(i, l);
+    const int u = e / (K - 1), jj = e % (K - 1);
+    my_e[i] = e < NE ? e : -1;
+    my_a[i] = jj < u ? jj : jj + 1;
+  }
 
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint4 nh[K], nd[K], na[K];
   bool nlive = t < total;
-  int64_t ng = 0, noff = 0;
+  int64_t ng = nlive ? t / row_vecs : 0;
+  int nj = nlive ? (int)(t - ng * row_vecs) : 0;
   auto fetch = [&]() {
-    ng = t / row_vecs;
-    noff = (t - ng * row_vecs) * VEC;
+    const int64_t noff = (int64_t)nj * VEC;
 #pragma unroll
     for (int u = 0; u < K; ++u) {
       nh[u] = *reinterpret_cast<const uint4*>(h + (ng * K + u) * ldh + noff);
@@ -156,23 +184,30 @@ __global__ void __launch_bounds__(256, 1) k_film_bwd_complete(const T* __restric
 
   for (int64_t r = 0; r < rounds; ++r) {         // whole warps iterate together (shuffles below)
     const bool live = nlive;
-    const int64_t g = ng, off = noff;
-    const int c = (int)(off / P);
-    const int64_t n0 = g * K, e0 = g * NE;
-    const T* zc = z + e0 * 2 * F + 2 * c;
+    const int64_t g = ng;
+    const int off = nj * VEC;
+    const int c = off / P;
+    const int64_t n0 = g * K;
+    const T* zc = z + g * NE * zrow + 2 * c;
     float hv[K][VEC], dv[K][VEC];
     uint4 ca[K];
 #pragma unroll
     for (int u = 0; u < K; ++u) { Vec16<T>::unpack(nh[u], hv[u]); Vec16<T>::unpack(nd[u], dv[u]); ca[u] = na[u]; }
     // gamma of every edge of the graph for this channel (the LPC lanes of a channel read the same bytes: broadcast)
     float gam[NE];
+    {
+      const T* zp = zc;
 #pragma unroll
-    for (int e = 0; e < NE; ++e) gam[e] = live ? ldg_pair<T>(zc + (int64_t)e * 2 * F).x : 0.f;
+      for (int e = 0; e < NE; ++e) { gam[e] = live ? ldg_pair<T>(zp).x : 0.f; zp += zrow; }
+    }
     // ---- prefetch the next iteration
     t += stride;
     nlive = t < total;
-    if (nlive) fetch();
-    else {
+    if (nlive) {
+      ng += dgs; nj += djs;
+      if (nj >= row_vecs) { nj -= row_vecs; ++ng; }
+      fetch();
+    } else {
 #pragma unroll
       for (int u = 0; u < K; ++u) { nh[u] = make_uint4(0, 0, 0, 0); nd[u] = nh[u]; }
     }
@@ -232,20 +267,17 @@ __global__ void __launch_bounds__(256, 1) k_film_bwd_complete(const T* __restric
     if (live) {
 #pragma unroll
       for (int i = 0; i < NVP / LPC; ++i) {
-        const int e = scattered_id<NVP, LPC>(i, l);
-        if (e < NE) {
-          const int u = e / (K - 1), jj = e % (K - 1);
-          const int a = jj < u ? jj : jj + 1;
+        if (my_e[i] >= 0) {
           float sda = sd[0];
 #pragma unroll
-          for (int q = 1; q < K; ++q) sda = (a == q) ? sd[q] : sda;
-          const int64_t zi = (int64_t)e * 2 * F;
+          for (int q = 1; q < K; ++q) sda = (my_a[i] == q) ? sd[q] : sda;
+          const int64_t zi = my_e[i] * zrow;
           float dg = pg[i] * w, db = sda * w;
           if (fuse_sig) {
             const float2 gb = ldg_pair<T>(zc + zi);
             dg *= gb.x * (1.f - gb.x); db *= gb.y * (1.f - gb.y);
           }
-          st_pair<T>(dz + e0 * 2 * F + 2 * c + zi, dg, db);
+          st_pair<T>(dz + (zc - z) + zi, dg, db);
         }
       }
     }
