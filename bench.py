@@ -254,9 +254,16 @@ def main():
                          "frac": round(ach / (hbm_peak if is_mem else tc_peak), 4)}
     top, topd = by_time[0]
     top_mem = top.startswith(MEM_KERNELS)
+    traffic = None
+    try:    # measured once under ncu --set full for this exact workload (profiles/); only valid for the default workload
+        if (G, K, F, a.dtype) == (4096, 5, 512, "bf16"):
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json"))).get(top)
+    except Exception:
+        pass
     roofline = {"kernel": top, "bound": "hbm" if top_mem else "tensor", "achieved": kernels[top]["achieved"],
                 "peak": hbm_peak if top_mem else tc_peak, "unit": kernels[top]["unit"], "frac": kernels[top]["frac"],
-                "traffic": None, "peak_source": peak_src, "ms_avg_per_launch": kernels[top]["ms_avg"]}
+                "traffic": traffic, "algorithmic_per_launch": topd["work_total"] / max(1, topd["calls"]),
+                "peak_source": peak_src, "ms_avg_per_launch": kernels[top]["ms_avg"]}
 
     cpu = None
     if not a.no_cpu_baseline:

@@ -34,8 +34,57 @@ __global__ void __launch_bounds__(256) k_mlp1_fwd(const float* __restrict__ pose
   }
 }
 
-// dw1[f,j] = sum_e da1[e,f] pose[e,j]; db1[f] = sum_e da1[e,f].  grid = (ceil(F/64), chunks over E); atomics on fp32
-// (outputs zeroed by the caller wrapper).  Thread = feature, loops edges of its chunk (coalesced over f).
+// dw1[f,j] = sum_e da1[e,f] pose[e,j]; db1[f] = sum_e da1[e,f].  Thread = 16-byte vector of features (coalesced 128-bit row reads),
+// streams its chunk of edges with the 9 pose values of each edge broadcast from shared memory; fp32 atomics at the end
+// (outputs zeroed by the caller wrapper).  grid = (ceil(F/VEC/64), chunks over E).
+template <typename T>
+__global__ void __launch_bounds__(64) k_mlp1_bwd_vec(const float* __restrict__ pose, const T* __restrict__ da1,
+                                                     float* __restrict__ dw1, float* __restrict__ db1, int64_t E, int F, int64_t chunk) {
+  constexpr int VEC = Vec16<T>::N;
+  const int fv = blockIdx.x * 64 + threadIdx.x;            // feature-vector index
+  const bool live = fv * VEC < F;
+  const int64_t e0 = (int64_t)blockIdx.y * chunk, e1 = min(E, e0 + chunk);
+  __shared__ float sp[64][9];
+  float acc[VEC][10];
+#pragma unroll
+  for (int q = 0; q < VEC; ++q)
+#pragma unroll
+    for (int j = 0; j < 10; ++j) acc[q][j] = 0.f;
+  for (int64_t base = e0; base < e1; base += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 9; i += 64) {
+      const int64_t e = base + i / 9;
+      sp[i / 9][i % 9] = e < e1 ? pose[e * 9 + i % 9] : 0.f;
+    }
+    __syncthreads();
+    if (live) {
+      const int n = (int)min((int64_t)64, e1 - base);
+      const T* row = da1 + base * F + (int64_t)fv * VEC;
+#pragma unroll 2
+      for (int r = 0; r < n; ++r) {
+        float d[VEC];
+        Vec16<T>::load(row + (int64_t)r * F, d);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+#pragma unroll
+          for (int j = 0; j < 9; ++j) acc[q][j] = fmaf(d[q], sp[r][j], acc[q][j]);
+          acc[q][9] += d[q];
+        }
+      }
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      const int f = fv * VEC + q;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) atomicAdd(dw1 + f * 9 + j, acc[q][j]);
+      atomicAdd(db1 + f, acc[q][9]);
+    }
+  }
+}
+
+// scalar variant for feature counts that are not a multiple of the 16-byte vector
 template <typename T>
 __global__ void __launch_bounds__(64) k_mlp1_bwd(const float* __restrict__ pose, const T* __restrict__ da1,
                                                  float* __restrict__ dw1, float* __restrict__ db1, int64_t E, int F, int64_t chunk) {
@@ -99,17 +148,24 @@ extern "C" int rgnn_edge_mlp1_bwd(int dtype, const float* pose, const void* da1,
   if (e != cudaSuccess) return cuda_fail(e, "memset dw1/db1");
   if (E == 0) return 0;
   RGNN_REQUIRE(pose && da1, RGNN_E_ARG, "rgnn_edge_mlp1_bwd: null input");
-  const int fb = (int)((F + 63) / 64);
-  int64_t chunks = (4 * kNumSMs + fb - 1) / fb;
-  const int64_t max_chunks = (E + 255) / 256;
+  const int es = dtype == RGNN_F32 ? 4 : 2, vec = 16 / es;
+  const bool vec_ok = F % vec == 0 && (reinterpret_cast<uintptr_t>(da1) & 15u) == 0;
+  const int fb = vec_ok ? (int)((F / vec + 63) / 64) : (int)((F + 63) / 64);
+  int64_t chunks = (8 * kNumSMs + fb - 1) / fb;
+  const int64_t max_chunks = (E + 63) / 64;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   if (chunks > 65535) chunks = 65535;
   const int64_t chunk = ((E + chunks - 1) / chunks + 63) / 64 * 64;
   chunks = (E + chunk - 1) / chunk;
   dim3 grid(fb, (unsigned)chunks);
-  if (dtype == RGNN_F32) k_mlp1_bwd<float><<<grid, 64, 0, st>>>(pose, static_cast<const float*>(da1), dw1, db1, E, (int)F, chunk);
-  else k_mlp1_bwd<__nv_bfloat16><<<grid, 64, 0, st>>>(pose, static_cast<const __nv_bfloat16*>(da1), dw1, db1, E, (int)F, chunk);
+  if (vec_ok) {
+    if (dtype == RGNN_F32) k_mlp1_bwd_vec<float><<<grid, 64, 0, st>>>(pose, static_cast<const float*>(da1), dw1, db1, E, (int)F, chunk);
+    else k_mlp1_bwd_vec<__nv_bfloat16><<<grid, 64, 0, st>>>(pose, static_cast<const __nv_bfloat16*>(da1), dw1, db1, E, (int)F, chunk);
+  } else {
+    if (dtype == RGNN_F32) k_mlp1_bwd<float><<<grid, 64, 0, st>>>(pose, static_cast<const float*>(da1), dw1, db1, E, (int)F, chunk);
+    else k_mlp1_bwd<__nv_bfloat16><<<grid, 64, 0, st>>>(pose, static_cast<const __nv_bfloat16*>(da1), dw1, db1, E, (int)F, chunk);
+  }
   RGNN_LAUNCH_CHECK("k_mlp1_bwd");
   return 0;
 }
