@@ -82,24 +82,32 @@ class GNNBlock(nn.Module):
             self.gcn2 = GCN(opt, return_key, film)
             self.conv2 = nn.Conv2d(f * 2, f, kernel_size=1)
 
-    def _layer(self, g, h, pose, gcn, conv):
-        if gcn.return_key == "images" and gcn.film:       # the whole layer as one fused autograd node
-            l0, l2 = gcn.edge_encoder.layers[0], gcn.edge_encoder.layers[2]
-            return Fn.gnn_layer(g, h, pose, l0.weight, l0.bias, l2.weight, l2.bias, conv.weight, conv.bias)
-        return Fn.compress(h, gcn(g, h, pose), conv.weight, conv.bias)
-
     def forward(self, g, h, pose=None):
-        pose = g.edata['pose'] if pose is None else pose
-        if self.opt.compress_gcn:
-            h = self._layer(g, h, pose, self.gcn1, self.conv1)
-        elif self.gcn1.return_key == "image":
-            h = torch.cat((h, h), dim=1)                                       # literal reference
-        else:                                                                   # cat(h, g_h) fused into the aggregation
-            z = self.gcn1.edge_encoder.film(pose, h.dtype) if self.gcn1.film else None
-            h = Fn.film_mean_cat(g, h, z)
-        if getattr(self.opt, "multi_gcn", False):
-            h = self._layer(g, h, pose, self.gcn2, self.conv2)
-        return h
+        return gnn_slice(self, g, h, pose)
+
+
+def _gnn_layer(g, h, pose, gcn, conv):
+    if gcn.return_key == "images" and gcn.film:       # the whole layer as one fused autograd node
+        l0, l2 = gcn.edge_encoder.layers[0], gcn.edge_encoder.layers[2]
+        return Fn.gnn_layer(g, h, pose, l0.weight, l0.bias, l2.weight, l2.bias, conv.weight, conv.bias)
+    return Fn.compress(h, gcn(g, h, pose), conv.weight, conv.bias)
+
+
+def gnn_slice(mod, g, h, pose=None):
+    """dgl/model/models.py:180-189 on any module that owns gcn1[/conv1][/gcn2/conv2] and .opt (GNNBlock, or a
+    multi_view_dgl_model that keeps the reference's flat parameter names)."""
+    opt = mod.opt
+    pose = g.edata['pose'] if pose is None else pose
+    if opt.compress_gcn:
+        h = _gnn_layer(g, h, pose, mod.gcn1, mod.conv1)
+    elif mod.gcn1.return_key == "image":
+        h = torch.cat((h, h), dim=1)                                       # literal reference (SURVEY F5)
+    else:                                                                   # cat(h, g_h) fused into the aggregation
+        z = mod.gcn1.edge_encoder.film(pose, h.dtype) if mod.gcn1.film else None
+        h = Fn.film_mean_cat(g, h, z)
+    if getattr(opt, "multi_gcn", False):
+        h = _gnn_layer(g, h, pose, mod.gcn2, mod.conv2)
+    return h
 
 
 class GraphConv(nn.Module):

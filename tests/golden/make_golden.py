@@ -294,11 +294,23 @@ def golden_pose():
         poses=poses, edges=edges)
 
 
+def golden_model_keys():
+    """state_dict keys + shapes of the reference multi_view_dgl_model (pins the script-level drop-in, compat/model/models.py)."""
+    import json
+    out = {}
+    for name, kw in {"resnet18_compress_multi": dict(backbone="resnet18", feature_dim=512, compress_gcn=True, multi_gcn=True, skip_level=False),
+                     "mobilenetv2_plain_skip": dict(backbone="mobilenetv2", feature_dim=1280, compress_gcn=False, multi_gcn=False, skip_level=True)}.items():
+        opt = types.SimpleNamespace(pretrained=False, camera_num=5, image_size=64, task="depth", output_dim=1, **kw)
+        out[name] = {k: list(v.shape) for k, v in ref.multi_view_dgl_model(opt).state_dict().items()}
+    json.dump(out, open(os.path.join(HERE, "model_state_keys.json"), "w"))
+    print("wrote model_state_keys.json")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
     a = ap.parse_args()
-    todo = dict(csr=golden_csr, layers=golden_layers, blocks=golden_blocks, script=golden_script_shape, pose=golden_pose)
+    todo = dict(csr=golden_csr, layers=golden_layers, blocks=golden_blocks, script=golden_script_shape, pose=golden_pose, keys=golden_model_keys)
     for k, fn_ in todo.items():
         if a.only in (None, k):
             print("==", k)
