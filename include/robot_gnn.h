@@ -94,6 +94,12 @@ int rgnn_build_batched_csr(const int64_t* src, const int64_t* dst, int64_t num_n
 int rgnn_check_complete(const int64_t* src, const int64_t* dst, int64_t num_graphs, int64_t robots, int64_t num_edges,
                         int32_t* status, void* stream);
 
+/* ---- next-row 3: edge features from raw robot poses (dgl/utils.py:54-77, dgl/dataloader.py:116-122) -------------
+ * poses [G, K, 7] (xyz + quaternion xyzw; fp64 if pose_is_f64 else fp32) -> edge_pose [G*K*(K-1), 9] fp32 in the reference's
+ * edge order: (t_j - t_i) || first six column-major entries of R(q_j * conj(q_i)).  fp64 arithmetic in the reference's
+ * operation order, rounded to fp32 at the end: bit-identical to cal_relative_pose(...).float(). */
+int rgnn_relative_pose(int pose_is_f64, const void* poses, float* edge_pose, int64_t num_graphs, int64_t robots, void* stream);
+
 /* ---- A5/A6 (+A10, A11): fused gather -> FiLM / normalise -> sum|mean ----------------------
  * out[v,c,p] = post_v( sum_{i in [ptr[v],ptr[v+1])} ( gamma(eid_i,c) * nbr_scale[nbr_i] * x[nbr_i,c,p]
  *                                                    + beta(eid_i,c) ) ) + addend[v,c,p]

@@ -24,6 +24,7 @@ SIGNATURES = {
     "rgnn_aggregate": [_i32, _vp, _i64, _vp, _i32, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp]
                       + [_i64] * 8 + [_vp],
     "rgnn_check_complete": [_vp, _vp, _i64, _i64, _i64, _vp, _vp],
+    "rgnn_relative_pose": [_i32, _vp, _vp, _i64, _i64, _vp],
     "rgnn_film_edge_grad": [_i32, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     "rgnn_film_backward": [_i32, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp] + [_i64] * 8 + [_vp],
     "rgnn_edge_mlp1_fwd": [_i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp],

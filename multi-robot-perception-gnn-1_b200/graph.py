@@ -260,3 +260,19 @@ def robot_batch(num_graphs, num_robots, device=None):
                    d.repeat(num_graphs).to(device) if device else d.repeat(num_graphs),
                    [k] * num_graphs, [k * (k - 1)] * num_graphs, complete_k=k)
     return g
+
+
+def relative_pose_edges(poses):
+    """Edge features for G samples of K robots from raw poses [G, K, 7] (xyz + quaternion xyzw) in the reference's edge order -
+    the batched, on-device replacement of the per-sample cal_relative_pose loops (dgl/dataloader.py:116-122, dgl/utils.py:54-77).
+    Returns [G*K*(K-1), 9] fp32, bit-identical to the reference's float64 computation rounded with .float()."""
+    _lib.require_cuda(poses)
+    if poses.dim() != 3 or poses.shape[-1] != 7 or poses.dtype not in (torch.float32, torch.float64):
+        raise ValueError("poses must be [G, K, 7] float32/float64")
+    poses = poses.contiguous()
+    g, k = poses.shape[0], poses.shape[1]
+    out = torch.empty((g * k * (k - 1), 9), dtype=torch.float32, device=poses.device)
+    with torch.cuda.device(poses.device):
+        _lib.check(_lib.lib().rgnn_relative_pose(int(poses.dtype == torch.float64), _lib.ptr(poses), _lib.ptr(out), g, k, _lib.stream()),
+                   "rgnn_relative_pose")
+    return out

@@ -353,3 +353,23 @@ def test_gcn2conv_vs_dgl_formula(R, project):
     assert nerr(conv.bias.grad, t[4].grad) <= 2 * FP32_TOL
     if not project:
         assert nerr(conv.weight2.grad, t[3].grad) <= 2 * FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------ next-row 3
+def test_relative_pose_edges_bit_exact(R):
+    """GPU edge-feature producer vs the reference's cal_relative_pose (dgl/utils.py:54-77) golden values, reference edge order."""
+    import os
+    from conftest import GOLDEN
+    from oracle import gnn_oracle as O
+    z = np.load(os.path.join(GOLDEN, "pose_cases.npz"))
+    got = R.relative_pose_edges(torch.from_numpy(z["poses"]).unsqueeze(0).cuda())
+    assert torch.equal(got.cpu(), torch.from_numpy(z["edges"]).float())
+    pair = torch.from_numpy(np.stack([z["p1"], z["p2"]])).unsqueeze(0).cuda()           # the reference's own self-check pair
+    got2 = R.relative_pose_edges(pair)
+    assert torch.equal(got2[0].cpu(), torch.from_numpy(z["rel12"]).float())
+    rng = np.random.RandomState(3)                                                        # a batch, several K
+    for k in (2, 4, 7):
+        poses = rng.randn(6, k, 7)
+        poses[..., 3:] /= np.linalg.norm(poses[..., 3:], axis=-1, keepdims=True)
+        ref = np.concatenate([O.relative_pose_edges(poses[g], k) for g in range(6)], 0)
+        assert torch.equal(R.relative_pose_edges(torch.from_numpy(poses).cuda()).cpu(), torch.from_numpy(ref).float())
