@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: scaling sweep over robots-per-graph x graphs-per-batch (fwd+bwd of the two-layer block, F=512,
+bf16, one GPU per process; run under torchrun for the multi-GPU variant).  The 64 robots x 64k graphs corner is 0.67 TB of
+bf16 features - cells whose tensors would exceed --mem-gb are skipped and reported as capped.
+
+    python benchmarks/sweep.py [--robots 4 8 16 32 64] [--graphs 1024 4096 16384 65536] [--feat 512] [--mem-gb 120]
+Prints one JSON line per cell.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def cell_bytes(g, k, f, es=2):
+    n, e = g * k, g * k * (k - 1)
+    feat = n * f * 64 * es
+    edge = e * f * es
+    # per layer: h, agg, y, dy, dh, dgh (features) ; a1, da1 (edge x F) ; z, dz, dzp (edge x 2F)
+    return 2 * (6 * feat + 2 * edge + 3 * 2 * edge) + 2 * feat
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--robots", type=int, nargs="+", default=[4, 8, 16, 32, 64])
+    ap.add_argument("--graphs", type=int, nargs="+", default=[1024, 4096, 16384, 65536])
+    ap.add_argument("--feat", type=int, default=512)
+    ap.add_argument("--mem-gb", type=float, default=120.0)
+    ap.add_argument("--steps", type=int, default=5)
+    a = ap.parse_args()
+    import robot_gnn_b200 as R
+    from multi_robot_check import make_block
+    from oracle import gnn_oracle as O      # parameter init only
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    blk, _ = make_block(R, O, a.feat, True, True, seed=1)
+    blk.to(dev)
+    for k in a.robots:
+        for g in a.graphs:
+            need = cell_bytes(g, k, a.feat) / 1e9
+            rec = {"robots": k, "graphs": g, "feat": a.feat, "est_gb": round(need, 1)}
+            if need > a.mem_gb:
+                rec["capped"] = True
+                print(json.dumps(rec), flush=True)
+                continue
+            n, e = g * k, g * k * (k - 1)
+            gen = torch.Generator(device=dev).manual_seed(1)
+            h = torch.rand((n, a.feat, 8, 8), generator=gen, device=dev).bfloat16().requires_grad_()
+            dy = torch.randn((n, a.feat, 8, 8), generator=gen, device=dev).bfloat16()
+            pose = torch.randn((e, 9), generator=gen, device=dev)
+            gr = R.robot_batch(g, k, device=dev)
+
+            def step():
+                h.grad = None
+                for p in blk.parameters():
+                    p.grad = None
+                blk(gr, h, pose).backward(dy)
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / a.steps
+            flops = 2 * 3 * (4 * e * a.feat ** 2 + 4 * n * 64 * a.feat ** 2)
+            rec.update(ms_per_step=round(ms, 3), graphs_per_s=round(g / ms * 1e3, 1), tflops=round(flops / ms / 1e9, 1),
+                       path="register kernels (K<=8)" if k <= 8 else "staged shared-memory kernels")
+            print(json.dumps(rec), flush=True)
+            del h, dy, pose, gr
+            torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
