@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--feat", type=int, default=F_DIM)
     ap.add_argument("--robots", type=int, default=K_ROBOTS)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cuda-graph", action="store_true", help="replay the step from a captured CUDA graph (small batches)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="graph chunks the host-buffer pipeline overlaps")
@@ -169,6 +170,10 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if a.cuda_graph and world == 1:
+        graphed = R.GraphedStep(blk, g, h, pose, dy)
+        step = lambda: graphed()      # noqa: E731  (inputs already live in the static buffers)
 
     for _ in range(max(a.warmup, 3)):
         step()

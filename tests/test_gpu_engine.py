@@ -37,3 +37,35 @@ def test_host_pipeline_matches_single_shot(R, dtype, tol):
     assert nerr(oy.float(), y_ref) <= tol and nerr(odh.float(), dh_ref) <= tol
     for n, p in blk.named_parameters():
         assert nerr(p.grad, ref[n]) <= 2 * tol, n
+
+
+@pytest.mark.parametrize("dtype,f", [(torch.bfloat16, 512), (torch.float32, 64)])
+def test_cuda_graph_replay_matches_eager(R, dtype, f):
+    """Script shape (G=8, K=5): the captured step must reproduce the eager step bit for bit, for fresh inputs on every replay."""
+    from multi_robot_check import make_block
+    from oracle import gnn_oracle as O
+    G, K = 8, 5
+    blk, _ = make_block(R, O, f, True, True)
+    blk.cuda()
+    g = R.robot_batch(G, K, device="cuda")
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    mk = lambda: (torch.rand((G * K, f, 8, 8), generator=gen, device="cuda").to(dtype),
+                  torch.randn((G * K * (K - 1), 9), generator=gen, device="cuda"),
+                  torch.randn((G * K, f, 8, 8), generator=gen, device="cuda").to(dtype))
+    h0, p0, d0 = mk()
+    step = R.GraphedStep(blk, g, h0, p0, d0)
+    for _ in range(3):
+        h, pose, dy = mk()
+        y, dh = step(h, pose, dy)
+        torch.cuda.synchronize()
+        y, dh = y.clone(), dh.clone()
+        grads = {n: p.grad.clone() for n, p in blk.named_parameters()}
+        he = h.clone().requires_grad_()
+        for p in blk.parameters():
+            p.grad = None
+        ye = blk(g, he, pose)
+        ye.backward(dy)
+        assert torch.equal(y, ye) and torch.equal(dh, he.grad)
+        for n, p in blk.named_parameters():
+            # atomics in the bias / edge-MLP layer-1 gradient kernels reorder fp32 sums between runs
+            assert nerr(grads[n], p.grad) <= 1e-5, n
