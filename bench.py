@@ -257,6 +257,10 @@ def main():
         kernels[name] = {"calls": d["calls"], "ms_avg": round(d["ms_avg"], 4), "share": round(d["ms_total"] / ms_total, 4),
                          "achieved": round(ach, 2), "unit": "GB/s" if is_mem else "TFLOP/s",
                          "frac": round(ach / (hbm_peak if is_mem else tc_peak), 4)}
+    if not by_time:      # CUDA-graph replay: no per-call events exist
+        by_time = [("cuda_graph_replay", dict(work_total=0.0, calls=1))]
+        kernels["cuda_graph_replay"] = {"calls": a.steps, "ms_avg": round(ms_total / a.steps, 4), "share": 1.0, "achieved": 0.0,
+                                        "unit": "GB/s", "frac": 0.0}
     top, topd = by_time[0]
     top_mem = top.startswith(MEM_KERNELS)
     traffic = None

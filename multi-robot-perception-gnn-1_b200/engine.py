@@ -102,6 +102,7 @@ class GraphedStep:
         with torch.cuda.graph(self.cuda_graph):
             self._run()
         self.dh = self.h.grad
+        self.param_grads = [(p, p.grad) for p in block.parameters()]     # static tensors every replay overwrites
 
     def _run(self):
         self.y = self.block(self.g, self.h, self.pose)
@@ -116,4 +117,6 @@ class GraphedStep:
             if dy is not None:
                 self.dy.copy_(dy)
         self.cuda_graph.replay()
+        for p, gr in self.param_grads:      # re-attach in case the caller replaced or cleared .grad (optimizer.zero_grad)
+            p.grad = gr
         return self.y, self.dh
