@@ -454,6 +454,10 @@ int film_fwd_complete(int dtype, int K, const void* x, int64_t ldx, const void* 
                       int64_t G, int64_t F, int64_t P, cudaStream_t st);
 int film_bwd_complete(int dtype, int K, const void* h, int64_t ldh, const void* dagg, int64_t ldd, const void* z, const void* addend,
                       int64_t ldadd, void* dh, int64_t lddh, void* dz, int64_t G, int64_t F, int64_t P, int fuse_sig, cudaStream_t st);
+int film_fwd_dense(int dtype, int K, const void* x, int64_t ldx, const void* z, void* out, int64_t ldout, void* copy_to,
+                   int64_t G, int64_t F, int64_t P, cudaStream_t st);
+int film_bwd_dense(int dtype, int K, const void* h, int64_t ldh, const void* dagg, int64_t ldd, const void* z, const void* addend,
+                   int64_t ldadd, void* dh, int64_t lddh, void* dz, int64_t G, int64_t F, int64_t P, int fuse_sig, cudaStream_t st);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -497,6 +501,12 @@ extern "C" int rgnn_aggregate(int dtype, const void* x, int64_t ldx, const void*
   if (complete_k >= 2 && complete_k <= 8 && post == RGNN_POST_MEAN && !nbr_scale && !addend && N == G * complete_k &&
       E == G * complete_k * (complete_k - 1) && (!z || (reinterpret_cast<uintptr_t>(z) & (2 * es - 1)) == 0) && use_beta) {
     return film_fwd_complete(dtype, (int)complete_k, x, ldx, z, out, ldout, copy_x_to, G, F, P, st);
+  }
+  // ---- complete graphs with more robots than the register kernels hold: shared-memory staged, register-tiled over destinations
+  if (complete_k > 8 && complete_k < 4096 && vec_ok && post == RGNN_POST_MEAN && !nbr_scale && !addend && N == G * complete_k &&
+      E == G * complete_k * (complete_k - 1) && use_beta) {
+    const int rc = film_fwd_dense(dtype, (int)complete_k, x, ldx, z, out, ldout, copy_x_to, G, F, P, st);
+    if (rc != RGNN_E_UNSUPPORTED) return rc;
   }
   // ---- staged path: needs the batch layout and every graph's tile + CSR slice to fit shared memory
   const int maxK = (int)max_graph_nodes, maxE = (int)max_graph_edges;
@@ -599,6 +609,11 @@ extern "C" int rgnn_film_backward(int dtype, const void* h, int64_t ldh, const v
   if (complete_k >= 2 && complete_k <= 8 && N == G * complete_k && E == G * complete_k * (complete_k - 1)) {
     const int rc = film_bwd_complete(dtype, (int)complete_k, h, ldh, dagg, lddagg, z, addend, ldadd, dh, lddh, dz, G, F, P,
                                      fuse_sigmoid_grad, as_stream(stream));
+    if (rc != RGNN_E_UNSUPPORTED) return rc;
+  }
+  if (complete_k > 8 && complete_k < 4096 && N == G * complete_k && E == G * complete_k * (complete_k - 1)) {
+    const int rc = film_bwd_dense(dtype, (int)complete_k, h, ldh, dagg, lddagg, z, addend, ldadd, dh, lddh, dz, G, F, P,
+                                  fuse_sigmoid_grad, as_stream(stream));
     if (rc != RGNN_E_UNSUPPORTED) return rc;
   }
   const int zalign = 8 / es;

@@ -102,7 +102,7 @@ class RobotGraph:
             src, dst, noff, eoff = self._globals()
             n, e, g = self._n, self._e, len(self._bnn)
             i64 = lambda k: torch.empty(k, dtype=torch.int64, device=dev)
-            ix = SimpleNamespace(N=n, E=e, G=g, complete_k=self.complete_k if 2 <= self.complete_k <= 8 else 0, max_nodes=max(self._bnn, default=0), max_edges=max(self._bne, default=0),
+            ix = SimpleNamespace(N=n, E=e, G=g, complete_k=self.complete_k if 2 <= self.complete_k < 4096 else 0, max_nodes=max(self._bnn, default=0), max_edges=max(self._bne, default=0),
                                  src=src, dst=dst, node_offsets=noff, edge_offsets=eoff,
                                  in_deg=i64(n), out_deg=i64(n), in_ptr=i64(n + 1), in_src=i64(e), in_eid=i64(e),
                                  out_ptr=i64(n + 1), out_dst=i64(e), out_eid=i64(e),
