@@ -69,6 +69,30 @@ __device__ __forceinline__ void stage_tiles(uint64_t* bar, T* sa, const T* a, in
   }
 }
 
+// Stage the gamma/beta pairs of the edges {(u, a): u in [0,K), a in [a_base, a_base + AP)} (transposed = false) or
+// {(u, a): u in [u_base, u_base + AP), a in [0,K)} (transposed = true) for the tile's CT channels into shared memory:
+// zs[outer][inner_local][2*CT].  Each (edge, tile) row is 2*CT*sizeof(T) = 32 bytes = two independent 16-byte loads, all
+// issued up front by the whole CTA (the inner loops then touch shared memory only - no exposed global latency).
+template <typename T, int CT>
+__device__ __forceinline__ void stage_z(T* zs, const T* __restrict__ zc0, int64_t zrow, int K, int base, int AP, bool transposed) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int HALVES = 2 * CT / VEC;            // 16-byte pieces per row (2 for both dtypes)
+  const int total = K * AP * HALVES;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int hf = i % HALVES, al = (i / HALVES) % AP, o = i / (HALVES * AP);
+    const int u = transposed ? base + al : o, a = transposed ? o : base + al;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (u < K && a < K && u != a) v = __ldg(reinterpret_cast<const uint4*>(zc0 + (int64_t)edge_of(K, u, a) * zrow + hf * VEC));
+    *reinterpret_cast<uint4*>(zs + ((size_t)o * AP + al) * 2 * CT + hf * VEC) = v;
+  }
+}
+template <typename T> __device__ __forceinline__ float2 lds_pair(const T* p);
+template <> __device__ __forceinline__ float2 lds_pair<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float2 lds_pair<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // forward: out[a] = (1/(K-1)) sum_{u != a} (gamma[e(u,a)] * x[u] + beta[e(u,a)])     (HAS_Z = false: plain mean)
 template <typename T, int LPC, int R, bool HAS_Z>
@@ -76,31 +100,36 @@ __global__ void __launch_bounds__(256) k_film_fwd_dense(const T* __restrict__ x,
                                                         int64_t ldout, T* __restrict__ copy_to, int K, int F, int P) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int CT = NVEC / LPC;
+  constexpr int AP = NGRP * R;                 // destinations per pass
   constexpr bool EXACT = sizeof(T) == 4;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   T* xs = reinterpret_cast<T*>(smem + 128);
-  const int tiles_c = (F + CT - 1) / CT;
+  T* zs = xs + (size_t)K * CT * P;
+  const int tiles_c = F / CT;                  // host guarantees F % CT == 0
   const int64_t g = blockIdx.x / tiles_c;
   const int c0 = (int)(blockIdx.x % tiles_c) * CT;
-  const int ct = min(CT, F - c0);
   const int64_t n0 = g * K, e0 = g * (int64_t)K * (K - 1);
-  const int slice = ct * P;
+  const int slice = CT * P;
   if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
-  stage_tiles<T>(bar, xs, x, ldx, nullptr, nullptr, 0, n0, K, c0, ct, P);
+  stage_tiles<T>(bar, xs, x, ldx, nullptr, nullptr, 0, n0, K, c0, CT, P);
   const int j = threadIdx.x & (NVEC - 1), grp = threadIdx.x / NVEC;
-  const bool live = j * VEC < slice;
-  const int off = j * VEC, c = c0 + off / P;
+  const int off = j * VEC, cl = off / P;
   const int64_t zrow = 2 * (int64_t)F;
-  const T* zc = z + e0 * zrow + 2 * c;
+  const T* zc0 = z + e0 * zrow + 2 * c0;
+  if (HAS_Z) stage_z<T, CT>(zs, zc0, zrow, K, 0, AP, false);
   mbar_wait(bar, 0);
-  if (copy_to && grp == 0 && live) {
+  if (copy_to && grp == 0) {
     for (int u = 0; u < K; ++u)
       *reinterpret_cast<uint4*>(copy_to + (n0 + u) * ldout + (int64_t)c0 * P + off) = *reinterpret_cast<const uint4*>(xs + (size_t)u * slice + off);
   }
   const float inv = 1.0f / (K - 1);
-  for (int a0 = grp * R; a0 < K; a0 += NGRP * R) {
+  for (int a_base = 0; a_base < K; a_base += AP) {
+    if (HAS_Z && a_base > 0) { __syncthreads(); stage_z<T, CT>(zs, zc0, zrow, K, a_base, AP, false); }
+    __syncthreads();
+    const int a0 = a_base + grp * R;
+    if (a0 >= K) continue;
     float acc[R][VEC], bsum[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -108,34 +137,32 @@ __global__ void __launch_bounds__(256) k_film_fwd_dense(const T* __restrict__ x,
 #pragma unroll
       for (int q = 0; q < VEC; ++q) acc[r][q] = 0.f;
     }
-    if (live) {
-      for (int u = 0; u < K; ++u) {        // ascending source == ascending edge id among the in-edges of every destination
-        float xv[VEC];
-        Vec16<T>::load(xs + (size_t)u * slice + off, xv);
-        const T* zu = zc + (int64_t)u * (K - 1) * zrow;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int a = a0 + r;
-          if (a >= K || a == u) continue;
-          float2 gb = make_float2(1.f, 0.f);
-          if (HAS_Z) gb = ldg_pair<T>(zu + (int64_t)(a < u ? a : a - 1) * zrow);
-          if (HAS_Z && !EXACT) bsum[r] += gb.y;
-#pragma unroll
-          for (int q = 0; q < VEC; ++q) {
-            if (!HAS_Z) acc[r][q] = __fadd_rn(acc[r][q], xv[q]);
-            else if (EXACT) acc[r][q] = __fadd_rn(acc[r][q], __fadd_rn(__fmul_rn(gb.x, xv[q]), gb.y));
-            else acc[r][q] = fmaf(gb.x, xv[q], acc[r][q]);
-          }
-        }
-      }
+    for (int u = 0; u < K; ++u) {        // ascending source == ascending edge id among the in-edges of every destination
+      float xv[VEC];
+      Vec16<T>::load(xs + (size_t)u * slice + off, xv);
+      const T* zu = zs + ((size_t)u * AP + grp * R) * 2 * CT + 2 * cl;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int a = a0 + r;
-        if (a >= K) continue;
+        if (a >= K || a == u) continue;
+        float2 gb = make_float2(1.f, 0.f);
+        if (HAS_Z) gb = lds_pair<T>(zu + r * 2 * CT);
+        if (HAS_Z && !EXACT) bsum[r] += gb.y;
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) acc[r][q] = EXACT ? __fdiv_rn(acc[r][q], (float)(K - 1)) : (acc[r][q] + bsum[r]) * inv;
-        Vec16<T>::store(out + (n0 + a) * ldout + (int64_t)c0 * P + off, acc[r]);
+        for (int q = 0; q < VEC; ++q) {
+          if (!HAS_Z) acc[r][q] = __fadd_rn(acc[r][q], xv[q]);
+          else if (EXACT) acc[r][q] = __fadd_rn(acc[r][q], __fadd_rn(__fmul_rn(gb.x, xv[q]), gb.y));
+          else acc[r][q] = fmaf(gb.x, xv[q], acc[r][q]);
+        }
       }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int a = a0 + r;
+      if (a >= K) continue;
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) acc[r][q] = EXACT ? __fdiv_rn(acc[r][q], (float)(K - 1)) : (acc[r][q] + bsum[r]) * inv;
+      Vec16<T>::store(out + (n0 + a) * ldout + (int64_t)c0 * P + off, acc[r]);
     }
   }
 }
@@ -148,132 +175,125 @@ __global__ void __launch_bounds__(256) k_film_bwd_dense(const T* __restrict__ h,
                                                         T* __restrict__ dz, int K, int F, int P, int fuse_sig) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int CT = NVEC / LPC;
+  constexpr int AP = NGRP * R;                 // sources per pass
   static_assert(R == LPC, "the reduce-scatter below hands one finished source per lane of the channel group");
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-  const int tiles_c = (F + CT - 1) / CT;
+  const int tiles_c = F / CT;
   const int64_t g = blockIdx.x / tiles_c;
   const int c0 = (int)(blockIdx.x % tiles_c) * CT;
-  const int ct = min(CT, F - c0);
   const int64_t n0 = g * K, e0 = g * (int64_t)K * (K - 1);
-  const int slice = ct * P;
+  const int slice = CT * P;
   T* hs = reinterpret_cast<T*>(smem + 128);
-  T* ds = hs + (size_t)K * CT * P;
+  T* ds = hs + (size_t)K * slice;
+  T* zs = ds + (size_t)K * slice;
   if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
-  stage_tiles<T>(bar, hs, h, ldh, ds, dagg, ldd, n0, K, c0, ct, P);
+  stage_tiles<T>(bar, hs, h, ldh, ds, dagg, ldd, n0, K, c0, CT, P);
   const int j = threadIdx.x & (NVEC - 1), grp = threadIdx.x / NVEC;
   const int l = j % LPC;
-  const bool live = j * VEC < slice;
-  const int off = live ? j * VEC : 0, c = c0 + off / P;
+  const int off = j * VEC, cl = off / P;
   const int64_t zrow = 2 * (int64_t)F;
-  const T* zc = z + e0 * zrow + 2 * c;
-  T* dzc = dz + e0 * zrow + 2 * c;
+  const T* zc0 = z + e0 * zrow + 2 * c0;
+  T* dzc = dz + e0 * zrow + 2 * (c0 + cl);
   const float w = 1.0f / (K - 1);
+  const int64_t go = (int64_t)c0 * P + off;
+  stage_z<T, CT>(zs, zc0, zrow, K, 0, AP, true);      // zs[a][u_local][2*CT] for the first chunk of sources
   mbar_wait(bar, 0);
 
-  // ---- dh: R sources per pass, every destination's staged gradient vector read once per R sources
-  for (int u0 = grp * R; u0 < K; u0 += NGRP * R) {
-    if (!live) continue;
-    float acc[R][VEC];
+  for (int u_base = 0; u_base < K; u_base += AP) {
+    if (u_base > 0) { __syncthreads(); stage_z<T, CT>(zs, zc0, zrow, K, u_base, AP, true); }
+    __syncthreads();
+    const int u0 = u_base + grp * R;
+    if (u0 >= K) continue;                      // warp-uniform: the warps of a destination group leave together
+    // ---- dh for sources u0 .. u0+R-1: every destination's staged gradient vector is read once per R sources
+    {
+      float acc[R][VEC];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+      for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int q = 0; q < VEC; ++q) acc[r][q] = 0.f;
-    for (int a = 0; a < K; ++a) {
-      float dv[VEC];
-      Vec16<T>::load(ds + (size_t)a * slice + off, dv);
+        for (int q = 0; q < VEC; ++q) acc[r][q] = 0.f;
+      for (int a = 0; a < K; ++a) {
+        float dv[VEC];
+        Vec16<T>::load(ds + (size_t)a * slice + off, dv);
+        const T* za = zs + ((size_t)a * AP + grp * R) * 2 * CT + 2 * cl;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float gam = lds_pair<T>(za + r * 2 * CT).x;     // rows of non-edges (u == a, u >= K) were staged as zeros
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[r][q] = fmaf(gam, dv[q], acc[r][q]);
+        }
+      }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int u = u0 + r;
-        if (u >= K || u == a) continue;
-        const float gam = ldg_pair<T>(zc + (int64_t)edge_of(K, u, a) * zrow).x;
+        if (u >= K) continue;
+        if (addend) {
+          float av[VEC];
+          Vec16<T>::load(addend + (n0 + u) * ldadd + go, av);
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) acc[r][q] = fmaf(gam, dv[q], acc[r][q]);
+          for (int q = 0; q < VEC; ++q) acc[r][q] = fmaf(acc[r][q], w, av[q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[r][q] *= w;
+        }
+        Vec16<T>::store(dh + (n0 + u) * lddh + go, acc[r]);
       }
     }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int u = u0 + r;
-      if (u >= K) continue;
-      const int64_t go = (int64_t)c0 * P + off;
-      if (addend) {
-        float av[VEC];
-        Vec16<T>::load(addend + (n0 + u) * ldadd + go, av);
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) acc[r][q] = fmaf(acc[r][q], w, av[q]);
-      } else {
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) acc[r][q] *= w;
-      }
-      Vec16<T>::store(dh + (n0 + u) * lddh + go, acc[r]);
-    }
-  }
-
-  // ---- dz: R = LPC sources in registers; for every destination the R partial pixel-dots are reduce-scattered over the LPC
-  //      lanes of the channel, so lane l finishes (and stores) the edge of source u0 + l.  All 32 lanes of a warp stay in step.
-  for (int u0 = grp * R; u0 < K; u0 += NGRP * R) {
-    float hv[R][VEC];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (live && u0 + r < K) Vec16<T>::load(hs + (size_t)(u0 + r) * slice + off, hv[r]);
-      else {
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) hv[r][q] = 0.f;
-      }
-    }
-    const int my_u = u0 + l;
-    for (int a = 0; a < K; ++a) {
-      float dv[VEC];
-      if (live) Vec16<T>::load(ds + (size_t)a * slice + off, dv);
-      else {
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) dv[q] = 0.f;
-      }
-      float sd = 0.f;
-#pragma unroll
-      for (int q = 0; q < VEC; ++q) sd += dv[q];
-      float pg[R];
+    // ---- dz for the same sources: R = LPC source vectors in registers; per destination the R partial pixel-dots are
+    //      reduce-scattered over the LPC lanes of the channel, so lane l finishes (and stores) the edge of source u0 + l.
+    {
+      float hv[R][VEC];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        float s = 0.f;
+        if (u0 + r < K) Vec16<T>::load(hs + (size_t)(u0 + r) * slice + off, hv[r]);
+        else {
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) s = fmaf(hv[r][q], dv[q], s);
-        pg[r] = s;
+          for (int q = 0; q < VEC; ++q) hv[r][q] = 0.f;
+        }
       }
-      // all-reduce sd, reduce-scatter pg (lane l keeps source l: halves are exchanged high bit first, so the surviving
-      // index is exactly the lane's own number)
+      const int my_u = u0 + l;
+      for (int a = 0; a < K; ++a) {
+        float dv[VEC];
+        Vec16<T>::load(ds + (size_t)a * slice + off, dv);
+        float sd = 0.f;
 #pragma unroll
-      for (int o = LPC / 2; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
-      float mine;
-      {
+        for (int q = 0; q < VEC; ++q) sd += dv[q];
         float v[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = pg[r];
-        int n = R;
+        for (int r = 0; r < R; ++r) {
+          float s = 0.f;
 #pragma unroll
-        for (int o = LPC / 2; o > 0; o >>= 1) {
-          n >>= 1;
-          const bool up = (l & o) != 0;
+          for (int q = 0; q < VEC; ++q) s = fmaf(hv[r][q], dv[q], s);
+          v[r] = s;
+        }
 #pragma unroll
-          for (int i = 0; i < R / 2; ++i) {
-            if (i < n) {
-              const float send = up ? v[i] : v[i + n];
-              const float keep = up ? v[i + n] : v[i];
-              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        for (int o = LPC / 2; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+        // reduce-scatter: halves are exchanged high bit first, so the surviving index is exactly the lane's own number
+        {
+          int n = R;
+#pragma unroll
+          for (int o = LPC / 2; o > 0; o >>= 1) {
+            n >>= 1;
+            const bool up = (l & o) != 0;
+#pragma unroll
+            for (int i = 0; i < R / 2; ++i) {
+              if (i < n) {
+                const float send = up ? v[i] : v[i + n];
+                const float keep = up ? v[i + n] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+              }
             }
           }
         }
-        mine = v[0];
-      }
-      if (live && my_u < K && my_u != a) {
-        const int64_t zi = (int64_t)edge_of(K, my_u, a) * zrow;
-        float dg = mine * w, db = sd * w;
-        if (fuse_sig) {
-          const float2 gb = ldg_pair<T>(zc + zi);
-          dg *= gb.x * (1.f - gb.x); db *= gb.y * (1.f - gb.y);
+        if (my_u < K && my_u != a) {
+          float dg = v[0] * w, db = sd * w;
+          if (fuse_sig) {
+            const float2 gb = lds_pair<T>(zs + ((size_t)a * AP + grp * R + l) * 2 * CT + 2 * cl);
+            dg *= gb.x * (1.f - gb.x); db *= gb.y * (1.f - gb.y);
+          }
+          st_pair<T>(dzc + (int64_t)edge_of(K, my_u, a) * zrow, dg, db);
         }
-        st_pair<T>(dzc + zi, dg, db);
       }
     }
   }
@@ -286,9 +306,11 @@ static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 template <typename T, int LPC>
 static int fwd_dense_t(int K, const T* x, int64_t ldx, const T* z, T* out, int64_t ldout, T* copy_to, int64_t G, int F, int P, cudaStream_t st) {
   constexpr int CT = dense::NVEC / LPC;
-  const size_t smem = 128 + (size_t)K * CT * P * sizeof(T);
+  if (F % CT != 0) return RGNN_E_UNSUPPORTED;
+  const int Rf = K <= 16 ? 4 : 8;
+  const size_t smem = 128 + (size_t)K * CT * P * sizeof(T) + (z ? (size_t)K * dense::NGRP * Rf * 2 * CT * sizeof(T) : 0);
   if (smem > 200 * 1024) return RGNN_E_UNSUPPORTED;
-  const int64_t blocks = G * ((F + CT - 1) / CT);
+  const int64_t blocks = G * (F / CT);
   if (blocks >= (1ll << 31)) return RGNN_E_RANGE;
 #define RGNN_GO(RR, ZZ)                                                                                                    \
   do {                                                                                                                     \
@@ -311,9 +333,10 @@ template <typename T, int LPC>
 static int bwd_dense_t(int K, const T* h, int64_t ldh, const T* dagg, int64_t ldd, const T* z, const T* addend, int64_t ldadd, T* dh,
                        int64_t lddh, T* dz, int64_t G, int F, int P, int fuse_sig, cudaStream_t st) {
   constexpr int CT = dense::NVEC / LPC;
-  const size_t smem = 128 + 2 * (size_t)K * CT * P * sizeof(T);
+  if (F % CT != 0) return RGNN_E_UNSUPPORTED;
+  const size_t smem = 128 + 2 * (size_t)K * CT * P * sizeof(T) + (size_t)K * dense::NGRP * LPC * 2 * CT * sizeof(T);
   if (smem > 200 * 1024) return RGNN_E_UNSUPPORTED;
-  const int64_t blocks = G * ((F + CT - 1) / CT);
+  const int64_t blocks = G * (F / CT);
   if (blocks >= (1ll << 31)) return RGNN_E_RANGE;
   static bool done = false;
   if (!done) {
