@@ -72,7 +72,7 @@ def main():
             ms = e0.elapsed_time(e1) / a.steps
             flops = 2 * 3 * (4 * e * a.feat ** 2 + 4 * n * 64 * a.feat ** 2)
             rec.update(ms_per_step=round(ms, 3), graphs_per_s=round(g / ms * 1e3, 1), tflops=round(flops / ms / 1e9, 1),
-                       path="register kernels (K<=8)" if k <= 8 else "staged shared-memory kernels")
+                       path="register-tiled complete-graph kernels (K<=8)" if k <= 8 else "dense shared-memory complete-graph kernels (K>8)")
             print(json.dumps(rec), flush=True)
             del h, dy, pose, gr
             torch.cuda.empty_cache()
