@@ -129,9 +129,7 @@ def main():
         return
     import torch.distributed as dist
     import types
-    import robot_gnn_b200 as R
-    from multi_robot_check import make_block
-    from oracle import gnn_oracle as O   # parameter init + (rank 0) the cpu_baseline leg only
+    import robot_gnn_b200 as R           # the oracle is imported by the cpu_baseline leg only (cpu_reference_rate)
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
@@ -143,7 +141,8 @@ def main():
     dtype = torch.bfloat16 if a.dtype == "bf16" else torch.float32
     G, K, F = a.graphs, a.robots, a.feat
     N, E = G * K, G * K * (K - 1)
-    blk, _ = make_block(R, O, F, True, True, seed=1)
+    torch.manual_seed(1)                 # reference default seed (training.py:24); PyTorch-default init of Linear / Conv2d
+    blk = R.GNNBlock(types.SimpleNamespace(feature_dim=F, compress_gcn=True, multi_gcn=True))
     blk.to(dev)
     sync = R.parallel.GradSync(blk) if world > 1 else None
 

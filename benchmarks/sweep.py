@@ -33,12 +33,12 @@ def main():
     ap.add_argument("--mem-gb", type=float, default=120.0)
     ap.add_argument("--steps", type=int, default=5)
     a = ap.parse_args()
+    import types
     import robot_gnn_b200 as R
-    from multi_robot_check import make_block
-    from oracle import gnn_oracle as O      # parameter init only
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
-    blk, _ = make_block(R, O, a.feat, True, True, seed=1)
+    torch.manual_seed(1)
+    blk = R.GNNBlock(types.SimpleNamespace(feature_dim=a.feat, compress_gcn=True, multi_gcn=True))
     blk.to(dev)
     for k in a.robots:
         for g in a.graphs:
