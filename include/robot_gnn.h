@@ -185,9 +185,11 @@ int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const void* x1, i
                     void* out0, int64_t m0, void* out1, int64_t m1, const float* bias, int64_t nodes, void* stream);
 
 /* weight gradient of the above: dW[m,k] = sum_v sum_p dy[v,m,p] x[v,k,p], x = x0 | x1; dW fp32 (row stride ldw);
- * partial fp32 [splits, M, c0+c1] scratch; the robots are split across CTAs and summed in a fixed order. */
+ * dbias (nullable) fp32 [M] = sum_v sum_p dy[v,m,p], computed by the otherwise idle epilogue warps from the dy tiles the
+ * mainloop stages anyway (no second pass over dy); partial fp32 [splits, M, c0+c1 (+1 if dbias)] scratch; the robots are
+ * split across CTAs and summed in a fixed order (deterministic). */
 int rgnn_tc_conv1x1_wgrad(const void* dy, int64_t M, const void* x0, int64_t c0, const void* x1, int64_t c1,
-                          float* dW, int64_t ldw, float* partial, int64_t splits, int64_t nodes, void* stream);
+                          float* dW, int64_t ldw, float* dbias, float* partial, int64_t splits, int64_t nodes, void* stream);
 
 /* C[M,N] = epi(A[M,K] . B[N,K]^T), bf16 row-major operands; epi = bit-or of RGNN_EPI_BIAS_N | _SIGMOID | _RELU_MASK
  * (nn.Linear(F,2F)+Sigmoid, models.py:149-150, and dA1 of its autograd). */

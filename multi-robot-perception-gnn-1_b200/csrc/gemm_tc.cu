@@ -41,6 +41,7 @@ struct TcParams {
   void* out0; void* out1; int m_split;   // rows >= m_split go to out1 (row index - m_split)
   int64_t ld0, ld1;     // NCHW: elements per robot in out0/out1; ROW/PARTIAL: ld0 = row stride
   const float* bias; const void* aux;
+  float* rowsum;        // WGRAD: if non-null, fp32 [splits, M] partial row sums of A (the bias gradient of the 1x1 conv) are written here
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -193,7 +194,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, CL); }
+    // a stage is free once every CTA's MMAs retired (+ this CTA's 4 epilogue warps when they also read the A tile: rowsum mode)
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, CL + (p.rowsum ? 4 : 0)); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -306,10 +308,37 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int ew = warp - 4;                    // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
     const int row = ew * 32 + lane;             // row inside the 128-row tile
     int as = 0; uint32_t aphase = 0;
+    int rstage = 0; uint32_t rphase = 0;        // rowsum mode: this warp's own walk over the operand ring
     for (int w = w_first; w < work_total; w += w_step) {
       const int tm = (w % tiles_mc) * CL + crank, tn = (w / tiles_mc) % p.tiles_n, sp = w / (tiles_mc * p.tiles_n);
       const int kb0 = sp * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
       const bool empty = kb1 <= kb0;
+      if (p.rowsum) {
+        // The bias gradient db[o] = sum_{v,p} dY[v,o,p] rides on the WGRAD mainloop: the A tile of every k-block IS dY[v, o-tile, :]
+        // in shared memory, and these four warps are idle until the accumulator is complete.  Thread = one tile row (128 B);
+        // the 16-byte chunks are visited in a lane-rotated order (the 128B swizzle only permutes chunks inside a row, which a
+        // row sum does not care about) so the 8 lanes of a quarter-warp hit 8 different bank groups.
+        float rs = 0.f;
+        const bool mine = tn == 0;              // every N-tile of an M-tile loads the same A: only one of them sums it
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_full + 8 * rstage, rphase);
+          if (mine) {
+            const uint32_t rowaddr = tiles + rstage * STAGE_BYTES + row * 128;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint32_t a0, a1, a2, a3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(rowaddr + (((i + lane) & 7) << 4)));
+              rs += (__uint_as_float(a0 << 16) + __uint_as_float(a0 & 0xffff0000u)) + (__uint_as_float(a1 << 16) + __uint_as_float(a1 & 0xffff0000u)) +
+                    (__uint_as_float(a2 << 16) + __uint_as_float(a2 & 0xffff0000u)) + (__uint_as_float(a3 << 16) + __uint_as_float(a3 & 0xffff0000u));
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_empty + 8 * rstage);
+          if (++rstage == NSTAGE) { rstage = 0; rphase ^= 1; }
+        }
+        const int64_t mr = (int64_t)tm * BM + row;
+        if (mine && mr < p.M) p.rowsum[(int64_t)sp * p.M + mr] = rs;
+      }
       mbar_wait(bar_tfull + 8 * as, aphase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(ew * 32) << 16);
@@ -585,7 +614,7 @@ extern "C" int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const 
 
 // dW[m, k] = sum_v sum_p dy[v,m,p] * x[v,k,p], x = x0 (k < c0) | x1;  dW fp32 [M, c0+c1] (row stride ldw), partial fp32 [splits, M, c0+c1].
 extern "C" int rgnn_tc_conv1x1_wgrad(const void* dy, int64_t M, const void* x0, int64_t c0, const void* x1, int64_t c1,
-                                     float* dW, int64_t ldw, float* partial, int64_t splits, int64_t nodes, void* stream) {
+                                     float* dW, int64_t ldw, float* dbias, float* partial, int64_t splits, int64_t nodes, void* stream) {
   RGNN_REQUIRE(dy && x0 && dW && partial && M > 0 && c0 > 0 && c1 >= 0 && nodes >= 0 && splits >= 1, RGNN_E_ARG, "rgnn_tc_conv1x1_wgrad: bad arguments");
   RGNN_REQUIRE(c1 == 0 || x1, RGNN_E_ARG, "rgnn_tc_conv1x1_wgrad: missing x1");
   constexpr int BN = 256;
@@ -596,6 +625,7 @@ extern "C" int rgnn_tc_conv1x1_wgrad(const void* dy, int64_t M, const void* x0, 
   cudaStream_t st = as_stream(stream);
   if (nodes == 0) {
     cudaError_t e = cudaMemset2DAsync(dW, ldw * 4, 0, Nn * 4, M, st);
+    if (e == cudaSuccess && dbias) e = cudaMemsetAsync(dbias, 0, M * 4, st);
     return e == cudaSuccess ? 0 : cuda_fail(e, "memset dW");
   }
   CUtensorMap ta, tb0, tb1;
@@ -623,6 +653,7 @@ extern "C" int rgnn_tc_conv1x1_wgrad(const void* dy, int64_t M, const void* x0, 
   p.splits = (int)splits;
   p.n_b0 = (int)c0; p.rows_a = (int)M; p.rows_b0 = (int)c0; p.rows_b1 = (int)c1;
   p.M = M; p.N = Nn; p.out0 = partial; p.ld0 = Nn;
+  p.rowsum = dbias ? partial + splits * M * Nn : nullptr;     // [splits, M] behind the tile partials
   int rc = launch<BN>(ta, tb0, tb1, p, st);
   if (rc) return rc;
   const int64_t n = M * Nn;
@@ -630,6 +661,10 @@ extern "C" int rgnn_tc_conv1x1_wgrad(const void* dy, int64_t M, const void* x0, 
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
   k_sum_partials<<<(unsigned)blocks, 256, 0, st>>>(partial, (int)splits, n, dW, ldw, Nn, 1.0f);
   RGNN_LAUNCH_CHECK("k_sum_partials");
+  if (dbias) {
+    k_sum_partials<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(p.rowsum, (int)splits, M, dbias, M, M, 1.0f);
+    RGNN_LAUNCH_CHECK("k_sum_partials(bias)");
+  }
   return 0;
 }
 

@@ -303,10 +303,13 @@ def _compress_backward(dy, h, gh, wc2, tc, need_dh, need_dgh, need_dw, need_db):
         if tc_dw and need_dw:
             dwc = torch.empty((fo, 2 * f), **f32)
             split = _tc_splits((fo // 128) * (2 * f // 256), n)
-            partial = torch.empty((split, fo, 2 * f), **f32)
+            partial = torch.empty((split * fo * (2 * f + 1),), **f32)
+            if need_db:       # the bias gradient rides on the same pass over dy (idle epilogue warps row-sum the staged tiles)
+                dbc = torch.empty((fo,), **f32)
+                need_db = False
             with _lib.timed("compress_dw", 2.0 * fo * 2 * f * n * p):
-                check(lib().rgnn_tc_conv1x1_wgrad(ptr(dy), fo, ptr(h), f, ptr(gh), f, ptr(dwc), 2 * f, ptr(partial), split, n, stream()),
-                      "rgnn_tc_conv1x1_wgrad")
+                check(lib().rgnn_tc_conv1x1_wgrad(ptr(dy), fo, ptr(h), f, ptr(gh), f, ptr(dwc), 2 * f, ptr(dbc), ptr(partial), split, n,
+                                                  stream()), "rgnn_tc_conv1x1_wgrad")
         if p == 1:
             sb, sc, bt, nn = (0, 0, 1, fo), (0, 1, f), 1, n
         else:

@@ -74,12 +74,15 @@ def test_tc_conv1x1_wgrad(R, nodes, m, c0, c1, splits):
     dy = bf(nodes, m, 64, seed=9)
     x0, x1 = bf(nodes, c0, 64, seed=10), (bf(nodes, c1, 64, seed=11) if c1 else None)
     dw = torch.full((m, c0 + c1), 3.0, device="cuda")
-    part = torch.empty((splits, m, c0 + c1), device="cuda")
-    L.check(L.lib().rgnn_tc_conv1x1_wgrad(L.ptr(dy), m, L.ptr(x0), c0, L.ptr(x1), c1, L.ptr(dw), c0 + c1, L.ptr(part), splits, nodes,
-                                          L.stream()), "wgrad")
-    torch.cuda.synchronize()
-    x = torch.cat([x0, x1], 1) if c1 else x0
-    assert nerr(dw, torch.einsum("vmp,vkp->mk", dy.float(), x.float())) <= 1e-5
+    db = torch.full((m,), 5.0, device="cuda")
+    part = torch.empty((splits * m * (c0 + c1 + 1),), device="cuda")
+    for with_bias in (True, False):
+        L.check(L.lib().rgnn_tc_conv1x1_wgrad(L.ptr(dy), m, L.ptr(x0), c0, L.ptr(x1), c1, L.ptr(dw), c0 + c1,
+                                              L.ptr(db) if with_bias else None, L.ptr(part), splits, nodes, L.stream()), "wgrad")
+        torch.cuda.synchronize()
+        x = torch.cat([x0, x1], 1) if c1 else x0
+        assert nerr(dw, torch.einsum("vmp,vkp->mk", dy.float(), x.float())) <= 1e-5
+    assert nerr(db, dy.float().sum((0, 2))) <= 1e-5
 
 
 def test_cast_weights(R):
