@@ -8,11 +8,12 @@
 //   nn.Linear(F,2F)+Sigmoid      dgl/model/models.py:149-150      -> gemm_tn  : Z = sigmoid(A1 . W2^T + b2)
 //   its autograd                                                  -> gemm_tn  : dA1 = (dZ . W2) * [A1>0] ;  gemm_nn : dW2 = dZ^T . A1
 //
-// One persistent, warp-specialised kernel (1 CTA / SM, 256 threads):
-//   warp 0   TMA producer   (4-stage ring of {A 128x64, B BNx64} bf16 tiles, mbarrier full/empty)
+// One persistent, warp-specialised kernel (1 CTA / SM, 384 threads):
+//   warp 0   TMA producer   (3-stage ring of {A 128x64, B BNx64} bf16 tiles, mbarrier full/empty)
 //   warp 1   MMA issuer     (one elected lane; 4 x tcgen05.mma 128xBNx16 per stage; tcgen05.commit frees the stage)
 //   warp 2   TMEM allocator (2 x BN fp32 columns = double-buffered accumulator, epilogue overlaps the next tile)
-//   warps 4-7 epilogue      (tcgen05.ld 32x32b.x32 -> bias / sigmoid / relu-mask -> bf16 or fp32 partial stores)
+//   warps 4-11 epilogue     (two warpgroups, one per column half: tcgen05.ld 32x32b.x32 -> bias / sigmoid / relu-mask ->
+//                            bf16 slabs staged in swizzled shared memory and written by TMA stores, or fp32 split partials)
 // NCHW feature maps are consumed where they lie: a [64 ch x 64 px] slab of one robot is exactly one MN-major
 // SWIZZLE_128B operand block (row = channel, 128 B = the 64 contiguous pixels), so the concat of models.py:182 is
 // just "k-blocks 0..F/64 from h, the rest from g_h" (two tensor maps) and is never materialised.
@@ -23,7 +24,9 @@
 namespace rgnn {
 namespace tc {
 
-constexpr int BM = 128, BK = 64, NSTAGE = 4;
+constexpr int BM = 128, BK = 64, NSTAGE = 3;
+constexpr int NTHREADS = 384;       // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: two epilogue warpgroups (column halves)
+constexpr int NOUT_STAGE = 4;       // bf16 output slabs in flight (2 per epilogue warpgroup)
 constexpr int LOAD_TN = 0, LOAD_CONV = 1, LOAD_WGRAD = 2, LOAD_NN = 3;
 constexpr int EPI_NCHW = 0, EPI_ROW = 1, EPI_PARTIAL = 2;
 
@@ -153,7 +156,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -164,7 +167,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // k-block.  Every stage's empty barrier then collects the tcgen05.commit of BOTH CTAs (multicast commit) before either
 // producer may overwrite the stage.  The MMAs themselves stay cta_group::1 (each CTA owns its accumulator).
 template <int BN, int CL>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
           const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmO0,
           const __grid_constant__ CUtensorMap tmO1, const TcParams p) {
@@ -175,8 +178,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t tiles = smem_u32(smem);
   constexpr uint32_t OUT_STAGE_BYTES = 128 * 128;      // one robot's [128 ch x 64 px] bf16 output slab
-  const uint32_t out_stage = tiles + NSTAGE * STAGE_BYTES;   // 2 slabs, 1024-aligned (TMA-store staging, NCHW epilogue)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES + 2 * OUT_STAGE_BYTES);
+  const uint32_t out_stage = tiles + NSTAGE * STAGE_BYTES;   // NOUT_STAGE slabs, 1024-aligned (TMA-store staging)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES + NOUT_STAGE * OUT_STAGE_BYTES);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NSTAGE);
   const uint32_t bar_tfull = smem_u32(bars + 2 * NSTAGE), bar_tempty = smem_u32(bars + 2 * NSTAGE + 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
@@ -196,7 +199,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 1 && lane == 0) {
     // a stage is free once every CTA's MMAs retired (+ this CTA's 4 epilogue warps when they also read the A tile: rowsum mode)
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, CL + (p.rowsum ? 4 : 0)); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -305,15 +308,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
-    const int ew = warp - 4;                    // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+    const int ew = (warp - 4) & 3;              // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+    const int eh = (warp - 4) >> 2;             // epilogue warpgroup: 0 = left half of the tile's columns, 1 = right half
     const int row = ew * 32 + lane;             // row inside the 128-row tile
+    const int bar_id = 1 + eh;                  // named barrier of this warpgroup
+    int sbuf = 0;                               // which of the warpgroup's two staging slabs is next
     int as = 0; uint32_t aphase = 0;
     int rstage = 0; uint32_t rphase = 0;        // rowsum mode: this warp's own walk over the operand ring
     for (int w = w_first; w < work_total; w += w_step) {
       const int tm = (w % tiles_mc) * CL + crank, tn = (w / tiles_mc) % p.tiles_n, sp = w / (tiles_mc * p.tiles_n);
       const int kb0 = sp * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
       const bool empty = kb1 <= kb0;
-      if (p.rowsum) {
+      if (p.rowsum && eh == 0) {
         // The bias gradient db[o] = sum_{v,p} dY[v,o,p] rides on the WGRAD mainloop: the A tile of every k-block IS dY[v, o-tile, :]
         // in shared memory, and these four warps are idle until the accumulator is complete.  Thread = one tile row (128 B);
         // the 16-byte chunks are visited in a lane-rotated order (the 128B swizzle only permutes chunks inside a row, which a
@@ -354,11 +360,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int row0 = tm * BM - (second ? p.m_split : 0);            // first channel of this tile inside its output tensor
         const int rows_per_node = second ? (int)(p.ld1 / 64) : (int)(p.ld0 / 64);
 #pragma unroll 1
-        for (int j = 0; j < BN / 64; ++j) {
+        for (int j = eh * (BN / 128); j < (eh + 1) * (BN / 128); ++j) {
           const int node = tn * (BN / 64) + j;
-          const uint32_t stg = out_stage + (j & 1) * OUT_STAGE_BYTES;
-          if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // slab j-2 fully read
-          epi_bar_sync();
+          const uint32_t stg = out_stage + (eh * 2 + sbuf) * OUT_STAGE_BYTES;
+          sbuf ^= 1;
+          if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this slab's previous store has read it
+          epi_bar_sync(bar_id);
           uint32_t r0[32], r1[32];
           tmem_ld32_issue(tacc + (2 * j) * 32, r0);
           tmem_ld32_issue(tacc + (2 * j + 1) * 32, r1);
@@ -396,7 +403,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          epi_bar_sync();
+          epi_bar_sync(bar_id);
           if (ew == 0 && lane == 0) {
             if (nchw) { if (node < p.nodes && (int64_t)tm * BM < p.M) tma_store_2d(second ? &tmO1 : &tmO0, stg, 0, node * rows_per_node + row0); }
             else if (n0 < p.N) tma_store_2d(&tmO0, stg, (int)n0, tm * BM);
@@ -405,7 +412,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       } else {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = eh * (BN / 64); c < (eh + 1) * (BN / 64); ++c) {
         uint32_t r[32];
         tmem_ld32_issue(tacc + c * 32, r);
         tmem_ld_wait();
@@ -427,7 +434,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive its readers
+    if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive its readers (both warpgroups)
   }
   // ================================ teardown ================================
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -506,7 +513,7 @@ static int g_cluster = -1;    // RGNN_TC_CLUSTER=1 disables the 2-CTA multicast 
 template <int BN, int CL>
 static int launch_cl(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const TcParams& p, cudaStream_t st,
                      const CUtensorMap* o0, const CUtensorMap* o1) {
-  constexpr size_t smem = 1024 + (size_t)NSTAGE * (BM * BK * 2 + BN * BK * 2) + 2 * 128 * 128 + 256;
+  constexpr size_t smem = 1024 + (size_t)NSTAGE * (BM * BK * 2 + BN * BK * 2) + NOUT_STAGE * 128 * 128 + 256;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -518,7 +525,7 @@ static int launch_cl(const CUtensorMap& a, const CUtensorMap& b0, const CUtensor
   if (groups < 1) return 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(groups * CL));
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
