@@ -9,7 +9,7 @@
 //   its autograd                                                  -> gemm_tn  : dA1 = (dZ . W2) * [A1>0] ;  gemm_nn : dW2 = dZ^T . A1
 //
 // One persistent, warp-specialised kernel (1 CTA / SM, 384 threads):
-//   warp 0   TMA producer   (3-stage ring of {A 128x64, B BNx64} bf16 tiles, mbarrier full/empty)
+//   warp 0   TMA producer   (4-stage ring of {A 128x64, B BNx64} bf16 tiles, mbarrier full/empty)
 //   warp 1   MMA issuer     (one elected lane; 4 x tcgen05.mma 128xBNx16 per stage; tcgen05.commit frees the stage)
 //   warp 2   TMEM allocator (2 x BN fp32 columns = double-buffered accumulator, epilogue overlaps the next tile)
 //   warps 4-11 epilogue     (two warpgroups, one per column half: tcgen05.ld 32x32b.x32 -> bias / sigmoid / relu-mask ->
@@ -24,9 +24,12 @@
 namespace rgnn {
 namespace tc {
 
-constexpr int BM = 128, BK = 64, NSTAGE = 3;
+constexpr int BM = 128, BK = 64, NSTAGE = 4;
+constexpr bool PREFETCH_L2 = false; // measured on B200: prefetching next-tile operands into L2 SLOWS the step (1.19 -> 1.43 ms
+                                    // compress fwd): the extra L2 requests cost more than the HBM misses they hide
+constexpr int PF_AHEAD = 12;        // WGRAD: k-blocks (robots) of L2 lead
 constexpr int NTHREADS = 384;       // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: two epilogue warpgroups (column halves)
-constexpr int NOUT_STAGE = 4;       // bf16 output slabs in flight (2 per epilogue warpgroup)
+constexpr int NOUT_STAGE = 2;       // bf16 output slabs (one per epilogue warpgroup; 4 x 48 KB operand stages leave room for no more)
 constexpr int LOAD_TN = 0, LOAD_CONV = 1, LOAD_WGRAD = 2, LOAD_NN = 3;
 constexpr int EPI_NCHW = 0, EPI_ROW = 1, EPI_PARTIAL = 2;
 
@@ -106,6 +109,15 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
+// L2 prefetch of a tensor-map box (no shared memory, no barrier): pulls a future operand tile from HBM into L2 so that the
+// real TMA load later is an L2 hit.  The mainloop is latency-sensitive (4 x 48 KB in flight per SM is all shared memory
+// allows) and output stores inflate DRAM latency, so HBM misses are taken a tile ahead of use.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -153,8 +165,13 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Outputs are streamed once and not re-read before they fall out of L2: store them evict-first so they do not displace the
+// operand tiles the M-tile siblings are about to re-read (policy constant = cute::TMA::CacheHintSm90::EVICT_FIRST).
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+  const uint64_t evict_first = 0x12F0000000000000ull;
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1), "l"(evict_first)
+               : "memory");
 }
 __device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -244,6 +261,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             tma_2d(sa, &tmA, fb, kb * BK, tm * BM);
             const CUtensorMap* mb = kb < p.kb_b0 ? &tmB0 : &tmB1;
             const int kc = (kb < p.kb_b0 ? kb : kb - p.kb_b0) * BK;
+            if (PREFETCH_L2 && crank == 0 && (w % tiles_mc) == 0 && w + w_step < work_total) {
+              // the activation tile of this CTA's NEXT work item (one whole tile of lead time); the M-tile siblings reuse it from L2
+              const int tn2 = ((w + w_step) / tiles_mc) % p.tiles_n;
+              tma_prefetch_3d(mb, 0, kc, tn2 * (BN / 64));
+              tma_prefetch_3d(mb, 0, kc, tn2 * (BN / 64) + BN / 128);
+            }
             for (int hb = h0; hb < h1; ++hb) {
               if (CL > 1) tma_3d_mc(sb + hb * HALF_B, mb, fb, 0, kc, tn * (BN / 64) + hb * (BN / 128), MC_MASK);
               else tma_3d(sb + hb * HALF_B, mb, fb, 0, kc, tn * (BN / 64) + hb * (BN / 128));
@@ -253,6 +276,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int n0 = tn * BN;
             const CUtensorMap* mb = n0 < p.n_b0 ? &tmB0 : &tmB1;
             const int rowb = n0 < p.n_b0 ? kb * p.rows_b0 + n0 : kb * p.rows_b1 + (n0 - p.n_b0);
+            if (PREFETCH_L2 && kb + PF_AHEAD < kb1) {     // robots further down this split: dY rows by the tn == 0 CTAs, X rows by tm == 0
+              if (tn == 0) tma_prefetch_2d(&tmA, 0, (kb + PF_AHEAD) * p.rows_a + tm * BM);
+              if (tm == 0) {
+                const int rb2 = n0 < p.n_b0 ? (kb + PF_AHEAD) * p.rows_b0 + n0 : (kb + PF_AHEAD) * p.rows_b1 + (n0 - p.n_b0);
+                tma_prefetch_2d(mb, 0, rb2);
+                tma_prefetch_2d(mb, 0, rb2 + BN / 2);
+              }
+            }
             for (int hb = h0; hb < h1; ++hb) {
               if (CL > 1) tma_2d_mc(sb + hb * HALF_B, mb, fb, 0, rowb + hb * (BN / 2), MC_MASK);
               else tma_2d(sb + hb * HALF_B, mb, fb, 0, rowb + hb * (BN / 2));
@@ -312,7 +343,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int eh = (warp - 4) >> 2;             // epilogue warpgroup: 0 = left half of the tile's columns, 1 = right half
     const int row = ew * 32 + lane;             // row inside the 128-row tile
     const int bar_id = 1 + eh;                  // named barrier of this warpgroup
-    int sbuf = 0;                               // which of the warpgroup's two staging slabs is next
     int as = 0; uint32_t aphase = 0;
     int rstage = 0; uint32_t rphase = 0;        // rowsum mode: this warp's own walk over the operand ring
     for (int w = w_first; w < work_total; w += w_step) {
@@ -359,12 +389,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const bool second = nchw && m >= p.m_split;
         const int row0 = tm * BM - (second ? p.m_split : 0);            // first channel of this tile inside its output tensor
         const int rows_per_node = second ? (int)(p.ld1 / 64) : (int)(p.ld0 / 64);
+        // NCHW (conv) tiles are limited by the output write traffic, not by these warps: one warpgroup walks all slabs with both
+        // staging buffers (store of slab j overlaps the staging of slab j+1).  ROW tiles (edge-MLP, short K, sigmoid) are limited
+        // by epilogue issue: the two warpgroups take one column half each, one buffer per warpgroup.
+        const int j_lo = nchw ? 0 : eh * (BN / 128), j_hi = nchw ? (eh == 0 ? BN / 64 : 0) : (eh + 1) * (BN / 128);
 #pragma unroll 1
-        for (int j = eh * (BN / 128); j < (eh + 1) * (BN / 128); ++j) {
+        for (int j = j_lo; j < j_hi; ++j) {
           const int node = tn * (BN / 64) + j;
-          const uint32_t stg = out_stage + (eh * 2 + sbuf) * OUT_STAGE_BYTES;
-          sbuf ^= 1;
-          if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this slab's previous store has read it
+          const uint32_t stg = out_stage + (nchw ? (j & 1) : eh) * OUT_STAGE_BYTES;
+          if (ew == 0 && lane == 0) {             // the buffer's previous store has finished reading it
+            if (nchw) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
           epi_bar_sync(bar_id);
           uint32_t r0[32], r1[32];
           tmem_ld32_issue(tacc + (2 * j) * 32, r0);
