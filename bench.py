@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--cuda-graph", action="store_true", help="replay the step from a captured CUDA graph (small batches)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="graph chunks the host-buffer pipeline overlaps")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="graph chunks the host-buffer pipeline overlaps")
     ap.add_argument("--cpu-graphs", type=int, default=32, help="graphs in the bounded CPU-baseline sample")
     return ap.parse_args()
 
