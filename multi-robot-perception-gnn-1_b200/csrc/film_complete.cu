@@ -8,6 +8,7 @@
 // and the instruction count per output vector is ~8x lower than the CSR-driven staged kernel (which stays as the
 // general path for any other topology).
 // fp32 keeps the reference's arithmetic: gamma*x rounded, +beta rounded, ascending-eid sum, true division by the degree.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace rgnn {
@@ -284,6 +285,205 @@ __global__ void __launch_bounds__(256, 1) k_film_bwd_complete(const T* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Same backward, operands staged by the bulk-copy engine (TMA without a tensor map) instead of by register prefetch:
+// per iteration the CTA's TPB consecutive vectors of h, dAgg and the addend for all K robots (3K contiguous runs, at most two
+// segments each where the chunk crosses a graph boundary) are fetched with cp.async.bulk into ONE shared-memory stage and
+// completed on an mbarrier.  A thread copies its 3K vectors to registers, the CTA syncs, and the copy engine refills the stage
+// for the next iteration while this one computes - the prefetch costs no registers and no LSU instructions, so the kernel
+// runs 12 warps per SM instead of 8.
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+}  // namespace tma
+
+constexpr int TMA_TPB = 384;
+
+template <typename T, int K, int LPC>
+__global__ void __launch_bounds__(TMA_TPB, 1) k_film_bwd_complete_tma(const T* __restrict__ h, int64_t ldh, const T* __restrict__ dagg, int64_t ldd,
+                                                                      const T* __restrict__ z, const T* addend, int64_t ldadd,
+                                                                      T* dh, int64_t lddh, T* __restrict__ dz,
+                                                                      int64_t G, int F, int P, int fuse_sig) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int NE = K * (K - 1);
+  constexpr int NVP = (NE + LPC - 1) / LPC * LPC;
+  constexpr int TPB = TMA_TPB;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  uint4* stage = reinterpret_cast<uint4*>(smem + 128);          // [3][K][TPB]
+  const int row_vecs = F * LPC;                                   // host guarantees row_vecs >= TPB
+  const int64_t total = G * (int64_t)row_vecs;
+  const float w = 1.0f / (K - 1);
+  const int64_t stride = (int64_t)gridDim.x * TPB;
+  const int64_t rounds = (total + stride - 1) / stride;
+  const int tid = threadIdx.x, l = tid % LPC;
+  const bool has_add = addend != nullptr;
+  const int nkind = has_add ? 3 : 2;
+  const int64_t zrow = 2 * (int64_t)F;
+  int my_e[NVP / LPC], my_a[NVP / LPC];
+#pragma unroll
+  for (int i = 0; i < NVP / LPC; ++i) {
+    const int e = scattered_id<NVP, LPC>(i, l);
+    const int u = e / (K - 1), jj = e % (K - 1);
+    my_e[i] = e < NE ? e : -1;
+    my_a[i] = jj < u ? jj : jj + 1;
+  }
+  // producer: warp 0 issues the (at most 2 * 3K) bulk copies of the chunk starting at vector t0
+  auto issue = [&](int64_t t0) {
+    if (t0 >= total) return;
+    const int n = (int)min((int64_t)TPB, total - t0);
+    const int64_t g0 = t0 / row_vecs;
+    const int j0 = (int)(t0 - g0 * row_vecs);
+    const int len0 = min(n, row_vecs - j0), len1 = n - len0;
+    if (tid == 0) tma::mbar_expect_tx(bar, (uint32_t)n * 16u * (uint32_t)(nkind * K));
+    __syncwarp();
+    for (int i = tid; i < nkind * K * 2; i += 32) {
+      const int seg = i & 1, u = (i >> 1) % K, kind = (i >> 1) / K;
+      const int len = seg ? len1 : len0;
+      if (len == 0) continue;
+      const T* base = kind == 0 ? h : (kind == 1 ? dagg : addend);
+      const int64_t ld = kind == 0 ? ldh : (kind == 1 ? ldd : ldadd);
+      const T* src = base + ((g0 + seg) * K + u) * ld + (seg ? 0 : (int64_t)j0 * VEC);
+      tma::bulk_g2s(stage + ((size_t)kind * K + u) * TPB + (seg ? len0 : 0), src, (uint32_t)len * 16u, bar);
+    }
+  };
+  if (tid == 0) { tma::mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  int64_t t0 = (int64_t)blockIdx.x * TPB;
+  if (tid < 32) issue(t0);
+  uint32_t phase = 0;
+
+  for (int64_t r = 0; r < rounds; ++r, t0 += stride) {
+    const int64_t t = t0 + tid;
+    const bool live = t < total;
+    const int64_t g = live ? t / row_vecs : 0;
+    const int off = live ? (int)(t - g * row_vecs) * VEC : 0;
+    const int c = off / P;
+    const int64_t n0 = g * K;
+    const T* zc = z + g * NE * zrow + 2 * c;
+    float hv[K][VEC], dv[K][VEC];
+    uint4 ca[K];
+    if (t0 < total) {                       // CTA-uniform: a chunk was issued for this round
+      tma::mbar_wait(bar, phase);
+      phase ^= 1;
+    }
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      uint4 ph = make_uint4(0, 0, 0, 0), pd = ph;
+      ca[u] = ph;
+      if (live) {
+        ph = stage[(size_t)u * TPB + tid];
+        pd = stage[((size_t)K + u) * TPB + tid];
+        if (has_add) ca[u] = stage[((size_t)2 * K + u) * TPB + tid];
+      }
+      Vec16<T>::unpack(ph, hv[u]);
+      Vec16<T>::unpack(pd, dv[u]);
+    }
+    __syncthreads();                        // everyone holds its vectors in registers: the stage may be refilled
+    if (tid < 32) issue(t0 + stride);
+    float gam[NE];
+    {
+      const T* zp = zc;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) { gam[e] = live ? ldg_pair<T>(zp).x : 0.f; zp += zrow; }
+    }
+    // ---- dh
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      float acc[VEC];
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+        if (a == u) continue;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) acc[q] = fmaf(gam[edge_id(K, u, a)], dv[a][q], acc[q]);
+      }
+      if (live) {
+        if (has_add) {
+          float av[VEC];
+          Vec16<T>::unpack(ca[u], av);
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[q] = fmaf(acc[q], w, av[q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[q] *= w;
+        }
+        Vec16<T>::store(dh + (n0 + u) * lddh + off, acc);
+      }
+    }
+    // ---- dz
+    float sd[K];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) s += dv[a][q];
+      sd[a] = s;
+    }
+#pragma unroll
+    for (int o = LPC / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (int a = 0; a < K; ++a) sd[a] += __shfl_xor_sync(0xffffffffu, sd[a], o);
+    }
+    float pg[NVP];
+#pragma unroll
+    for (int e = 0; e < NVP; ++e) pg[e] = 0.f;
+#pragma unroll
+    for (int u = 0; u < K; ++u)
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+        if (a == u) continue;
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) s = fmaf(hv[u][q], dv[a][q], s);
+        pg[edge_id(K, u, a)] = s;
+      }
+    reduce_scatter<NVP, LPC>(pg, l);
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < NVP / LPC; ++i) {
+        if (my_e[i] >= 0) {
+          float sda = sd[0];
+#pragma unroll
+          for (int q = 1; q < K; ++q) sda = (my_a[i] == q) ? sd[q] : sda;
+          const int64_t zi = my_e[i] * zrow;
+          float dg = pg[i] * w, db = sda * w;
+          if (fuse_sig) {
+            const float2 gb = ldg_pair<T>(zc + zi);
+            dg *= gb.x * (1.f - gb.x); db *= gb.y * (1.f - gb.y);
+          }
+          st_pair<T>(dz + (zc - z) + zi, dg, db);
+        }
+      }
+    }
+  }
+}
+
 template <typename T, bool HAS_Z>
 static int launch_fwd(int K, const T* x, int64_t ldx, const T* z, T* out, int64_t ldout, T* copy_to, int64_t G, int F, int P,
                       cudaStream_t st) {
@@ -299,10 +499,32 @@ static int launch_fwd(int K, const T* x, int64_t ldx, const T* z, T* out, int64_
   return 0;
 }
 
+static int g_bwd_tma = -1;
+
 template <typename T, int LPC>
 static int launch_bwd_lpc(int K, const T* h, int64_t ldh, const T* dagg, int64_t ldd, const T* z, const T* addend, int64_t ldadd, T* dh,
                           int64_t lddh, T* dz, int64_t G, int F, int P, int fuse_sig, cudaStream_t st) {
   const int64_t total = G * ((int64_t)F * P / Vec16<T>::N);
+  if (g_bwd_tma < 0) { const char* e = getenv("RGNN_BWD_TMA"); g_bwd_tma = (e && e[0] == '0') ? 0 : 1; }   // RGNN_BWD_TMA=0: register-prefetch variant
+  if (g_bwd_tma == 1 && F * LPC >= TMA_TPB && total > 0) {
+    const size_t smem = 128 + (size_t)3 * K * TMA_TPB * 16;
+    int64_t tblocks = (total + TMA_TPB - 1) / TMA_TPB;
+    if (tblocks > kNumSMs) tblocks = kNumSMs;
+#define RGNN_CASE(KK)                                                                                                                   \
+  case KK: {                                                                                                                           \
+    static bool done = false;                                                                                                          \
+    if (!done) {                                                                                                                       \
+      cudaError_t e = cudaFuncSetAttribute(k_film_bwd_complete_tma<T, KK, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_film_bwd_complete_tma)");                                      \
+      done = true;                                                                                                                     \
+    }                                                                                                                                  \
+    k_film_bwd_complete_tma<T, KK, LPC><<<(unsigned)tblocks, TMA_TPB, smem, st>>>(h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sig); \
+  } break;
+    switch (K) { RGNN_CASE(2) RGNN_CASE(3) RGNN_CASE(4) RGNN_CASE(5) RGNN_CASE(6) RGNN_CASE(7) RGNN_CASE(8) default: return RGNN_E_UNSUPPORTED; }
+#undef RGNN_CASE
+    RGNN_LAUNCH_CHECK("k_film_bwd_complete_tma");
+    return 0;
+  }
   int64_t blocks = (total + 255) / 256;
   if (blocks > kNumSMs) blocks = kNumSMs;        // persistent: one pipelined CTA per SM
   if (blocks < 1) return 0;
