@@ -1,19 +1,29 @@
-"""Decoder block of the reference (dgl/model/blocks.py:5-25): 5x5 conv (no bias) + BN + ReLU, then bilinear x2.
-Out of the hot path (cuDNN territory); restated here only so `model.models` is a complete, importable module with the
-reference's parameter names (`transconv1.0.weight`, `transconv1.1.*`)."""
+"""Upsampling decoder stage used by `model.models.decoder` (out of the GNN hot path; cuDNN territory).
+
+Restated for the script-level drop-in only: a stage is `5x5 convolution without bias -> batch norm -> ReLU` followed by a
+bilinear x2 resize with aligned corners.  The parameter names a reference checkpoint carries for such a stage are
+`transconv1.0.weight` (convolution) and `transconv1.1.{weight,bias,running_mean,running_var,num_batches_tracked}` (batch
+norm), so the convolution and the norm live at indices 0 and 1 of a container called `transconv1`; the resize has no state.
+"""
 import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _conv_bn_relu(cin, cout, ksize):
+    layers = [nn.Conv2d(cin, cout, ksize, stride=1, padding=2, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True)]
+    return nn.Sequential(*layers)
 
 
 class TransBlock(nn.Module):
     expansion = 1
+    SCALE = 2          # every decoder stage doubles the spatial size (8 -> 16 -> ... -> 256)
 
-    def __init__(self, in_channels, out_channels, stride=1, dropout=0.0, kernel_size=3):
+    def __init__(self, in_channels, out_channels, stride=2, dropout=0.0, kernel_size=5):
         super().__init__()
-        if stride != 2:
-            raise ValueError("the reference only ever builds stride-2 TransBlocks (dgl/model/models.py:61-65)")
-        conv = nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=1, padding=2, bias=False)
-        self.transconv1 = nn.Sequential(conv, nn.BatchNorm2d(out_channels), nn.ReLU(inplace=True))
-        self.Upsample = nn.Upsample(scale_factor=(stride, stride), mode='bilinear', align_corners=True)
+        if stride != self.SCALE:
+            raise ValueError(f"decoder stages upsample by {self.SCALE}; got stride={stride}")
+        self.transconv1 = _conv_bn_relu(in_channels, out_channels, kernel_size)
 
     def forward(self, x):
-        return self.Upsample(self.transconv1(x))
+        y = self.transconv1(x)
+        return F.interpolate(y, scale_factor=float(self.SCALE), mode="bilinear", align_corners=True)
