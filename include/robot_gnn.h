@@ -191,14 +191,17 @@ int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const void* x1, i
 int rgnn_tc_conv1x1_wgrad(const void* dy, int64_t M, const void* x0, int64_t c0, const void* x1, int64_t c1,
                           float* dW, int64_t ldw, float* dbias, float* partial, int64_t splits, int64_t nodes, void* stream);
 
-/* C[M,N] = epi(A[M,K] . B[N,K]^T), bf16 row-major operands; epi = bit-or of RGNN_EPI_BIAS_N | _SIGMOID | _RELU_MASK
- * (nn.Linear(F,2F)+Sigmoid, models.py:149-150, and dA1 of its autograd). */
+/* C[M,N] = epi(alpha * A[M,K] . B[N,K]^T), bf16 row-major operands; epi = bit-or of RGNN_EPI_BIAS_N | _SIGMOID | _RELU_MASK |
+ * _ADD_AUX (+ beta * aux[m,n], aux bf16 with C's row stride).  nn.Linear(F,2F)+Sigmoid (models.py:149-150) and dA1 of its
+ * autograd; the GraphConv weight transform; GCN2Conv's identity mapping (1-b) X + b X W fused in the epilogue. */
 int rgnn_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
-                    int64_t M, int64_t N, int64_t K, int epi, const float* bias, const void* aux, void* stream);
+                    int64_t M, int64_t N, int64_t K, int epi, const float* bias, const void* aux, float alpha, float beta,
+                    void* stream);
 
-/* C[M,N] fp32 = A^T . B with A bf16 [K,M], B bf16 [K,N] (dW2 = dZ^T . A1); split over K, partial fp32 [splits,M,N]. */
+/* C[M,N] fp32 = alpha * A^T . B with A bf16 [K,M], B bf16 [K,N] (dW2 = dZ^T . A1; dW of GraphConv/GCN2Conv); split over K,
+ * partial fp32 [splits,M,N]. */
 int rgnn_tc_gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
-                    int64_t M, int64_t N, int64_t K, float* partial, int64_t splits, void* stream);
+                    int64_t M, int64_t N, int64_t K, float alpha, float* partial, int64_t splits, void* stream);
 
 /* dzpre = dz * z * (1 - z)  elementwise over n values (sigmoid backward, models.py:150) */
 int rgnn_sigmoid_grad(int dtype, const void* z, const void* dz, void* dzpre, int64_t n, void* stream);

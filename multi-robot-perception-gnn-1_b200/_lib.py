@@ -34,8 +34,8 @@ SIGNATURES = {
     "rgnn_tc_cast_weights": [_vp, _i64, _i64, _vp, _vp, _vp],
     "rgnn_tc_conv1x1": [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp],
     "rgnn_tc_conv1x1_wgrad": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _vp],
-    "rgnn_tc_gemm_tn": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp],
-    "rgnn_tc_gemm_nn": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp],
+    "rgnn_tc_gemm_tn": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _f32, _f32, _vp],
+    "rgnn_tc_gemm_nn": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _i64, _vp],
     "rgnn_sigmoid_grad": [_i32, _vp, _vp, _vp, _i64, _vp],
     "rgnn_axpby": [_i32, _f32, _vp, _f32, _vp, _vp, _i64, _vp],
     "rgnn_bias_add": [_i32, _vp, _vp, _vp, _i64, _i64, _vp],

@@ -47,6 +47,7 @@ struct TcParams {
   void* out0; void* out1; int m_split;   // rows >= m_split go to out1 (row index - m_split)
   int64_t ld0, ld1;     // NCHW: elements per robot in out0/out1; ROW/PARTIAL: ld0 = row stride
   const float* bias; const void* aux;
+  float alpha, beta;    // ROW epilogue: v = alpha * acc [+ beta * aux[m,n] with RGNN_EPI_ADD_AUX] (GCN2Conv identity mapping)
   float* rowsum;        // WGRAD: if non-null, fp32 [splits, M] partial row sums of A (the bias gradient of the 1x1 conv) are written here
 };
 
@@ -415,6 +416,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[b + i]) + bias_m;
             if (!nchw) {
+              if (p.alpha != 1.0f) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] *= p.alpha;
+              }
+              if ((p.epi_flags & RGNN_EPI_ADD_AUX) && m < p.M) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.aux) + m * p.ld0 + n0 + q * 8));
+                const uint32_t ws[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  v[2 * i] = fmaf(p.beta, __uint_as_float(ws[i] << 16), v[2 * i]);
+                  v[2 * i + 1] = fmaf(p.beta, __uint_as_float(ws[i] & 0xffff0000u), v[2 * i + 1]);
+                }
+              }
               if (p.epi_flags & RGNN_EPI_BIAS_N) {
                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + q * 8));
                 const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + q * 8 + 4));
@@ -634,7 +648,7 @@ extern "C" int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const 
     int rc = make_map(&tb1, x1, 3, d, s, b); if (rc) return rc;
   } else tb1 = tb0;
   TcParams p = {};
-  p.load_mode = LOAD_CONV; p.epi_mode = EPI_NCHW; p.epi_flags = bias ? RGNN_EPI_BIAS_M : 0;
+  p.load_mode = LOAD_CONV; p.epi_mode = EPI_NCHW; p.epi_flags = bias ? RGNN_EPI_BIAS_M : 0; p.alpha = 1.0f;
   p.tiles_m = (int)(M / 128); p.tiles_n = (int)((nodes + BN / 64 - 1) / (BN / 64)); p.splits = 1;
   p.kblocks = (int)(K / 64); p.kb_per_split = p.kblocks; p.kb_b0 = (int)(c0 / 64);
   p.nodes = (int)nodes; p.M = M; p.N = nodes * 64;
@@ -714,11 +728,13 @@ extern "C" int rgnn_tc_conv1x1_wgrad(const void* dy, int64_t M, const void* x0, 
 // C[M,N] = epi(A[M,K] . B[N,K]^T): A, B bf16 K-major (row strides lda, ldb elements); C bf16 row-major (ldc); bias fp32 [N];
 // aux bf16 [M, ldc] for RGNN_EPI_RELU_MASK.  epi: bit-or of RGNN_EPI_BIAS_N | RGNN_EPI_SIGMOID | RGNN_EPI_RELU_MASK.
 extern "C" int rgnn_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
-                               int64_t M, int64_t N, int64_t K, int epi, const float* bias, const void* aux, void* stream) {
+                               int64_t M, int64_t N, int64_t K, int epi, const float* bias, const void* aux, float alpha, float beta,
+                               void* stream) {
   RGNN_REQUIRE(A && B && C && M >= 0 && N > 0 && K > 0, RGNN_E_ARG, "rgnn_tc_gemm_tn: bad arguments");
-  RGNN_REQUIRE((epi & ~(RGNN_EPI_BIAS_N | RGNN_EPI_SIGMOID | RGNN_EPI_RELU_MASK)) == 0, RGNN_E_UNSUPPORTED, "rgnn_tc_gemm_tn: unsupported epilogue");
+  RGNN_REQUIRE((epi & ~(RGNN_EPI_BIAS_N | RGNN_EPI_SIGMOID | RGNN_EPI_RELU_MASK | RGNN_EPI_ADD_AUX)) == 0, RGNN_E_UNSUPPORTED, "rgnn_tc_gemm_tn: unsupported epilogue");
+  RGNN_REQUIRE(!((epi & RGNN_EPI_RELU_MASK) && (epi & RGNN_EPI_ADD_AUX)), RGNN_E_ARG, "rgnn_tc_gemm_tn: aux is either the ReLU mask or the addend");
   RGNN_REQUIRE(!(epi & RGNN_EPI_BIAS_N) || bias, RGNN_E_ARG, "rgnn_tc_gemm_tn: bias missing");
-  RGNN_REQUIRE(!(epi & RGNN_EPI_RELU_MASK) || aux, RGNN_E_ARG, "rgnn_tc_gemm_tn: aux missing");
+  RGNN_REQUIRE(!(epi & (RGNN_EPI_RELU_MASK | RGNN_EPI_ADD_AUX)) || aux, RGNN_E_ARG, "rgnn_tc_gemm_tn: aux missing");
   RGNN_REQUIRE(K % 64 == 0 && N % 128 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0, RGNN_E_UNSUPPORTED,
                "rgnn_tc_gemm_tn: K %% 64, N %% 128 and 16-byte row strides required");
   RGNN_REQUIRE(al16(A) && al16(B) && al16(C) && (!aux || al16(aux)), RGNN_E_ALIGN, "rgnn_tc_gemm_tn: 16-byte alignment");
@@ -741,7 +757,7 @@ extern "C" int rgnn_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_
   p.load_mode = LOAD_TN; p.epi_mode = EPI_ROW; p.epi_flags = epi;
   p.tiles_m = (int)((M + 127) / 128); p.tiles_n = (int)(N / BN); p.splits = 1;
   p.kblocks = (int)(K / 64); p.kb_per_split = p.kblocks;
-  p.M = M; p.N = N; p.out0 = C; p.ld0 = ldc; p.bias = bias; p.aux = aux;
+  p.M = M; p.N = N; p.out0 = C; p.ld0 = ldc; p.bias = bias; p.aux = aux; p.alpha = alpha; p.beta = beta;
   RGNN_REQUIRE(!bias || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0, RGNN_E_ALIGN, "rgnn_tc_gemm_tn: bias must be 16-byte aligned");
   CUtensorMap to;
   {
@@ -755,7 +771,7 @@ extern "C" int rgnn_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_
 // C[M,N] fp32 = A^T . B with A bf16 [K, M] (row stride lda), B bf16 [K, N] (row stride ldb): both operands MN-major.
 // Split over K; partial fp32 [splits, M, N].  (dW2 = dZ^T . A1 of the edge encoder.)
 extern "C" int rgnn_tc_gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
-                               int64_t M, int64_t N, int64_t K, float* partial, int64_t splits, void* stream) {
+                               int64_t M, int64_t N, int64_t K, float alpha, float* partial, int64_t splits, void* stream) {
   RGNN_REQUIRE(A && B && C && partial && M > 0 && N > 0 && K >= 0 && splits >= 1, RGNN_E_ARG, "rgnn_tc_gemm_nn: bad arguments");
   RGNN_REQUIRE(M % 128 == 0 && N % 128 == 0 && lda % 8 == 0 && ldb % 8 == 0, RGNN_E_UNSUPPORTED, "rgnn_tc_gemm_nn: M, N %% 128 and 16-byte row strides required");
   RGNN_REQUIRE(al16(A) && al16(B) && al16(partial), RGNN_E_ALIGN, "rgnn_tc_gemm_nn: 16-byte alignment");
@@ -792,7 +808,7 @@ extern "C" int rgnn_tc_gemm_nn(const void* A, int64_t lda, const void* B, int64_
   const int64_t n = M * N;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-  k_sum_partials<<<(unsigned)blocks, 256, 0, st>>>(partial, (int)splits, n, C, ldc, N, 1.0f);
+  k_sum_partials<<<(unsigned)blocks, 256, 0, st>>>(partial, (int)splits, n, C, ldc, N, alpha);
   RGNN_LAUNCH_CHECK("k_sum_partials");
   return 0;
 }

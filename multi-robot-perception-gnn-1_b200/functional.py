@@ -195,7 +195,7 @@ def _edge_mlp_forward(pose, w1, b1, w2, b2, out_dtype):
             w2b = _cast_w(w2)
             with _lib.timed("mlp2_fwd", 2.0 * e * f2 * hid):
                 check(lib().rgnn_tc_gemm_tn(ptr(a1), hid, ptr(w2b), hid, ptr(z), f2, e, f2, hid,
-                                            _lib.EPI_BIAS_N | _lib.EPI_SIGMOID, ptr(b2), None, stream()), "rgnn_tc_gemm_tn")
+                                            _lib.EPI_BIAS_N | _lib.EPI_SIGMOID, ptr(b2), None, 1.0, 0.0, stream()), "rgnn_tc_gemm_tn")
         else:
             _gemm(a1, (0, 0, hid, 1), w2, (0, 0, 1, hid), z, (0, f2, 1), e, f2, hid,
                   epi=_lib.EPI_BIAS_N | _lib.EPI_SIGMOID, bias=b2, tag="mlp2_fwd")
@@ -235,11 +235,11 @@ def edge_mlp_param_grads(pose, w2, a1, dzp):
         w2t = _cast_w(w2, transpose=True)                       # [hid, f2], K-major for dA1 = dZ . W2
         with _lib.timed("mlp2_dx", 2.0 * e * f2 * hid):
             check(lib().rgnn_tc_gemm_tn(ptr(dzp), f2, ptr(w2t), f2, ptr(da1), hid, e, hid, f2, _lib.EPI_RELU_MASK, None, ptr(a1),
-                                        stream()), "rgnn_tc_gemm_tn")
+                                        1.0, 0.0, stream()), "rgnn_tc_gemm_tn")
         split = _tc_splits((f2 // 128) * (hid // (256 if hid % 256 == 0 else 128)), (e + 63) // 64)
         partial = torch.empty((split, f2, hid), **f32)
         with _lib.timed("mlp2_dw", 2.0 * e * f2 * hid):
-            check(lib().rgnn_tc_gemm_nn(ptr(dzp), f2, ptr(a1), hid, ptr(dw2), hid, f2, hid, e, ptr(partial), split, stream()),
+            check(lib().rgnn_tc_gemm_nn(ptr(dzp), f2, ptr(a1), hid, ptr(dw2), hid, f2, hid, e, 1.0, ptr(partial), split, stream()),
                   "rgnn_tc_gemm_nn")
     else:
         _gemm(dzp, (0, 0, f2, 1), w2, (0, 0, hid, 1), da1, (0, hid, 1), e, hid, f2, epi=_lib.EPI_RELU_MASK, aux=a1, tag="mlp2_dx")
@@ -449,9 +449,16 @@ class LinearFn(torch.autograd.Function):
             bf = bias.detach().float().contiguous()
         if ident != 0.0:
             epi |= _lib.EPI_ADD_AUX
+        ctx.tc = bool(_lib.USE_TC and x.dtype == torch.bfloat16 and din % 128 == 0 and dout % 128 == 0 and rows > 0)
         with torch.cuda.device(x.device):
-            _gemm(x, (0, 0, din, 1), wf, (0, 0, dout, 1), y, (0, dout, 1), rows, dout, din, epi=epi, bias=bf,
-                  aux=x if ident != 0.0 else None, alpha=float(alpha), beta=float(ident))
+            if ctx.tc:     # tcgen05 path: W^T in bf16 is the K-major B operand; alpha, identity mapping and bias fused in the epilogue
+                wt = _cast_w(wf, transpose=True)
+                with _lib.timed("linear_fwd", 2.0 * rows * din * dout):
+                    check(lib().rgnn_tc_gemm_tn(ptr(x), din, ptr(wt), din, ptr(y), dout, rows, dout, din, epi, ptr(bf),
+                                                ptr(x) if ident != 0.0 else None, float(alpha), float(ident), stream()), "rgnn_tc_gemm_tn")
+            else:
+                _gemm(x, (0, 0, din, 1), wf, (0, 0, dout, 1), y, (0, dout, 1), rows, dout, din, epi=epi, bias=bf,
+                      aux=x if ident != 0.0 else None, alpha=float(alpha), beta=float(ident))
         ctx.save_for_backward(x, wf)
         ctx.alpha, ctx.ident, ctx.has_bias = float(alpha), float(ident), bias is not None
         return y
@@ -467,10 +474,23 @@ class LinearFn(torch.autograd.Function):
         with torch.cuda.device(dy.device):
             if ctx.needs_input_grad[0]:
                 dx = torch.empty_like(x)
-                _gemm(dy, (0, 0, dout, 1), wf, (0, 0, 1, dout), dx, (0, din, 1), rows, din, dout,
-                      epi=_lib.EPI_ADD_AUX if ctx.ident != 0.0 else 0, aux=dy if ctx.ident != 0.0 else None,
-                      alpha=ctx.alpha, beta=ctx.ident)
-            if ctx.needs_input_grad[1]:
+                epi = _lib.EPI_ADD_AUX if ctx.ident != 0.0 else 0
+                if ctx.tc:     # dX = alpha * dY . W^T (+ ident * dY): W [in, out] in bf16 is already the K-major B operand
+                    wb = _cast_w(wf)
+                    with _lib.timed("linear_dx", 2.0 * rows * din * dout):
+                        check(lib().rgnn_tc_gemm_tn(ptr(dy), dout, ptr(wb), dout, ptr(dx), din, rows, din, dout, epi, None,
+                                                    ptr(dy) if ctx.ident != 0.0 else None, ctx.alpha, ctx.ident, stream()), "rgnn_tc_gemm_tn")
+                else:
+                    _gemm(dy, (0, 0, dout, 1), wf, (0, 0, 1, dout), dx, (0, din, 1), rows, din, dout,
+                          epi=epi, aux=dy if ctx.ident != 0.0 else None, alpha=ctx.alpha, beta=ctx.ident)
+            if ctx.needs_input_grad[1] and ctx.tc:
+                dw = torch.empty((din, dout), **f32)
+                split = _tc_splits((din // 128) * (dout // (256 if dout % 256 == 0 else 128)), (rows + 63) // 64)
+                partial = torch.empty((split, din, dout), **f32)
+                with _lib.timed("linear_dw", 2.0 * rows * din * dout):
+                    check(lib().rgnn_tc_gemm_nn(ptr(x), din, ptr(dy), dout, ptr(dw), dout, din, dout, rows, ctx.alpha, ptr(partial), split,
+                                                stream()), "rgnn_tc_gemm_nn")
+            elif ctx.needs_input_grad[1]:
                 dw = torch.empty((din, dout), **f32)
                 split = _splits(((din + 63) // 64) * ((dout + 63) // 64), max(1, (rows + 63) // 64))
                 partial = torch.empty((split, din, dout), **f32) if split > 1 else None

@@ -52,13 +52,13 @@ def test_gemm_tn_and_nn_guards(R, m, n, k):
     L = R._lib
     a, b = bf(m, k, seed=4), bf(n, k, seed=5, scale=0.1)
     c = Guarded((m, n), torch.bfloat16, 555.0)
-    L.check(L.lib().rgnn_tc_gemm_tn(L.ptr(a), k, L.ptr(b), k, L.ptr(c.view), n, m, n, k, 0, None, None, L.stream()), "tn")
+    L.check(L.lib().rgnn_tc_gemm_tn(L.ptr(a), k, L.ptr(b), k, L.ptr(c.view), n, m, n, k, 0, None, None, 1.0, 0.0, L.stream()), "tn")
     c.check("gemm_tn")
     kk = 130
     at, bt = bf(kk, 256, seed=6), bf(kk, n, seed=7)
     cf = Guarded((256, n), torch.float32, 9e9)
     part = Guarded((3, 256, n), torch.float32, 9e9)
-    L.check(L.lib().rgnn_tc_gemm_nn(L.ptr(at), 256, L.ptr(bt), n, L.ptr(cf.view), n, 256, n, kk, L.ptr(part.view), 3, L.stream()), "nn")
+    L.check(L.lib().rgnn_tc_gemm_nn(L.ptr(at), 256, L.ptr(bt), n, L.ptr(cf.view), n, 256, n, kk, 1.0, L.ptr(part.view), 3, L.stream()), "nn")
     cf.check("gemm_nn C")
     part.check("gemm_nn partial")
 

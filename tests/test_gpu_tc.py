@@ -33,7 +33,7 @@ def test_tc_gemm_tn(R, m, n, k, epi):
     else:
         flags, pb, pa = L.EPI_RELU_MASK, None, aux
         ref = ref * (aux.float() > 0)
-    L.check(L.lib().rgnn_tc_gemm_tn(L.ptr(a), k, L.ptr(b), k, L.ptr(c), n, m, n, k, flags, L.ptr(pb), L.ptr(pa), L.stream()), "tn")
+    L.check(L.lib().rgnn_tc_gemm_tn(L.ptr(a), k, L.ptr(b), k, L.ptr(c), n, m, n, k, flags, L.ptr(pb), L.ptr(pa), 1.0, 0.0, L.stream()), "tn")
     torch.cuda.synchronize()
     assert nerr(c.float(), ref) <= 6e-3      # bf16 output rounding = 2^-8 relative
 
@@ -44,7 +44,7 @@ def test_tc_gemm_nn(R, m, n, k, splits):
     a, b = bf(k, m, seed=4), bf(k, n, seed=5)
     c = torch.full((m, n), 7.0, device="cuda")
     part = torch.empty((splits, m, n), device="cuda")
-    L.check(L.lib().rgnn_tc_gemm_nn(L.ptr(a), m, L.ptr(b), n, L.ptr(c), n, m, n, k, L.ptr(part), splits, L.stream()), "nn")
+    L.check(L.lib().rgnn_tc_gemm_nn(L.ptr(a), m, L.ptr(b), n, L.ptr(c), n, m, n, k, 1.0, L.ptr(part), splits, L.stream()), "nn")
     torch.cuda.synchronize()
     assert nerr(c, a.float().t() @ b.float()) <= 1e-5
 
@@ -117,3 +117,54 @@ def test_block_tc_matches_cuda_core_path_and_oracle(R, g_, k, f):
             R._lib.USE_TC = True
     for a, b in zip(*outs):
         assert nerr(a, b) <= 2e-2
+
+
+@pytest.mark.parametrize("m,n,k", [(200, 256, 256), (77, 128, 128)])
+def test_tc_gemm_tn_axpby_identity_mapping(R, m, n, k):
+    """alpha * A.B^T + beta * aux + bias: GCN2Conv's (1-b) X + b X W in one epilogue."""
+    L = R._lib
+    a, b = bf(m, k, seed=21), bf(n, k, seed=22, scale=0.1)
+    aux = bf(m, n, seed=23)
+    bias = torch.randn(n, device="cuda")
+    c = torch.zeros((m, n), dtype=torch.bfloat16, device="cuda")
+    L.check(L.lib().rgnn_tc_gemm_tn(L.ptr(a), k, L.ptr(b), k, L.ptr(c), n, m, n, k, L.EPI_ADD_AUX | L.EPI_BIAS_N, L.ptr(bias), L.ptr(aux),
+                                    0.3, 0.7, L.stream()), "tn")
+    torch.cuda.synchronize()
+    assert nerr(c.float(), 0.3 * (a.float() @ b.float().t()) + 0.7 * aux.float() + bias) <= 6e-3
+
+
+@pytest.mark.parametrize("which", ["graphconv", "gcn2"])
+def test_dgl_style_transforms_on_tensor_cores_bf16(R, which):
+    """GraphConv / GCN2Conv (north-star A11) in bf16 with D = 256: weight transform on tcgen05, vs the fp64 DGL formula."""
+    from oracle import gnn_oracle as O
+    gen = torch.Generator().manual_seed(6)
+    g_, k, d = 40, 5, 256
+    sb = O.synthetic_batch(g_, k, 8, p=1, seed=6)
+    n = g_ * k
+    x, x0 = torch.randn((n, d), generator=gen), torch.randn((n, d), generator=gen)
+    w = torch.randn((d, d), generator=gen) * 0.05
+    b = torch.randn((d,), generator=gen)
+    dy = torch.randn((n, d), generator=gen)
+    t = [v.double().requires_grad_() for v in (x, x0, w, b)]
+    g = R.robot_batch(g_, k, device="cuda")
+    xc, x0c = x.cuda().bfloat16().requires_grad_(), x0.cuda().bfloat16().requires_grad_()
+    if which == "graphconv":
+        ref = O.graphconv(t[0], sb["src"], sb["dst"], t[2], t[3], "both")
+        conv = R.GraphConv(d, d, norm="both")
+        conv.load_state_dict({"weight": w, "bias": b})
+        y = conv.cuda()(g, xc)
+        wparam = conv.weight
+    else:
+        ref = O.gcn2conv(t[0], t[1], sb["src"], sb["dst"], t[2], t[3], layer=2, alpha=0.1, lambda_=1.0)
+        conv = R.GCN2Conv(d, layer=2, alpha=0.1, lambda_=1)
+        conv.load_state_dict({"weight1": w, "bias": b})
+        y = conv.cuda()(g, xc, x0c)
+        wparam = conv.weight1
+    ref.backward(dy.double())
+    y.backward(dy.cuda().bfloat16())
+    assert y.dtype == torch.bfloat16
+    assert nerr(y.float(), ref) <= 2e-2
+    assert nerr(xc.grad.float(), t[0].grad) <= 2e-2
+    assert nerr(wparam.grad, t[2].grad) <= 4e-2 and nerr(conv.bias.grad, t[3].grad) <= 4e-2
+    if which == "gcn2":
+        assert nerr(x0c.grad.float(), t[1].grad) <= 2e-2
