@@ -94,7 +94,7 @@ def test_cast_weights(R):
     assert torch.equal(o, w.to(torch.bfloat16)) and torch.equal(ot, w.t().contiguous().to(torch.bfloat16))
 
 
-@pytest.mark.parametrize("g_,k,f", [(6, 5, 256), (8, 5, 512)])
+@pytest.mark.parametrize("g_,k,f", [(6, 5, 256), (8, 5, 512), (3, 4, 384), (2, 7, 640), (1, 2, 128)])
 def test_block_tc_matches_cuda_core_path_and_oracle(R, g_, k, f):
     """Whole 2-layer block in bf16: tensor-core path vs the CUDA-core rgnn_gemm path (same bf16 operands) and vs the fp64 oracle."""
     from multi_robot_check import check_block, make_block
