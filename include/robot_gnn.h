@@ -184,6 +184,14 @@ int rgnn_tc_cast_weights(const float* w, int64_t rows, int64_t cols, void* out_b
 int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const void* x1, int64_t c1,
                     void* out0, int64_t m0, void* out1, int64_t m1, const float* bias, int64_t nodes, void* stream);
 
+/* the two steps above FUSED (north_star (c)): FiLM-mean aggregation in the prologue of the compress GEMM.
+ * y[v] = W[:, :F] h[v] + W[:, F:] g[v] + bias with g = mean_{u != v} (gamma_{u->v} h[u] + beta_{u->v}) over `graphs` complete
+ * `robots`-node graphs (2..8, reference edge order); h [G*K, F, 64], z [G*K(K-1), 2F] interleaved (gamma,beta), W [Fo, 2F],
+ * y [G*K, Fo, 64], all bf16; bias fp32 [Fo] or NULL.  g is built in shared memory in the tensor-core operand layout and is
+ * written to g_out only if g_out != NULL (the backward needs it); otherwise it never reaches HBM.  F %% 32 == 0, Fo %% 128 == 0. */
+int rgnn_tc_conv_film_fused(const void* W, const void* h, const void* z, const float* bias, void* y, void* g_out,
+                            int64_t graphs, int64_t robots, int64_t F, int64_t Fo, void* stream);
+
 /* weight gradient of the above: dW[m,k] = sum_v sum_p dy[v,m,p] x[v,k,p], x = x0 | x1; dW fp32 (row stride ldw);
  * dbias (nullable) fp32 [M] = sum_v sum_p dy[v,m,p], computed by the otherwise idle epilogue warps from the dy tiles the
  * mainloop stages anyway (no second pass over dy); partial fp32 [splits, M, c0+c1 (+1 if dbias)] scratch; the robots are

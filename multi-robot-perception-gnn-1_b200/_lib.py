@@ -33,6 +33,7 @@ SIGNATURES = {
                  + [_i64] * 6 + [_vp, _i32, _vp, _vp, _f32, _f32, _vp],
     "rgnn_tc_cast_weights": [_vp, _i64, _i64, _vp, _vp, _vp],
     "rgnn_tc_conv1x1": [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp],
+    "rgnn_tc_conv_film_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp],
     "rgnn_tc_conv1x1_wgrad": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _vp],
     "rgnn_tc_gemm_tn": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _f32, _f32, _vp],
     "rgnn_tc_gemm_nn": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _i64, _vp],
@@ -43,6 +44,7 @@ SIGNATURES = {
 }
 
 _lib = None
+USE_FUSED = True   # FiLM aggregation fused into the compress GEMM's prologue (complete graphs of 2..8 robots, bf16, P = 64)
 USE_TC = True      # bf16 transforms on the tcgen05 path when the shape allows (tests flip it to compare with rgnn_gemm)
 
 

@@ -395,10 +395,31 @@ class GNNLayerFn(torch.autograd.Function):
         pose, w2f, a1, z = _edge_mlp_forward(pose, w1, b1, w2, b2, h.dtype)
         if z.shape[1] != 2 * h.shape[1]:
             raise ValueError("edge encoder width does not match the feature maps")
-        gh = torch.empty_like(h)
-        with torch.cuda.device(h.device):
-            _aggregate(ix, h, z, True, None, _lib.POST_MEAN, None, None, gh, None, False)
-        y, wc2, ctx.tc = _compress_forward(h, gh, wc, bc)
+        f = h.shape[1]
+        _, p = _row_shape(h)
+        fo = wc.shape[0]
+        need_bwd = any(ctx.needs_input_grad)
+        fused = bool(_lib.USE_FUSED and _lib.USE_TC and h.dtype == torch.bfloat16 and p == 64 and 2 <= ix.complete_k <= 8 and
+                     f % 32 == 0 and fo % 128 == 0 and ix.N > 0)
+        if fused:
+            # aggregation in the GEMM prologue: g_h is produced in shared memory; it is written out only for the backward
+            wc2 = wc.detach().float().reshape(fo, -1).contiguous()
+            bcf = bc.detach().float().contiguous()
+            y = torch.empty((ix.N, fo) + tuple(h.shape[2:]), dtype=h.dtype, device=h.device)
+            gh = torch.empty_like(h) if need_bwd else None
+            with torch.cuda.device(h.device):
+                wb = _cast_w(wc2)
+                with _lib.timed("compress_film_fused_fwd", 2.0 * fo * 2 * f * ix.N * p):
+                    check(lib().rgnn_tc_conv_film_fused(ptr(wb), ptr(h), ptr(z), ptr(bcf), ptr(y), ptr(gh), ix.G, ix.complete_k, f, fo,
+                                                        stream()), "rgnn_tc_conv_film_fused")
+            ctx.tc = True
+            if gh is None:
+                gh = h.new_empty(0)
+        else:
+            gh = torch.empty_like(h)
+            with torch.cuda.device(h.device):
+                _aggregate(ix, h, z, True, None, _lib.POST_MEAN, None, None, gh, None, False)
+            y, wc2, ctx.tc = _compress_forward(h, gh, wc, bc)
         ctx.g, ctx.wshape = g, tuple(wc.shape)
         ctx.save_for_backward(h, pose, w2f, a1, z, gh, wc2)
         return y

@@ -168,3 +168,32 @@ def test_dgl_style_transforms_on_tensor_cores_bf16(R, which):
     assert nerr(wparam.grad, t[2].grad) <= 4e-2 and nerr(conv.bias.grad, t[3].grad) <= 4e-2
     if which == "gcn2":
         assert nerr(x0c.grad.float(), t[1].grad) <= 2e-2
+
+
+@pytest.mark.parametrize("k,gN,f,fo", [(5, 6, 64, 128), (5, 40, 512, 512), (3, 7, 96, 128), (8, 5, 128, 256), (2, 9, 32, 128), (6, 4, 256, 128)])
+def test_fused_film_conv_forward(R, k, gN, f, fo):
+    """rgnn_tc_conv_film_fused vs the two separate kernels: the aggregated features it writes out are BIT-identical to
+    k_film_fwd_complete (same fp32 formula, same order), y agrees to bf16 rounding (the K loop interleaves the halves)."""
+    L = R._lib
+    g = R.robot_batch(gN, k, device="cuda")
+    ix = g.index()
+    h = bf(gN * k, f, 64, seed=31).abs()
+    z = torch.rand((ix.E, 2 * f), generator=torch.Generator(device="cuda").manual_seed(32), device="cuda").bfloat16()
+    w = bf(fo, 2 * f, seed=33, scale=0.05)
+    bias = torch.randn(fo, device="cuda")
+    gh_ref = torch.empty_like(h)
+    R.functional._aggregate(ix, h, z, True, None, L.POST_MEAN, None, None, gh_ref, None, False)
+    y_ref = torch.empty((gN * k, fo, 64), dtype=torch.bfloat16, device="cuda")
+    if f % 64 == 0:
+        L.check(L.lib().rgnn_tc_conv1x1(L.ptr(w), L.ptr(h), f, L.ptr(gh_ref), f, L.ptr(y_ref), fo, None, 0, L.ptr(bias), gN * k, L.stream()), "conv")
+        y_ref = y_ref.float()
+    else:
+        y_ref = torch.einsum("ok,vkp->vop", w.float(), torch.cat([h, gh_ref], 1).float()) + bias.view(1, -1, 1)
+    for store in (True, False):
+        y = torch.zeros((gN * k, fo, 64), dtype=torch.bfloat16, device="cuda")
+        gh = torch.zeros_like(h) if store else None
+        L.check(L.lib().rgnn_tc_conv_film_fused(L.ptr(w), L.ptr(h), L.ptr(z), L.ptr(bias), L.ptr(y), L.ptr(gh), gN, k, f, fo, L.stream()), "fused")
+        torch.cuda.synchronize()
+        if store:
+            assert torch.equal(gh, gh_ref)
+        assert nerr(y.float(), y_ref) <= 6e-3
