@@ -35,6 +35,7 @@ struct FusedParams {
   const __nv_bfloat16* z;       // unused on device (z arrives through its tensor map); kept for debugging
   const float* bias;
   int store_g;                  // also write the aggregated features (needed by the backward)
+  int debug;                    // RGNN_FUSED_DEBUG bit mask (experiments only): 1 = FiLM warps skip the arithmetic, 2 = epilogue skips stores
 };
 
 template <int KR> struct Cfg {
@@ -45,10 +46,18 @@ template <int KR> struct Cfg {
   static constexpr uint32_t A_BYTES = BM * BKF * 2;                      // 8 KB, SWIZZLE_64B
   static constexpr uint32_t H_BYTES = KR * BKF * 128;                    // K x 4 KB, SWIZZLE_128B
   static constexpr uint32_t Z_BYTES = ((NE * 128 + 1023) / 1024) * 1024; // keeps the next stage 1024-aligned
-  static constexpr uint32_t STAGE = 2 * A_BYTES + 2 * H_BYTES + Z_BYTES;
-  static constexpr int NST = (3 * STAGE + 2 * 16384 + 2048 <= 227 * 1024) ? 3 : 2;
+  // Operand ring (filled by TMA, deep: HBM/L2 latency) and aggregated-tile ring (filled by the FiLM warps, shallow: on-chip latency)
+  static constexpr uint32_t STAGE = 2 * A_BYTES + H_BYTES + Z_BYTES;
+  static constexpr int NG = 2;
+  static constexpr uint32_t OUT_BYTES = 16384;                           // one bf16 output slab
+  static constexpr int NST_FIT = (227 * 1024 - 1024 - 512 - NG * (int)H_BYTES - (int)OUT_BYTES) / (int)STAGE;
+  static constexpr int NST = NST_FIT > 6 ? 6 : NST_FIT;
+  static_assert(NST >= 2, "shared memory budget");
   static constexpr uint32_t TX = 2 * A_BYTES + H_BYTES + NE * 128;       // bytes the producer's TMA loads deliver per stage
-  static constexpr size_t SMEM = 1024 + (size_t)NST * STAGE + 2 * 16384 + 256;
+  static constexpr uint32_t G_OFF = NST * STAGE;
+  static constexpr uint32_t OUT_OFF = G_OFF + NG * H_BYTES;
+  static constexpr uint32_t BAR_OFF = OUT_OFF + OUT_BYTES;
+  static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 512;
 };
 
 template <int KR>
@@ -61,11 +70,12 @@ k_conv_film_fused(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t base = smem_u32(smem);
-  const uint32_t out_stage = base + NST * C::STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NST * C::STAGE + 2 * 16384);
-  const uint32_t bar_full = smem_u32(bars), bar_gfull = smem_u32(bars + NST), bar_empty = smem_u32(bars + 2 * NST);
-  const uint32_t bar_tfull = smem_u32(bars + 3 * NST), bar_tempty = smem_u32(bars + 3 * NST + 1);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NST + 2);
+  const uint32_t g_ring = base + C::G_OFF, out_stage = base + C::OUT_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NST);
+  const uint32_t bar_gfull = smem_u32(bars + 2 * NST), bar_gempty = smem_u32(bars + 2 * NST + C::NG);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * NST + 2 * C::NG), bar_tempty = smem_u32(bars + 2 * NST + 2 * C::NG + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 2 * C::NG + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -76,7 +86,8 @@ k_conv_film_fused(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_gfull + 8 * i, 8); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < C::NG; ++i) { mbar_init(bar_gfull + 8 * i, 8); mbar_init(bar_gempty + 8 * i, 1); }
     mbar_init(bar_tfull, 1);
     mbar_init(bar_tempty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -107,49 +118,60 @@ k_conv_film_fused(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           tma_2d(s0, &tmW, fb, kb * BKF, tm * BM);                               // Wc[:, k-block]
           tma_2d(s0 + C::A_BYTES, &tmW, fb, p.F + kb * BKF, tm * BM);            // Wc[:, F + k-block]
           tma_3d(s0 + 2 * C::A_BYTES, &tmH, fb, 0, kb * BKF, (int)(g * KR));     // h of the graph's robots
-          tma_2d(s0 + 2 * C::A_BYTES + 2 * C::H_BYTES, &tmZ, fb, 2 * kb * BKF, (int)(g * C::NE));   // gamma/beta of its edges
+          tma_2d(s0 + 2 * C::A_BYTES + C::H_BYTES, &tmZ, fb, 2 * kb * BKF, (int)(g * C::NE));   // gamma/beta of its edges
           if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(C::N1 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)((C::N2 > 0 ? C::N2 : 64) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    int stage = 0; uint32_t phase = 0; uint32_t tphase = 0;
-    for (int64_t w = blockIdx.x; w < work_total; w += gridDim.x) {
-      mbar_wait(bar_tempty, tphase ^ 1);                 // the single accumulator has been drained
-      tphase ^= 1;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int kb = 0; kb < p.kblocks; ++kb) {
-        const uint32_t s0 = base + stage * C::STAGE;
-        mbar_wait(bar_full + 8 * stage, phase);
+    // ONE thread runs the whole issue loop (tcgen05.mma / commit are single-thread instructions; eight small MMAs per 32-channel
+    // stage make the issuer's own instruction latency the critical path, so descriptors are precomputed and only their 14-bit
+    // address field is bumped).  Skewed by one k-block: the h half of block i is issued as soon as its operands land, the
+    // aggregated half of block i-1 right after it - the tensor pipe always has queued work while the FiLM warps process block i.
+    if (lane == 0) {
+      const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(C::N1 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)((C::N2 > 0 ? C::N2 : 64) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint64_t dA = make_desc(base, 0, 512, 4);                    // K-major SWIZZLE_64B template (address field = base)
+      const uint64_t dB = make_desc(base, BKF * 128, 1024);              // MN-major SWIZZLE_128B template
+      auto at = [](uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); };   // stays inside the 14-bit field (< 256 KB)
+      int stage = 0; uint32_t phase = 0;         // operand ring position of the h half being issued
+      int pstage = 0;                            // operand stage of the pending aggregated half
+      int gb = 0; uint32_t gphase = 0;           // aggregated-tile ring position of the pending aggregated half
+      uint32_t tphase = 0;
+      auto issue_agg = [&](bool last_of_tile) {
+        mbar_wait(bar_gfull + 8 * gb, gphase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one()) {
+        const uint32_t a_off = pstage * C::STAGE + C::A_BYTES, g_off = C::G_OFF + gb * C::H_BYTES;
+#pragma unroll
+        for (int k = 0; k < BKF / 16; ++k) {             // aggregated half:  D += Wc[:, F + kb] . g
+          umma(tmem_base, at(dA, a_off + k * 32), at(dB, g_off + k * 2048), idesc1, 1u);
+          if (C::N2 > 0) umma(tmem_base + C::N1, at(dA, a_off + k * 32), at(dB, g_off + k * 2048 + (C::N1 / 64) * (BKF * 128)), idesc2, 1u);
+        }
+        umma_commit(bar_empty + 8 * pstage);             // operand stage free (its h tile was also read by the FiLM warps: done before gfull)
+        umma_commit(bar_gempty + 8 * gb);                // aggregated tile buffer free
+        if (last_of_tile) umma_commit(bar_tfull);
+        if (++gb == C::NG) { gb = 0; gphase ^= 1; }
+      };
+      for (int64_t w = blockIdx.x; w < work_total; w += gridDim.x) {
+        mbar_wait(bar_tempty, tphase ^ 1);               // the single accumulator has been drained
+        tphase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_off = stage * C::STAGE, h_off = a_off + 2 * C::A_BYTES;
+          const uint32_t acc0 = kb > 0 ? 1u : 0u;
 #pragma unroll
           for (int k = 0; k < BKF / 16; ++k) {           // h half:  D += Wc[:, kb] . h
-            const uint64_t da = make_desc(s0 + k * 32, 0, 512, 4);
-            const uint32_t hb = s0 + 2 * C::A_BYTES + k * 2048;
-            umma(tmem_base, da, make_desc(hb, BKF * 128, 1024), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
-            if (C::N2 > 0) umma(tmem_base + C::N1, da, make_desc(hb + (C::N1 / 64) * (BKF * 128), BKF * 128, 1024), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+            umma(tmem_base, at(dA, a_off + k * 32), at(dB, h_off + k * 2048), idesc1, k > 0 ? 1u : acc0);
+            if (C::N2 > 0) umma(tmem_base + C::N1, at(dA, a_off + k * 32), at(dB, h_off + k * 2048 + (C::N1 / 64) * (BKF * 128)), idesc2, k > 0 ? 1u : acc0);
           }
+          if (kb > 0) issue_agg(false);                  // aggregated half of the previous k-block
+          pstage = stage;
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        mbar_wait(bar_gfull + 8 * stage, phase);         // the FiLM warps have written the aggregated tile
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < BKF / 16; ++k) {           // aggregated half:  D += Wc[:, F + kb] . g
-            const uint64_t da = make_desc(s0 + C::A_BYTES + k * 32, 0, 512, 4);
-            const uint32_t gb = s0 + 2 * C::A_BYTES + C::H_BYTES + k * 2048;
-            umma(tmem_base, da, make_desc(gb, BKF * 128, 1024), idesc1, 1u);
-            if (C::N2 > 0) umma(tmem_base + C::N1, da, make_desc(gb + (C::N1 / 64) * (BKF * 128), BKF * 128, 1024), idesc2, 1u);
-          }
-          umma_commit(bar_empty + 8 * stage);
-          if (kb == p.kblocks - 1) umma_commit(bar_tfull);
-        }
-        __syncwarp();
-        if (++stage == NST) { stage = 0; phase ^= 1; }
+        issue_agg(true);                                 // aggregated half of the tile's last k-block
       }
     }
   } else if (warp >= 4 && warp < 12) {
@@ -160,53 +182,71 @@ k_conv_film_fused(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const bool issuer = ft == 0;
     const float inv = 1.0f / (KR - 1);
     int stage = 0; uint32_t phase = 0;
+    int gb = 0; uint32_t gphase = 0;
     for (int64_t w = blockIdx.x; w < work_total; w += gridDim.x) {
       const int tm = (int)(w % p.tiles_m);
       const int64_t g = w / p.tiles_m;
       for (int kb = 0; kb < p.kblocks; ++kb) {
         const uint32_t s0 = base + stage * C::STAGE;
-        const uint32_t hs = s0 + 2 * C::A_BYTES, gs = hs + C::H_BYTES, zs = gs + C::H_BYTES;
+        const uint32_t hs = s0 + 2 * C::A_BYTES, zs = hs + C::H_BYTES;
+        const uint32_t gs = g_ring + gb * C::H_BYTES;
+        mbar_wait(bar_full + 8 * stage, phase);
+        float2 xv[KR][4];
+        const unsigned char* hsp = smem + (hs - base);
+#pragma unroll
+        for (int u = 0; u < KR; ++u) {      // plain shared loads (not volatile asm): the compiler is free to hoist / interleave them
+          const uint4 t = *reinterpret_cast<const uint4*>(hsp + u * (BKF * 128) + voff);
+          const uint32_t ws[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xv[u][i] = make_float2(__uint_as_float(ws[i] << 16), __uint_as_float(ws[i] & 0xffff0000u));
+        }
+        // the KR(KR-1) gamma/beta pairs of this channel, fetched up front (plain loads: the compiler may schedule them freely)
+        const uint32_t* zrow = reinterpret_cast<const uint32_t*>(smem + (zs - base)) + c;
+        uint32_t gw[C::NE];
+#pragma unroll
+        for (int e = 0; e < C::NE; ++e) gw[e] = zrow[e * 32];
+        // the aggregated-tile buffer: its previous tensor-core reader (and, when g is stored, its TMA store) must be done
+        mbar_wait(bar_gempty + 8 * gb, gphase ^ 1);
         if (p.store_g) {
-          // the aggregated tile written NST k-blocks ago into this buffer must have been read by its TMA store
-          if (issuer) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NST - 1) : "memory");
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::NG - 1) : "memory");
           named_bar_sync(3, 256);
         }
-        mbar_wait(bar_full + 8 * stage, phase);
-        float xv[KR][8];
+        unsigned char* gsp = smem + (gs - base);
+        uint4 outv[KR];
+        if (!(p.debug & 1)) {
 #pragma unroll
-        for (int u = 0; u < KR; ++u) {
-          uint32_t a0, a1, a2, a3;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(hs + u * (BKF * 128) + voff));
-          const uint32_t ws[4] = {a0, a1, a2, a3};
+          for (int a = 0; a < KR; ++a) {
+            float2 acc[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { xv[u][2 * i] = __uint_as_float(ws[i] << 16); xv[u][2 * i + 1] = __uint_as_float(ws[i] & 0xffff0000u); }
-        }
+            for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
+            float bsum = 0.f;
 #pragma unroll
-        for (int a = 0; a < KR; ++a) {
-          float acc[8];
+            for (int u = 0; u < KR; ++u) {
+              if (u == a) continue;
+              const uint32_t g1 = gw[u * (KR - 1) + (a < u ? a : a - 1)];
+              const float gam = __uint_as_float(g1 << 16);
+              bsum += __uint_as_float(g1 & 0xffff0000u);
+              const float2 g2 = make_float2(gam, gam);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-          float bsum = 0.f;
+              for (int i = 0; i < 4; ++i) acc[i] = ffma2(g2, xv[u][i], acc[i]);      // FFMA2: two fp32 FMAs per instruction
+            }
+            const float2 b2 = make_float2(bsum, bsum), i2 = make_float2(inv, inv);
+            uint32_t o[4];
 #pragma unroll
-          for (int u = 0; u < KR; ++u) {
-            if (u == a) continue;
-            const int e = u * (KR - 1) + (a < u ? a : a - 1);
-            uint32_t gw;
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(gw) : "r"(zs + e * 128 + c * 4));
-            const float gam = __uint_as_float(gw << 16), bet = __uint_as_float(gw & 0xffff0000u);
-            bsum += bet;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaf(gam, xv[u][i], acc[i]);
+            for (int i = 0; i < 4; ++i) {
+              const float2 t = fmul2(fadd2(acc[i], b2), i2);
+              o[i] = pack_bf16(t.x, t.y);
+            }
+            outv[a] = make_uint4(o[0], o[1], o[2], o[3]);
           }
-          uint32_t o[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) o[i] = pack_bf16((acc[2 * i] + bsum) * inv, (acc[2 * i + 1] + bsum) * inv);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(gs + a * (BKF * 128) + voff), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+          for (int a = 0; a < KR; ++a) *reinterpret_cast<uint4*>(gsp + a * (BKF * 128) + voff) = outv[a];
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to tcgen05 / TMA
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_gfull + 8 * stage);
-        if (p.store_g && tm == 0) {                       // every M-tile computes the same g: one of them writes it out
+        if (lane == 0) mbar_arrive(bar_gfull + 8 * gb);
+        if (p.store_g && tm == (int)(g % p.tiles_m)) {    // every M-tile computes the same g: one of them (rotating with g, so
+                                                          // that the duty is spread over all CTAs) writes it out
           named_bar_sync(3, 256);
           if (issuer) {
             tma_store_3d(&tmG, gs, 0, kb * BKF, (int)(g * KR));
@@ -216,6 +256,7 @@ k_conv_film_fused(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");       // keep the group count in step with the wait above
         }
         if (++stage == NST) { stage = 0; phase ^= 1; }
+        if (++gb == C::NG) { gb = 0; gphase ^= 1; }
       }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -234,8 +275,8 @@ k_conv_film_fused(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       const float bias_m = p.bias ? p.bias[tm * BM + row] : 0.f;
 #pragma unroll 1
       for (int j = 0; j < KR; ++j) {
-        const uint32_t stg = out_stage + (j & 1) * 16384;
-        if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        const uint32_t stg = out_stage;
+        if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the slab's previous store has read it
         named_bar_sync(2, 128);
         uint32_t r0[32], r1[32];
         tmem_ld32_issue(tacc + (2 * j) * 32, r0);
@@ -260,7 +301,7 @@ k_conv_film_fused(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         named_bar_sync(2, 128);
         if (ew == 0 && lane == 0) {
-          tma_store_2d(&tmY, stg, 0, (int)((g * KR + j) * p.Fo + tm * BM));
+          if (!(p.debug & 2)) tma_store_2d(&tmY, stg, 0, (int)((g * KR + j) * p.Fo + tm * BM));
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
@@ -311,6 +352,7 @@ static int launch_fused(const void* W, const void* h, const void* z, const float
   FusedParams p = {};
   p.tiles_m = (int)(Fo / BM); p.graphs = graphs; p.F = (int)F; p.Fo = (int)Fo; p.kblocks = (int)(F / BKF);
   p.bias = bias; p.store_g = gout != nullptr;
+  { const char* e = getenv("RGNN_FUSED_DEBUG"); p.debug = e ? atoi(e) : 0; }
   const int64_t work = graphs * p.tiles_m;
   const int grid = (int)(work < kNumSMs ? work : kNumSMs);
   if (grid < 1) return 0;

@@ -197,3 +197,32 @@ def test_fused_film_conv_forward(R, k, gN, f, fo):
         if store:
             assert torch.equal(gh, gh_ref)
         assert nerr(y.float(), y_ref) <= 6e-3
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_block_with_fused_prologue_matches_unfused(R, train):
+    """The opt-in fused path (USE_FUSED) inside the whole block: same outputs / gradients as the default path; in eval the
+    aggregated features are never written."""
+    from multi_robot_check import make_block
+    from oracle import gnn_oracle as O
+    G, K, F = 6, 5, 256
+    sb = O.synthetic_batch(G, K, F, p=64, seed=4)
+    res = []
+    for fused in (False, True):
+        R._lib.USE_FUSED = fused
+        try:
+            blk, _ = make_block(R, O, F, True, True)
+            blk.cuda()
+            g = R.robot_batch(G, K, device="cuda")
+            h = sb["h"].reshape(G * K, F, 8, 8).cuda().bfloat16().requires_grad_(train)
+            if train:
+                y = blk(g, h, sb["pose"].cuda())
+                y.backward(sb["dy"].reshape(y.shape).cuda().bfloat16())
+                res.append((y.detach().float(), h.grad.float(), blk.conv1.weight.grad.clone(), blk.gcn2.edge_encoder.layers[2].weight.grad.clone()))
+            else:
+                with torch.no_grad():
+                    res.append((blk(g, h, sb["pose"].cuda()).float(),))
+        finally:
+            R._lib.USE_FUSED = False
+    for a, b in zip(*res):
+        assert nerr(b, a) <= 1e-2
