@@ -42,13 +42,47 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="graph chunks the host-buffer pipeline overlaps")
-    ap.add_argument("--cpu-graphs", type=int, default=32, help="graphs in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-graphs", type=int, default=192, help="graphs in the bounded CPU-baseline sample")
+    ap.add_argument("--layers", type=int, default=2, choices=[1, 2], help="1 = gcn1 only (-multi_gcn off)")
+    ap.add_argument("--no-compress", action="store_true", help="no 1x1 compress conv (-compress_gcn off; single layer only)")
+    ap.add_argument("--torch-baseline", action="store_true",
+                    help="also time a plain PyTorch-on-GPU restatement (index_select / index_add_ / conv2d) of the same step")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return (f"warehouse gcn2 stack (2x FiLM-GCN + 1x1 compress), F={a.feat} (resnet18 width), K={a.robots} robots, P=8x8, "
-            f"{a.graphs} graphs/GPU, {a.dtype}")
+    width = {512: " (resnet18 width)", 1280: " (mobilenetv2 width)", 2048: " (resnet50 width)"}.get(a.feat, "")
+    if a.layers == 2:
+        stack = "warehouse gcn2 stack (2x FiLM-GCN + 1x1 compress)"
+    else:
+        stack = "gcn stack (1x FiLM-GCN" + (")" if a.no_compress else " + 1x1 compress)")
+    return f"{stack}, F={a.feat}{width}, K={a.robots} robots, P=8x8, {a.graphs} graphs/GPU, {a.dtype}"
+
+
+def torch_gpu_step_fn(blk, g, a):
+    """A plain PyTorch-on-GPU restatement of the same block (what a user without DGL or this library would write): gather,
+    broadcast FiLM, index_add_ mean, cat, conv2d.  Uses the block's own parameters; timed as a reported baseline only."""
+    import torch.nn.functional as Fn
+    src, dst = g.edges()
+    src, dst = src.long(), dst.long()
+    inv = 1.0 / g.in_degrees().clamp(min=1).to(torch.float32)
+
+    def layer(gcn, conv, h, pose):
+        l0, l2 = gcn.edge_encoder.layers[0], gcn.edge_encoder.layers[2]
+        z = torch.sigmoid(Fn.linear(torch.relu(Fn.linear(pose.to(h.dtype), l0.weight.to(h.dtype), l0.bias.to(h.dtype))),
+                                    l2.weight.to(h.dtype), l2.bias.to(h.dtype)))
+        m = z[:, 0::2, None, None] * h.index_select(0, src) + z[:, 1::2, None, None]
+        agg = torch.zeros_like(h).index_add_(0, dst, m) * inv.to(h.dtype)[:, None, None, None]
+        if conv is None:
+            return agg
+        return Fn.conv2d(torch.cat((h, agg), 1), conv.weight.to(h.dtype), conv.bias.to(h.dtype))
+
+    def fwd(h, pose):
+        y = layer(blk.gcn1, None if a.no_compress else blk.conv1, h, pose)
+        if a.layers == 2:
+            y = layer(blk.gcn2, blk.conv2, y, pose)
+        return y
+    return fwd
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -98,7 +132,7 @@ def cpu_reference_rate(a, reps):
     from oracle import ref_port
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sec = ref_port.time_block(a.feat, a.robots, a.cpu_graphs, True, True, reps=reps, threads=cores)
+    sec = ref_port.time_block(a.feat, a.robots, a.cpu_graphs, not a.no_compress, a.layers == 2, reps=reps, threads=cores)
     return a.cpu_graphs / sec, cores, sec
 
 
@@ -142,7 +176,9 @@ def main():
     G, K, F = a.graphs, a.robots, a.feat
     N, E = G * K, G * K * (K - 1)
     torch.manual_seed(1)                 # reference default seed (training.py:24); PyTorch-default init of Linear / Conv2d
-    blk = R.GNNBlock(types.SimpleNamespace(feature_dim=F, compress_gcn=True, multi_gcn=True))
+    if a.no_compress and a.layers == 2:
+        raise SystemExit("two layers need the compress conv (dgl/model/models.py:169)")
+    blk = R.GNNBlock(types.SimpleNamespace(feature_dim=F, compress_gcn=not a.no_compress, multi_gcn=a.layers == 2))
     blk.to(dev)
     sync = R.parallel.GradSync(blk) if world > 1 else None
 
@@ -234,6 +270,28 @@ def main():
                "d2h_bytes_per_step": d2h, "steps": n_e2e,
                "api": f"HostPipeline.step: pinned host h/pose/dy in, y/dh out, {a.e2e_chunks} graph chunks overlapped on 3 streams"}
 
+    torch_gpu = None
+    if a.torch_baseline and rank == 0:
+        fwd = torch_gpu_step_fn(blk, g, a)
+
+        def tstep():
+            h.grad = None
+            for p in blk.parameters():
+                p.grad = None
+            fwd(h, pose).backward(dy)
+        for _ in range(3):
+            tstep()
+        torch.cuda.synchronize()
+        nt = max(3, min(a.steps, 10))
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(nt):
+            tstep()
+        t1.record()
+        torch.cuda.synchronize()
+        torch_gpu = {"value": G * nt / (t0.elapsed_time(t1) * 1e-3), "unit": "graphs/s", "ms_per_step": t0.elapsed_time(t1) / nt,
+                     "what": f"plain PyTorch {torch.__version__} eager on the same GPU and inputs (index_select / index_add_ / cuBLAS / cuDNN), 1 GPU"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -284,10 +342,12 @@ def main():
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": a.dtype, "data": "synthetic",
             "config": {"workload": workload_name(a), "graphs_per_gpu": G, "robots": K, "feature_dim": F, "pixels": PIX,
-                       "layers": 2, "compress": True, "l2_policy": "inputs (1.3 GB/GPU) larger than the 126 MB L2",
+                       "layers": a.layers, "compress": not a.no_compress, "l2_policy": "inputs (1.3 GB/GPU) larger than the 126 MB L2",
                        "parallelism": f"dp{world}: graphs sharded, NCCL all-reduce of GNN-layer grads only"},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk}
+    if torch_gpu is not None:
+        line["torch_gpu_baseline"] = torch_gpu
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

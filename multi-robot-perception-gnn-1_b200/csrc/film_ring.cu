@@ -1,0 +1,205 @@
+// A5/A6/A10 on complete K-robot graphs (dgl/model/models.py:207-211,223 and their autograd), streaming variant for P = 8x8:
+// a producer warp keeps a ring of shared-memory stages full with the bulk-copy engine (cp.async.bulk + mbarrier, no tensor
+// map: every piece is a contiguous run), consumer warps read their vectors from shared memory, do the FiLM arithmetic with
+// packed fp32 (FFMA2) and store straight to global memory.  Compared with the register-prefetch kernels of film_complete.cu
+// the bytes in flight per SM no longer depend on occupancy x registers (NST-1 whole stages are always outstanding), no LSU
+// instruction is spent on global loads, and gamma/beta come from the same stage instead of 20 scattered 4-byte loads.
+//
+// Work item = (graph g, block of CH channels): K pieces of CH*P elements (4 KB each, one per robot; kinds x K for the
+// backward) plus K(K-1) pieces of 2*CH interleaved gamma/beta values (128 B each).  CH * P = TPB * 16 B / sizeof(T).
+#include <stdlib.h>
+#include "common.cuh"
+#include "film_common.cuh"
+
+namespace rgnn {
+
+constexpr int RING_P = 64;        // pixels per channel this variant is built for (8x8 maps: image_size 256 / 32, models.py:41)
+constexpr int RING_TPB = 256;     // consumer threads = 16-byte vectors per robot per item
+
+template <typename T, int K> struct RingShape {
+  static constexpr int VEC = Vec16<T>::N;
+  static constexpr int NE = K * (K - 1);
+  static constexpr int LPC = RING_P / VEC;                 // lanes per channel
+  static constexpr int CH = RING_TPB / LPC;                // channels per item: 32 (bf16) / 16 (fp32)
+  static constexpr int PIECE = RING_TPB * 16;              // 4 KB
+  static constexpr int ZPIECE = 2 * CH * (int)sizeof(T);   // 128 B
+};
+
+__device__ __forceinline__ float2 unpack_pair(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+
+template <typename T> __device__ __forceinline__ float2 lds_pair(const unsigned char* p);
+template <> __device__ __forceinline__ float2 lds_pair<float>(const unsigned char* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float2 lds_pair<__nv_bfloat16>(const unsigned char* p) { return unpack_pair(*reinterpret_cast<const uint32_t*>(p)); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// forward: out[a] = mean_{u != a} (gamma[e(u,a)] * x[u] + beta[e(u,a)])       (HAS_Z = false: plain mean, copy_u)
+template <typename T, int K, bool HAS_Z, int NST>
+__global__ void __launch_bounds__(RING_TPB + 32) k_film_fwd_ring(const T* __restrict__ x, int64_t ldx, const T* __restrict__ z,
+                                                                 T* __restrict__ out, int64_t ldout, T* __restrict__ copy_to,
+                                                                 int64_t G, int F) {
+  using S = RingShape<T, K>;
+  constexpr int VEC = S::VEC, NE = S::NE, NP = VEC / 2;
+  constexpr bool EXACT = sizeof(T) == 4;       // fp32: the reference's rounding order; bf16: fused multiply-add
+  constexpr int STAGE = K * S::PIECE + (HAS_Z ? NE * S::ZPIECE : 0);
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + NST;
+  unsigned char* ring = smem + 128;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int ipg = F / S::CH;                               // items per graph
+  const int64_t items = G * ipg;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; ++s) { tma::mbar_init(full + s, 1); tma::mbar_init(empty + s, RING_TPB / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid >= RING_TPB) {                                   // ---- producer warp
+    int s = 0; uint32_t ph = 0;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+      const int64_t g = it / ipg;
+      const int cb = (int)(it - g * ipg);
+      tma::mbar_wait(empty + s, ph ^ 1);                   // first lap: passes immediately (phase bit starts at 0)
+      unsigned char* st = ring + (size_t)s * STAGE;
+      if (lane == 0) tma::mbar_expect_tx(full + s, STAGE);
+      __syncwarp();
+      for (int i = lane; i < K + (HAS_Z ? NE : 0); i += 32) {
+        if (i < K) tma::bulk_g2s(st + i * S::PIECE, x + (g * K + i) * ldx + (int64_t)cb * S::CH * RING_P, S::PIECE, full + s);
+        else tma::bulk_g2s(st + K * S::PIECE + (i - K) * S::ZPIECE, z + (g * NE + (i - K)) * 2 * (int64_t)F + 2 * cb * S::CH, S::ZPIECE, full + s);
+      }
+      if (++s == NST) { s = 0; ph ^= 1; }
+    }
+    return;
+  }
+
+  // ---- consumers
+  const int cl = tid / S::LPC;                             // channel of this thread inside the item
+  const float w = 1.0f / (K - 1);
+  int s = 0; uint32_t ph = 0;
+  for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+    const int64_t g = it / ipg;
+    const int cb = (int)(it - g * ipg);
+    const int64_t off = (int64_t)cb * S::CH * RING_P + tid * VEC;
+    const int64_t n0 = g * K;
+    const unsigned char* st = ring + (size_t)s * STAGE;
+    tma::mbar_wait(full + s, ph);
+    float2 xv[K][NP];
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      const uint4 cx = *reinterpret_cast<const uint4*>(st + u * S::PIECE + tid * 16);
+      if (copy_to) *reinterpret_cast<uint4*>(copy_to + (n0 + u) * ldout + off) = cx;
+      if constexpr (EXACT) {
+        xv[u][0] = make_float2(__uint_as_float(cx.x), __uint_as_float(cx.y));
+        xv[u][1] = make_float2(__uint_as_float(cx.z), __uint_as_float(cx.w));
+      } else {
+        xv[u][0] = unpack_pair(cx.x); xv[u][1] = unpack_pair(cx.y); xv[u][2] = unpack_pair(cx.z); xv[u][3] = unpack_pair(cx.w);
+      }
+    }
+    const unsigned char* zs = st + K * S::PIECE + cl * 2 * (int)sizeof(T);
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+      float2 acc[NP];
+#pragma unroll
+      for (int q = 0; q < NP; ++q) acc[q] = make_float2(0.f, 0.f);
+      float bsum = 0.f;
+#pragma unroll
+      for (int u = 0; u < K; ++u) {      // ascending u == ascending edge id among the in-edges of a
+        if (u == a) continue;
+        if constexpr (!HAS_Z) {
+#pragma unroll
+          for (int q = 0; q < NP; ++q) acc[q] = fadd2(acc[q], xv[u][q]);
+        } else {
+          const float2 gb = lds_pair<T>(zs + edge_id(K, u, a) * S::ZPIECE);
+          const float2 g2 = make_float2(gb.x, gb.x);
+          if constexpr (EXACT) {      // scalar on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (one rounding)
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+              acc[q].x = __fadd_rn(acc[q].x, __fadd_rn(__fmul_rn(gb.x, xv[u][q].x), gb.y));
+              acc[q].y = __fadd_rn(acc[q].y, __fadd_rn(__fmul_rn(gb.x, xv[u][q].y), gb.y));
+            }
+          } else {
+            bsum += gb.y;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) acc[q] = ffma2(g2, xv[u][q], acc[q]);
+          }
+        }
+      }
+      float o[VEC];
+      if constexpr (EXACT) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) { o[2 * q] = __fdiv_rn(acc[q].x, (float)(K - 1)); o[2 * q + 1] = __fdiv_rn(acc[q].y, (float)(K - 1)); }
+      } else {
+        const float2 b2 = make_float2(bsum, bsum), w2 = make_float2(w, w);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) { const float2 r = fmul2(fadd2(acc[q], b2), w2); o[2 * q] = r.x; o[2 * q + 1] = r.y; }
+      }
+      Vec16<T>::store(out + (n0 + a) * ldout + off, o);
+    }
+    __syncwarp();
+    if (lane == 0) tma::mbar_arrive(empty + s);
+    if (++s == NST) { s = 0; ph ^= 1; }
+  }
+}
+
+template <int K> constexpr int ring_fwd_stages() { return K <= 3 ? 8 : (K <= 5 ? 4 : 3); }
+
+template <typename T, int K, bool HAS_Z>
+static int launch_fwd_ring_k(const T* x, int64_t ldx, const T* z, T* out, int64_t ldout, T* copy_to, int64_t G, int F, cudaStream_t st) {
+  using S = RingShape<T, K>;
+  constexpr int NST = ring_fwd_stages<K>();
+  constexpr size_t smem = 128 + (size_t)NST * (K * S::PIECE + (HAS_Z ? S::NE * S::ZPIECE : 0));
+  auto kern = k_film_fwd_ring<T, K, HAS_Z, NST>;
+  static bool done = false;
+  static int per_sm = 1;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_film_fwd_ring)");
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RING_TPB + 32, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(k_film_fwd_ring)");
+    if (per_sm < 1) per_sm = 1;
+    done = true;
+  }
+  const int64_t items = G * (F / S::CH);
+  int64_t blocks = (int64_t)per_sm * kNumSMs;
+  if (blocks > items) blocks = items;
+  if (blocks < 1) return 0;
+  kern<<<(unsigned)blocks, RING_TPB + 32, smem, st>>>(x, ldx, z, out, ldout, copy_to, G, F);
+  RGNN_LAUNCH_CHECK("k_film_fwd_ring");
+  return 0;
+}
+
+template <typename T, bool HAS_Z>
+static int launch_fwd_ring(int K, const T* x, int64_t ldx, const T* z, T* out, int64_t ldout, T* copy_to, int64_t G, int F, cudaStream_t st) {
+#define RGNN_CASE(KK) case KK: return launch_fwd_ring_k<T, KK, HAS_Z>(x, ldx, z, out, ldout, copy_to, G, F, st);
+  switch (K) { RGNN_CASE(2) RGNN_CASE(3) RGNN_CASE(4) RGNN_CASE(5) RGNN_CASE(6) RGNN_CASE(7) RGNN_CASE(8) default: return RGNN_E_UNSUPPORTED; }
+#undef RGNN_CASE
+}
+
+static int g_ring = -1;
+static bool ring_enabled() {
+  if (g_ring < 0) { const char* e = getenv("RGNN_FILM_RING"); g_ring = (e && e[0] == '0') ? 0 : 1; }   // RGNN_FILM_RING=0: register-prefetch kernels
+  return g_ring == 1;
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// true when the streaming variant can take the call (the caller falls back to film_complete.cu otherwise)
+bool film_fwd_ring_ok(int dtype, int K, const void* x, int64_t ldx, const void* z, int64_t F, int64_t P) {
+  const int es = dtype == RGNN_F32 ? 4 : 2;
+  const int ch = dtype == RGNN_F32 ? RingShape<float, 2>::CH : RingShape<__nv_bfloat16, 2>::CH;
+  return ring_enabled() && K >= 2 && K <= 8 && P == RING_P && F % ch == 0 && (ldx * es) % 16 == 0 && aligned16(x) && (!z || aligned16(z));
+}
+
+int film_fwd_ring(int dtype, int K, const void* x, int64_t ldx, const void* z, void* out, int64_t ldout, void* copy_to, int64_t G,
+                  int64_t F, cudaStream_t st) {
+  if (dtype == RGNN_F32) {
+    auto X = static_cast<const float*>(x); auto Z = static_cast<const float*>(z);
+    return z ? launch_fwd_ring<float, true>(K, X, ldx, Z, static_cast<float*>(out), ldout, static_cast<float*>(copy_to), G, (int)F, st)
+             : launch_fwd_ring<float, false>(K, X, ldx, Z, static_cast<float*>(out), ldout, static_cast<float*>(copy_to), G, (int)F, st);
+  }
+  auto X = static_cast<const __nv_bfloat16*>(x); auto Z = static_cast<const __nv_bfloat16*>(z);
+  return z ? launch_fwd_ring<__nv_bfloat16, true>(K, X, ldx, Z, static_cast<__nv_bfloat16*>(out), ldout, static_cast<__nv_bfloat16*>(copy_to), G, (int)F, st)
+           : launch_fwd_ring<__nv_bfloat16, false>(K, X, ldx, Z, static_cast<__nv_bfloat16*>(out), ldout, static_cast<__nv_bfloat16*>(copy_to), G, (int)F, st);
+}
+
+}  // namespace rgnn
