@@ -499,8 +499,15 @@ int film_fwd_complete(int dtype, int K, const void* x, int64_t ldx, const void* 
            : launch_fwd<__nv_bfloat16, false>(K, X, ldx, Z, static_cast<__nv_bfloat16*>(out), ldout, static_cast<__nv_bfloat16*>(copy_to), G, (int)F, (int)P, st);
 }
 
+int film_bwd_ring(int dtype, int K, const void* h, int64_t ldh, const void* dagg, int64_t ldd, const void* z, const void* addend,
+                  int64_t ldadd, void* dh, int64_t lddh, void* dz, int64_t G, int64_t F, int64_t P, int fuse_sig, cudaStream_t st);
+
 int film_bwd_complete(int dtype, int K, const void* h, int64_t ldh, const void* dagg, int64_t ldd, const void* z, const void* addend,
                       int64_t ldadd, void* dh, int64_t lddh, void* dz, int64_t G, int64_t F, int64_t P, int fuse_sig, cudaStream_t st) {
+  {
+    const int rc = film_bwd_ring(dtype, K, h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sig, st);
+    if (rc != RGNN_E_UNSUPPORTED) return rc;
+  }
   if (dtype == RGNN_F32)
     return launch_bwd<float>(K, static_cast<const float*>(h), ldh, static_cast<const float*>(dagg), ldd, static_cast<const float*>(z),
                              static_cast<const float*>(addend), ldadd, static_cast<float*>(dh), lddh, static_cast<float*>(dz), G, (int)F, (int)P, fuse_sig, st);

@@ -176,6 +176,240 @@ static int launch_fwd_ring(int K, const T* x, int64_t ldx, const T* z, T* out, i
 #undef RGNN_CASE
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// backward:  dh[u] = addend[u] + w * sum_{a != u} gamma[e(u,a)] * dagg[a]
+//            dz[e(u,a)] = (sig') * w * (sum_p h[u] dagg[a], sum_p dagg[a]),   w = 1/(K-1)
+// Two consumer groups of TPB threads share every stage: group A produces dh (reads dagg, gamma, addend), group B produces
+// dz (reads h, dagg; per-lane pixel partials, one reduce-scatter over the LPC lanes of a channel, sigmoid' in the epilogue).
+// Splitting the work instead of the items halves the registers either group needs and doubles the warps that hide latency.
+template <typename T, int K, int TPB> struct RingBwd {
+  static constexpr int VEC = Vec16<T>::N;
+  static constexpr int NE = K * (K - 1);
+  static constexpr int LPC = RING_P / VEC;
+  static constexpr int CH = TPB / LPC;
+  static constexpr int PIECE = TPB * 16;
+  static constexpr int ZPIECE = 2 * CH * (int)sizeof(T);
+  static constexpr int NVP = (NE + LPC - 1) / LPC * LPC;
+  __host__ __device__ static constexpr int stage(int nkind) { return nkind * K * PIECE + NE * ZPIECE; }
+  static constexpr int HEAD = 128 + (8 * CH * K * 4 + 127) / 128 * 128;     // barriers + sum exchange (<= 8 stages)
+};
+
+template <typename T> __device__ __forceinline__ void unpack2(const uint4& v, float2 (&o)[Vec16<T>::N / 2]);
+template <> __device__ __forceinline__ void unpack2<float>(const uint4& v, float2 (&o)[2]) {
+  o[0] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y)); o[1] = make_float2(__uint_as_float(v.z), __uint_as_float(v.w));
+}
+template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(const uint4& v, float2 (&o)[4]) {
+  o[0] = unpack_pair(v.x); o[1] = unpack_pair(v.y); o[2] = unpack_pair(v.z); o[3] = unpack_pair(v.w);
+}
+
+template <typename T, int K, int TPB, int NST>
+__global__ void __launch_bounds__(2 * TPB + 32, 1) k_film_bwd_ring(const T* __restrict__ h, int64_t ldh, const T* __restrict__ dagg, int64_t ldd,
+                                                                   const T* __restrict__ z, const T* addend, int64_t ldadd,
+                                                                   T* dh, int64_t lddh, T* __restrict__ dz, int64_t G, int F, int fuse_sig) {
+  using S = RingBwd<T, K, TPB>;
+  constexpr int VEC = S::VEC, NE = S::NE, NP = VEC / 2, LPC = S::LPC, NVP = S::NVP;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + NST;
+  uint64_t* sdfull = empty + NST;                          // group A -> group B: the per-channel sums of dagg are in sdx
+  float* sdx = reinterpret_cast<float*>(smem + 128);        // [NST][CH][K]
+  unsigned char* ring = smem + S::HEAD;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool has_add = addend != nullptr;
+  const int stage_bytes = S::stage(has_add ? 3 : 2);
+  const int ipg = F / S::CH;
+  const int64_t items = G * ipg;
+  constexpr int OFF_D = K * S::PIECE, OFF_Z = 2 * K * S::PIECE, OFF_A = OFF_Z + NE * S::ZPIECE;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; ++s) { tma::mbar_init(full + s, 1); tma::mbar_init(empty + s, 2 * TPB / 32); tma::mbar_init(sdfull + s, TPB / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid >= 2 * TPB) {                                    // ---- producer warp
+    int s = 0; uint32_t ph = 0;
+    const int ncopy = (has_add ? 3 : 2) * K + NE;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+      const int64_t g = it / ipg;
+      const int cb = (int)(it - g * ipg);
+      const int64_t coff = (int64_t)cb * S::CH * RING_P;
+      tma::mbar_wait(empty + s, ph ^ 1);
+      unsigned char* st = ring + (size_t)s * stage_bytes;
+      if (lane == 0) tma::mbar_expect_tx(full + s, stage_bytes);
+      __syncwarp();
+      for (int i = lane; i < ncopy; i += 32) {
+        if (i < K) tma::bulk_g2s(st + i * S::PIECE, h + (g * K + i) * ldh + coff, S::PIECE, full + s);
+        else if (i < 2 * K) tma::bulk_g2s(st + OFF_D + (i - K) * S::PIECE, dagg + (g * K + (i - K)) * ldd + coff, S::PIECE, full + s);
+        else if (i < 2 * K + NE) tma::bulk_g2s(st + OFF_Z + (i - 2 * K) * S::ZPIECE, z + (g * NE + (i - 2 * K)) * 2 * (int64_t)F + 2 * cb * S::CH, S::ZPIECE, full + s);
+        else tma::bulk_g2s(st + OFF_A + (i - 2 * K - NE) * S::PIECE, addend + (g * K + (i - 2 * K - NE)) * ldadd + coff, S::PIECE, full + s);
+      }
+      if (++s == NST) { s = 0; ph ^= 1; }
+    }
+    return;
+  }
+
+  const float w = 1.0f / (K - 1);
+  const float2 w2 = make_float2(w, w);
+  const bool grp_b = tid >= TPB;
+  const int t = grp_b ? tid - TPB : tid;                    // vector of the item this thread owns
+  const int cl = t / LPC;
+  int s = 0; uint32_t ph = 0;
+
+  if (!grp_b) {                                            // ---- group A: dh
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+      const int64_t g = it / ipg;
+      const int cb = (int)(it - g * ipg);
+      const int64_t off = (int64_t)cb * S::CH * RING_P + t * VEC;
+      const unsigned char* st = ring + (size_t)s * stage_bytes;
+      tma::mbar_wait(full + s, ph);
+      float2 dv[K][NP];
+#pragma unroll
+      for (int a = 0; a < K; ++a) unpack2<T>(*reinterpret_cast<const uint4*>(st + OFF_D + a * S::PIECE + t * 16), dv[a]);
+      {   // pixel sums of dagg per (channel, destination) for group B's dbeta: lane partial -> LPC-lane reduction -> shared memory
+        float sd[K];
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+          float2 s2 = dv[a][0];
+#pragma unroll
+          for (int q = 1; q < NP; ++q) s2 = fadd2(s2, dv[a][q]);
+          sd[a] = s2.x + s2.y;
+        }
+#pragma unroll
+        for (int o = LPC / 2; o > 0; o >>= 1) {
+#pragma unroll
+          for (int a = 0; a < K; ++a) sd[a] += __shfl_xor_sync(0xffffffffu, sd[a], o);
+        }
+        if (t % LPC == 0) {
+#pragma unroll
+          for (int a = 0; a < K; ++a) sdx[(s * S::CH + cl) * K + a] = sd[a];
+        }
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(sdfull + s);
+      }
+      const unsigned char* zs = st + OFF_Z + cl * 2 * (int)sizeof(T);
+#pragma unroll
+      for (int u = 0; u < K; ++u) {
+        float2 acc[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) acc[q] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+          if (a == u) continue;
+          const float gam = lds_pair<T>(zs + edge_id(K, u, a) * S::ZPIECE).x;
+          const float2 g2 = make_float2(gam, gam);
+#pragma unroll
+          for (int q = 0; q < NP; ++q) acc[q] = ffma2(g2, dv[a][q], acc[q]);
+        }
+        if (has_add) {
+          float2 av[NP];
+          unpack2<T>(*reinterpret_cast<const uint4*>(st + OFF_A + u * S::PIECE + t * 16), av);
+#pragma unroll
+          for (int q = 0; q < NP; ++q) acc[q] = ffma2(acc[q], w2, av[q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < NP; ++q) acc[q] = fmul2(acc[q], w2);
+        }
+        float o[VEC];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) { o[2 * q] = acc[q].x; o[2 * q + 1] = acc[q].y; }
+        Vec16<T>::store(dh + (g * K + u) * lddh + off, o);
+      }
+      __syncwarp();
+      if (lane == 0) tma::mbar_arrive(empty + s);
+      if (++s == NST) { s = 0; ph ^= 1; }
+    }
+    return;
+  }
+
+  // ---- group B: dz
+  const int l = t % LPC;
+  int my_e[NVP / LPC], my_a[NVP / LPC];
+#pragma unroll
+  for (int i = 0; i < NVP / LPC; ++i) {
+    const int e = scattered_id<NVP, LPC>(i, l);
+    const int u = e / (K - 1), jj = e % (K - 1);
+    my_e[i] = e < NE ? e : -1;
+    my_a[i] = jj < u ? jj : jj + 1;
+  }
+  for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+    const int64_t g = it / ipg;
+    const int cb = (int)(it - g * ipg);
+    const unsigned char* st = ring + (size_t)s * stage_bytes;
+    tma::mbar_wait(full + s, ph);
+    float2 dv[K][NP];
+#pragma unroll
+    for (int a = 0; a < K; ++a) unpack2<T>(*reinterpret_cast<const uint4*>(st + OFF_D + a * S::PIECE + t * 16), dv[a]);
+    float pg[NVP];
+#pragma unroll
+    for (int e = 0; e < NVP; ++e) pg[e] = 0.f;
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      float2 hv[NP];
+      unpack2<T>(*reinterpret_cast<const uint4*>(st + u * S::PIECE + t * 16), hv);
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+        if (a == u) continue;
+        float2 s2 = fmul2(hv[0], dv[a][0]);
+#pragma unroll
+        for (int q = 1; q < NP; ++q) s2 = ffma2(hv[q], dv[a][q], s2);
+        pg[edge_id(K, u, a)] = s2.x + s2.y;
+      }
+    }
+    reduce_scatter<NVP, LPC>(pg, l);
+    tma::mbar_wait(sdfull + s, ph);
+    const float* sdc = sdx + (s * S::CH + cl) * K;
+    const unsigned char* zs = st + OFF_Z + cl * 2 * (int)sizeof(T);
+    T* dzc = dz + g * NE * 2 * (int64_t)F + 2 * (cb * S::CH + cl);
+#pragma unroll
+    for (int i = 0; i < NVP / LPC; ++i) {
+      if (my_e[i] >= 0) {
+        float dg = pg[i] * w, db = sdc[my_a[i]] * w;
+        if (fuse_sig) {
+          const float2 gb = lds_pair<T>(zs + my_e[i] * S::ZPIECE);
+          dg *= gb.x * (1.f - gb.x); db *= gb.y * (1.f - gb.y);
+        }
+        st_pair<T>(dzc + my_e[i] * 2 * (int64_t)F, dg, db);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) tma::mbar_arrive(empty + s);
+    if (++s == NST) { s = 0; ph ^= 1; }
+  }
+}
+
+template <typename T, int K>
+static int launch_bwd_ring_k(const T* h, int64_t ldh, const T* dagg, int64_t ldd, const T* z, const T* addend, int64_t ldadd, T* dh, int64_t lddh,
+                             T* dz, int64_t G, int F, int fuse_sig, cudaStream_t st) {
+  constexpr int TPB = K <= 5 ? 256 : 128;
+  using S = RingBwd<T, K, TPB>;
+  constexpr int NST = (200 * 1024) / S::stage(3) >= 4 ? 4 : ((200 * 1024) / S::stage(3) >= 3 ? 3 : 2);
+  const size_t smem = S::HEAD + (size_t)NST * S::stage(addend ? 3 : 2);
+  auto kern = k_film_bwd_ring<T, K, TPB, NST>;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::HEAD + NST * S::stage(3));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_film_bwd_ring)");
+    done = true;
+  }
+  if (F % S::CH) return RGNN_E_UNSUPPORTED;
+  const int64_t items = G * (F / S::CH);
+  int64_t blocks = kNumSMs;
+  if (blocks > items) blocks = items;
+  if (blocks < 1) return 0;
+  kern<<<(unsigned)blocks, 2 * TPB + 32, smem, st>>>(h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, fuse_sig);
+  RGNN_LAUNCH_CHECK("k_film_bwd_ring");
+  return 0;
+}
+
+template <typename T>
+static int launch_bwd_ring(int K, const T* h, int64_t ldh, const T* dagg, int64_t ldd, const T* z, const T* addend, int64_t ldadd, T* dh,
+                           int64_t lddh, T* dz, int64_t G, int F, int fuse_sig, cudaStream_t st) {
+#define RGNN_CASE(KK) case KK: return launch_bwd_ring_k<T, KK>(h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, fuse_sig, st);
+  switch (K) { RGNN_CASE(2) RGNN_CASE(3) RGNN_CASE(4) RGNN_CASE(5) RGNN_CASE(6) RGNN_CASE(7) RGNN_CASE(8) default: return RGNN_E_UNSUPPORTED; }
+#undef RGNN_CASE
+}
+
 static int g_ring = -1;
 static bool ring_enabled() {
   if (g_ring < 0) { const char* e = getenv("RGNN_FILM_RING"); g_ring = (e && e[0] == '0') ? 0 : 1; }   // RGNN_FILM_RING=0: register-prefetch kernels
@@ -200,6 +434,21 @@ int film_fwd_ring(int dtype, int K, const void* x, int64_t ldx, const void* z, v
   auto X = static_cast<const __nv_bfloat16*>(x); auto Z = static_cast<const __nv_bfloat16*>(z);
   return z ? launch_fwd_ring<__nv_bfloat16, true>(K, X, ldx, Z, static_cast<__nv_bfloat16*>(out), ldout, static_cast<__nv_bfloat16*>(copy_to), G, (int)F, st)
            : launch_fwd_ring<__nv_bfloat16, false>(K, X, ldx, Z, static_cast<__nv_bfloat16*>(out), ldout, static_cast<__nv_bfloat16*>(copy_to), G, (int)F, st);
+}
+
+// Backward; returns RGNN_E_UNSUPPORTED when the shape / alignment is not covered (caller falls back to film_complete.cu).
+int film_bwd_ring(int dtype, int K, const void* h, int64_t ldh, const void* dagg, int64_t ldd, const void* z, const void* addend,
+                  int64_t ldadd, void* dh, int64_t lddh, void* dz, int64_t G, int64_t F, int64_t P, int fuse_sig, cudaStream_t st) {
+  const int es = dtype == RGNN_F32 ? 4 : 2;
+  if (!ring_enabled() || K < 2 || K > 8 || P != RING_P || !aligned16(h) || !aligned16(dagg) || !aligned16(z) || (addend && !aligned16(addend)) ||
+      (ldh * es) % 16 || (ldd * es) % 16 || (addend && (ldadd * es) % 16))
+    return RGNN_E_UNSUPPORTED;
+  if (dtype == RGNN_F32)
+    return launch_bwd_ring<float>(K, static_cast<const float*>(h), ldh, static_cast<const float*>(dagg), ldd, static_cast<const float*>(z),
+                                  static_cast<const float*>(addend), ldadd, static_cast<float*>(dh), lddh, static_cast<float*>(dz), G, (int)F, fuse_sig, st);
+  return launch_bwd_ring<__nv_bfloat16>(K, static_cast<const __nv_bfloat16*>(h), ldh, static_cast<const __nv_bfloat16*>(dagg), ldd,
+                                        static_cast<const __nv_bfloat16*>(z), static_cast<const __nv_bfloat16*>(addend), ldadd,
+                                        static_cast<__nv_bfloat16*>(dh), lddh, static_cast<__nv_bfloat16*>(dz), G, (int)F, fuse_sig, st);
 }
 
 }  // namespace rgnn
