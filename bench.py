@@ -74,7 +74,7 @@ def torch_gpu_step_fn(blk, g, a):
         m = z[:, 0::2, None, None] * h.index_select(0, src) + z[:, 1::2, None, None]
         agg = torch.zeros_like(h).index_add_(0, dst, m) * inv.to(h.dtype)[:, None, None, None]
         if conv is None:
-            return agg
+            return torch.cat((h, agg), 1)
         return Fn.conv2d(torch.cat((h, agg), 1), conv.weight.to(h.dtype), conv.bias.to(h.dtype))
 
     def fwd(h, pose):
@@ -185,7 +185,8 @@ def main():
     # synthetic inputs of the scripts' shape, seeded per rank; resident in HBM for `value`
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     h = torch.relu(torch.randn((N, F, 8, 8), generator=gen, device=dev, dtype=torch.float32)).to(dtype).requires_grad_()
-    dy = torch.randn((N, F, 8, 8), generator=gen, device=dev, dtype=torch.float32).to(dtype)
+    f_out = 2 * F if a.no_compress else F       # without the compress conv the block returns cat(h, agg) (models.py:182)
+    dy = torch.randn((N, f_out, 8, 8), generator=gen, device=dev, dtype=torch.float32).to(dtype)
     pose = torch.randn((E, 9), generator=gen, device=dev, dtype=torch.float32)
     pose[:, :3] *= 3.0
     g = R.robot_batch(G, K, device=dev)
@@ -240,11 +241,11 @@ def main():
     e2e = None
     if not a.no_e2e:
         hh = h.detach().cpu().pin_memory(); hdy = dy.cpu().pin_memory(); hpose = pose.cpu().pin_memory()
-        out_y = torch.empty((N, F, 8, 8), dtype=dtype).pin_memory(); out_dh = torch.empty((N, F, 8, 8), dtype=dtype).pin_memory()
+        out_y = torch.empty((N, f_out, 8, 8), dtype=dtype).pin_memory(); out_dh = torch.empty((N, F, 8, 8), dtype=dtype).pin_memory()
         h2d = hh.numel() * hh.element_size() + hdy.numel() * hdy.element_size() + hpose.numel() * 4
         d2h = 2 * out_y.numel() * out_y.element_size()
 
-        pipe = R.HostPipeline(blk, G, K, F, dtype=dtype, device=dev, chunks=a.e2e_chunks)
+        pipe = R.HostPipeline(blk, G, K, F, dtype=dtype, device=dev, chunks=a.e2e_chunks, out_feat=f_out)
         h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
 
         def e2e_step():
@@ -273,6 +274,8 @@ def main():
     torch_gpu = None
     if a.torch_baseline and rank == 0:
         fwd = torch_gpu_step_fn(blk, g, a)
+        torch.backends.cudnn.allow_tf32 = False          # our fp32 mode is true fp32 (1e-5 parity); keep the baseline's arithmetic the same
+        torch.backends.cuda.matmul.allow_tf32 = False
 
         def tstep():
             h.grad = None

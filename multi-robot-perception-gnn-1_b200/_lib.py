@@ -6,7 +6,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librobotgnn.so")
+LIB_PATH = os.environ.get("RGNN_LIB") or os.path.join(_HERE, "librobotgnn.so")      # RGNN_LIB: an experimental build (development)
 
 F32, BF16 = 0, 1
 POST_NONE, POST_MEAN, POST_SCALE = 0, 1, 2

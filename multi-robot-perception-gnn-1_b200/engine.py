@@ -18,7 +18,7 @@ from .graph import robot_batch
 
 
 class HostPipeline:
-    def __init__(self, block, num_graphs, robots, feat, dtype=torch.bfloat16, device="cuda", chunks=8, slots=3, hw=(8, 8)):
+    def __init__(self, block, num_graphs, robots, feat, dtype=torch.bfloat16, device="cuda", chunks=8, slots=3, hw=(8, 8), out_feat=None):
         if num_graphs % chunks:
             raise ValueError("num_graphs must be a multiple of chunks")
         self.block, self.G, self.K, self.F, self.dtype = block, num_graphs, robots, feat, dtype
@@ -27,15 +27,17 @@ class HostPipeline:
         self.gc = num_graphs // chunks
         self.nc, self.ec = self.gc * robots, self.gc * robots * (robots - 1)
         self.hw = hw
+        out_feat = feat if out_feat is None else out_feat        # 2 * feat for a block without the compress conv (cat output)
         self.graph = robot_batch(self.gc, robots, device=self.dev)
         self.graph.index()
         mk = lambda *s, dt=dtype: torch.empty(s, dtype=dt, device=self.dev)
         self.h_d = [mk(self.nc, feat, *hw) for _ in range(slots)]
-        self.dy_d = [mk(self.nc, feat, *hw) for _ in range(slots)]
+        self.dy_d = [mk(self.nc, out_feat, *hw) for _ in range(slots)]
         self.pose_d = [mk(self.ec, 9, dt=torch.float32) for _ in range(slots)]
         self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
-        self.h2d_bytes = num_graphs * robots * feat * hw[0] * hw[1] * 2 * self.h_d[0].element_size() + num_graphs * robots * (robots - 1) * 36
-        self.d2h_bytes = num_graphs * robots * feat * hw[0] * hw[1] * 2 * self.h_d[0].element_size()
+        es, px = self.h_d[0].element_size(), hw[0] * hw[1]
+        self.h2d_bytes = num_graphs * robots * (feat + out_feat) * px * es + num_graphs * robots * (robots - 1) * 36
+        self.d2h_bytes = num_graphs * robots * (feat + out_feat) * px * es
 
     def step(self, h, pose, dy, y_out, dh_out):
         """h, dy, y_out, dh_out: pinned host [N, F, 8, 8]; pose: pinned host [E, 9] fp32.  Parameter .grad holds the sum over
