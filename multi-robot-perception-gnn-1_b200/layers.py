@@ -155,9 +155,9 @@ class GraphConv(nn.Module):
         if self._norm == 'both':
             ns, ds = ix.rsqrt_out, ix.rsqrt_in
         elif self._norm == 'left':
-            ns, ds = _reciprocal_clamped(ix.out_deg), None
+            ns, ds = _inv_out_deg(ix), None
         elif self._norm == 'right':
-            ns, ds = None, _reciprocal_clamped(ix.in_deg)
+            ns, ds = None, _inv_in_deg(ix)
         else:
             ns, ds = None, None
         bias_in_gemm = None
@@ -179,6 +179,20 @@ class GraphConv(nn.Module):
 
 def _reciprocal_clamped(deg):
     return 1.0 / deg.clamp(min=1).to(torch.float32)   # [N] index-side vector, not feature math
+
+
+def _inv_out_deg(ix):
+    """1 / max(out_deg, 1), cached on the graph index (the aggregation recognises the index's own degree norms)."""
+    if getattr(ix, "inv_out_deg", None) is None:
+        ix.inv_out_deg = _reciprocal_clamped(ix.out_deg)
+    return ix.inv_out_deg
+
+
+def _inv_in_deg(ix):
+    """1 / max(in_deg, 1): the builder's 1/in_deg vector when no node is isolated (it stores 0 there), else computed."""
+    if getattr(ix, "inv_in_deg_clamped", None) is None:
+        ix.inv_in_deg_clamped = ix.inv_in_deg if ix.complete_k else _reciprocal_clamped(ix.in_deg)
+    return ix.inv_in_deg_clamped
 
 
 class GCN2Conv(nn.Module):
