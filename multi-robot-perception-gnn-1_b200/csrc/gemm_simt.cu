@@ -2,6 +2,7 @@
 // (fp32 1e-5 cannot be met by a single-pass bf16/tf32 MMA on the K = 2F contraction) and the
 // general-shape fallback of the tcgen05 path in gemm_tc.cu.
 // Tile 64x64x16, 256 threads, 4x4 register micro-tile, operands converted to fp32 in shared memory.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace rgnn {
@@ -15,6 +16,7 @@ struct GemmParams {
   int epi; const float* bias; const void* aux; float alpha, beta;
   int c_dtype;
   int64_t tiles_m, tiles_n;
+  int fold;            // k_sgemm_v only: 2 = one 128-column tile spans two batch items of N = 64 columns (per-node conv products)
 };
 
 constexpr int BM = 64, BN = 64, BK = 16;
@@ -124,6 +126,222 @@ __global__ void __launch_bounds__(256) k_gemm_simt(GemmParams p) {
       }
     }
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Vectorised fp32 kernel for the large, aligned all-fp32 products of the parity mode (same arithmetic as k_gemm_simt: one
+// fmaf chain per output in ascending k and the same split-K chunking, so results are bit-identical).  128 x BN2 x 16 tiles,
+// 8 x (BN2/16) register micro-tile, packed FFMA2; the A operand is kept duplicated in shared memory so that (a, a) pairs load
+// directly; 16-byte global loads through per-thread pointers that advance by a constant per tile; the next tile's loads are
+// in flight while the current one is multiplied (register staging, double-buffered shared memory, one barrier per tile).
+constexpr int VM = 128, VK = 16;
+constexpr int VA_LD = VM + 2;                  // float2 per k row (+2: rows stay 16-byte aligned, k-fast stores spread over banks)
+
+template <bool A_KFAST, bool B_NFAST, int BN2>
+__global__ void __launch_bounds__(256, 2) k_sgemm_v(GemmParams p) {
+  constexpr int TNV = BN2 / 64;                // float4 column chunks per thread (chunk c = columns c*64 + tx*4 .. +3)
+  constexpr int VB_LD = BN2 + 4;
+  constexpr int NBV = BN2 * VK / 4 / 256;      // float4 of B per thread per tile (2 or 1)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* As = reinterpret_cast<float2*>(smem_raw);                                   // [2][VK][VA_LD]
+  float* Bs = reinterpret_cast<float*>(smem_raw + 2 * VK * VA_LD * sizeof(float2));    // [2][VK][VB_LD]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  int64_t bid = blockIdx.x;
+  const int64_t tn = bid % p.tiles_n; bid /= p.tiles_n;
+  const int64_t tm = bid % p.tiles_m; bid /= p.tiles_m;
+  const int64_t zs = bid;
+  const bool fold = p.fold == 2;
+  const int64_t z = p.split > 1 ? 0 : zs * p.fold;
+  int64_t r0 = 0, r1 = p.red, kbeg = 0, kend = p.K;
+  if (p.split > 1) {
+    if (p.red > 1) {
+      const int64_t chunk = (p.red + p.split - 1) / p.split;
+      r0 = zs * chunk; r1 = min(p.red, r0 + chunk);
+    } else {
+      const int64_t chunk = ((p.K + p.split - 1) / p.split + BK - 1) / BK * BK;
+      kbeg = min(p.K, zs * chunk); kend = min(p.K, kbeg + chunk);
+    }
+  }
+  const int64_t m0 = tm * VM, n0 = tn * BN2;
+  const float* __restrict__ A = static_cast<const float*>(p.A) + z * p.sAz;
+  const float* __restrict__ B = static_cast<const float*>(p.B) + z * p.sBz;
+  const int tpr = (int)((kend - kbeg + VK - 1) / VK);            // k tiles per reduction item
+  const int64_t ntiles = (r1 > r0 && kend > kbeg) ? (r1 - r0) * tpr : 0;
+
+  // ---- per-thread load slots: element offsets inside the operand at (r = 0, k = kbeg), validity along the non-k direction
+  int a_k[2], a_m[2], b_k[NBV], b_n[NBV];
+  int64_t a_off[2], b_off[NBV];
+  bool a_ok[2], b_ok[NBV];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int q = tid + it * 256;
+    if (A_KFAST) { a_k[it] = (q & 3) * 4; a_m[it] = q >> 2; } else { a_m[it] = (q & 31) * 4; a_k[it] = q >> 5; }
+    a_ok[it] = m0 + a_m[it] < p.M;           // M % 4 == 0 when vectors run along m
+    a_off[it] = (m0 + a_m[it]) * p.sAm + (kbeg + a_k[it]) * p.sAk;
+  }
+#pragma unroll
+  for (int it = 0; it < NBV; ++it) {
+    const int q = tid + it * 256;
+    if (B_NFAST) { b_n[it] = (q % (BN2 / 4)) * 4; b_k[it] = q / (BN2 / 4); } else { b_k[it] = (q & 3) * 4; b_n[it] = q >> 2; }
+    int64_t gn = n0 + b_n[it], zo = 0;
+    if (fold) { zo = b_n[it] >> 6; gn = b_n[it] & 63; }
+    b_ok[it] = gn < p.N && (!fold || z + zo < p.batch);
+    b_off[it] = zo * p.sBz + gn * p.sBn + (kbeg + b_k[it]) * p.sBk;
+  }
+
+  float2 acc[8][2 * TNV];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 2 * TNV; ++j) acc[i][j] = make_float2(0.f, 0.f);
+
+  float4 ra[2], rb[NBV];
+  int64_t r = r0; int kt = 0;                  // the tile the NEXT gload fetches: reduction item r, k tile kt
+  auto gload = [&]() {
+    const int64_t k0 = kbeg + (int64_t)kt * VK;
+    const float* Ar = A + r * p.sAr + (int64_t)kt * VK * p.sAk;
+    const float* Br = B + r * p.sBr + (int64_t)kt * VK * p.sBk;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const bool ok = a_ok[it] && k0 + a_k[it] < kend;          // K % 4 == 0 when vectors run along k
+      ra[it] = ok ? __ldg(reinterpret_cast<const float4*>(Ar + a_off[it])) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int it = 0; it < NBV; ++it) {
+      const bool ok = b_ok[it] && k0 + b_k[it] < kend;
+      rb[it] = ok ? __ldg(reinterpret_cast<const float4*>(Br + b_off[it])) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (++kt == tpr) { kt = 0; ++r; }
+  };
+  auto sstore = [&](int buf) {
+    float2* as = As + buf * VK * VA_LD;
+    float* bs = Bs + buf * VK * VB_LD;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      if (A_KFAST) {
+        float2* d = as + a_k[it] * VA_LD + a_m[it];
+        d[0] = make_float2(ra[it].x, ra[it].x); d[VA_LD] = make_float2(ra[it].y, ra[it].y);
+        d[2 * VA_LD] = make_float2(ra[it].z, ra[it].z); d[3 * VA_LD] = make_float2(ra[it].w, ra[it].w);
+      } else {
+        float4* d = reinterpret_cast<float4*>(as + a_k[it] * VA_LD + a_m[it]);
+        d[0] = make_float4(ra[it].x, ra[it].x, ra[it].y, ra[it].y);
+        d[1] = make_float4(ra[it].z, ra[it].z, ra[it].w, ra[it].w);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NBV; ++it) {
+      if (B_NFAST) {
+        *reinterpret_cast<float4*>(bs + b_k[it] * VB_LD + b_n[it]) = rb[it];
+      } else {
+        float* d = bs + b_k[it] * VB_LD + b_n[it];
+        d[0] = rb[it].x; d[VB_LD] = rb[it].y; d[2 * VB_LD] = rb[it].z; d[3 * VB_LD] = rb[it].w;
+      }
+    }
+  };
+
+  if (ntiles > 0) { gload(); sstore(0); }
+  __syncthreads();
+  for (int64_t t = 0; t < ntiles; ++t) {
+    const int buf = (int)(t & 1);
+    if (t + 1 < ntiles) gload();
+    const float2* as = As + buf * VK * VA_LD + ty * 8;
+    const float* bs = Bs + buf * VK * VB_LD + tx * 4;
+#pragma unroll
+    for (int kk = 0; kk < VK; ++kk) {
+      float2 b2[2 * TNV];
+#pragma unroll
+      for (int c = 0; c < TNV; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(bs + kk * VB_LD + c * 64);
+        b2[2 * c] = make_float2(v.x, v.y); b2[2 * c + 1] = make_float2(v.z, v.w);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(as + kk * VA_LD + 2 * i);
+        const float2 a0 = make_float2(v.x, v.y), a1 = make_float2(v.z, v.w);
+#pragma unroll
+        for (int j = 0; j < 2 * TNV; ++j) {
+          acc[2 * i][j] = ffma2(a0, b2[j], acc[2 * i][j]);
+          acc[2 * i + 1][j] = ffma2(a1, b2[j], acc[2 * i + 1][j]);
+        }
+      }
+    }
+    if (t + 1 < ntiles) sstore(buf ^ 1);
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + ty * 8 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int c = 0; c < TNV; ++c) {
+      const int col = c * 64 + tx * 4;
+      int64_t n = n0 + col, zz = z;
+      if (fold) { zz = z + c; n = tx * 4; }
+      if (fold && zz >= p.batch) continue;
+      const float v[4] = {acc[i][2 * c].x, acc[i][2 * c].y, acc[i][2 * c + 1].x, acc[i][2 * c + 1].y};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (n + j >= p.N) continue;
+        if (p.split > 1) {
+          p.partial[(zs * p.M + m) * p.N + n + j] = v[j];
+        } else {
+          const int64_t idx = zz * p.sCz + m * p.sCm + (n + j) * p.sCn;
+          store_c(p.c_dtype, p.C, idx, epilogue(p.epi, v[j], m, n + j, p.bias, load_aux(p.c_dtype, p.aux, idx), p.alpha, p.beta));
+        }
+      }
+    }
+  }
+}
+
+static bool al16p(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
+// true when k_sgemm_v can take the product: all-fp32 operands, unit stride along one direction of A and of B, every vector
+// 16-byte aligned and entirely inside or outside the operand
+static bool sgemm_v_ok(const GemmParams& p, int a_dtype, int b_dtype) {
+  if (a_dtype != RGNN_F32 || b_dtype != RGNN_F32) return false;
+  if (p.M < 64 || p.N < 64) return false;
+  if ((double)p.M * p.N * p.K * (p.red > 1 ? p.red : 1) * p.batch < 2e7) return false;
+  const bool a_k = p.sAk == 1, a_m = p.sAm == 1, b_n = p.sBn == 1, b_k = p.sBk == 1;
+  if (!(a_k || a_m) || !(b_n || b_k)) return false;
+  if (!al16p(p.A) || !al16p(p.B)) return false;
+  auto m4 = [](int64_t v) { return (v & 3) == 0; };
+  if (!m4(p.sAz) || !m4(p.sAr) || !m4(p.sBz) || !m4(p.sBr)) return false;
+  if (a_k) { if (!m4(p.sAm) || !m4(p.K)) return false; } else { if (!m4(p.sAk) || !m4(p.M)) return false; }
+  if (b_n) { if (!m4(p.sBk) || !m4(p.N)) return false; } else { if (!m4(p.sBn) || !m4(p.K)) return false; }
+  return true;
+}
+
+static int launch_sgemm_v(GemmParams& p, cudaStream_t st) {
+  const bool a_k = p.sAk == 1, b_n = p.sBn == 1;
+  if (p.split == 1 && p.batch > 1 && p.N == 64 && p.sAz == 0 && p.red <= 1 && b_n) p.fold = 2;
+  const bool wide = p.fold == 2 || p.N > 64;
+  const int bn2 = wide ? 128 : 64;
+  p.tiles_m = (p.M + VM - 1) / VM;
+  p.tiles_n = p.fold == 2 ? 1 : (p.N + bn2 - 1) / bn2;
+  const int64_t zcount = p.split > 1 ? p.split : (p.batch + p.fold - 1) / p.fold;
+  const int64_t blocks = p.tiles_m * p.tiles_n * zcount;
+  if (blocks >= (1ll << 31)) { set_error("rgnn_gemm: grid too large"); return RGNN_E_RANGE; }
+  const size_t smem = 2 * VK * VA_LD * sizeof(float2) + 2 * VK * (bn2 + 4) * sizeof(float);
+#define RGNN_SG(AK, BNF, W)                                                                                            \
+  {                                                                                                                    \
+    static bool done = false;                                                                                          \
+    if (!done) {                                                                                                       \
+      cudaError_t e = cudaFuncSetAttribute(k_sgemm_v<AK, BNF, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_sgemm_v)");                                    \
+      done = true;                                                                                                     \
+    }                                                                                                                  \
+    k_sgemm_v<AK, BNF, W><<<(unsigned)blocks, 256, smem, st>>>(p);                                                     \
+  }
+  if (wide) {
+    if (a_k && b_n) RGNN_SG(true, true, 128) else if (a_k) RGNN_SG(true, false, 128) else if (b_n) RGNN_SG(false, true, 128) else RGNN_SG(false, false, 128)
+  } else {
+    if (a_k && b_n) RGNN_SG(true, true, 64) else if (a_k) RGNN_SG(true, false, 64) else if (b_n) RGNN_SG(false, true, 64) else RGNN_SG(false, false, 64)
+  }
+#undef RGNN_SG
+  RGNN_LAUNCH_CHECK("k_sgemm_v");
+  return 0;
 }
 
 __global__ void __launch_bounds__(256) k_splitk_reduce(GemmParams p) {
@@ -253,15 +471,23 @@ extern "C" int rgnn_gemm(int a_dtype, const void* A, int64_t sAz, int64_t sAr, i
   if (red <= 1 && p.split > (K + BK - 1) / BK) p.split = (K + BK - 1) / BK;
   if (p.split < 1) p.split = 1;
   p.partial = partial; p.epi = epi; p.bias = bias; p.aux = aux; p.alpha = alpha; p.beta = beta; p.c_dtype = c_dtype;
+  p.fold = 1;
+  cudaStream_t st = as_stream(stream);
+  static int use_v = -1;
+  if (use_v < 0) { const char* e = getenv("RGNN_SGEMM_V"); use_v = (e && e[0] == '0') ? 0 : 1; }   // RGNN_SGEMM_V=0: general kernel only
+  if (use_v && sgemm_v_ok(p, a_dtype, b_dtype)) {
+    const int rc = launch_sgemm_v(p, st);
+    if (rc) return rc;
+  } else {
   p.tiles_m = (M + BM - 1) / BM; p.tiles_n = (N + BN - 1) / BN;
   const int64_t blocks = p.tiles_m * p.tiles_n * (p.split > 1 ? p.split : batch);
   RGNN_REQUIRE(blocks < (1ll << 31), RGNN_E_RANGE, "rgnn_gemm: grid too large");
-  cudaStream_t st = as_stream(stream);
   if (a_dtype == RGNN_F32 && b_dtype == RGNN_F32) k_gemm_simt<float, float><<<(unsigned)blocks, 256, 0, st>>>(p);
   else if (a_dtype == RGNN_F32) k_gemm_simt<float, __nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(p);
   else if (b_dtype == RGNN_F32) k_gemm_simt<__nv_bfloat16, float><<<(unsigned)blocks, 256, 0, st>>>(p);
   else k_gemm_simt<__nv_bfloat16, __nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(p);
   RGNN_LAUNCH_CHECK("k_gemm_simt");
+  }
   if (p.split > 1) {
     int64_t rb = (M * N + 255) / 256;
     if (rb > 16 * kNumSMs) rb = 16 * kNumSMs;

@@ -206,6 +206,15 @@ def _splits(tiles, work_items):
     return max(1, min(s, work_items))
 
 
+def _splits_mn(m, n, work_items):
+    """Split count for an [m, n] CUDA-core product: the large fp32 products run 128-wide tiles, two CTAs per SM (k_sgemm_v), so
+    aim for ~4 CTAs per SM; small ones keep the 64 x 64 rule."""
+    if m >= 64 and n >= 64:
+        tiles = ((m + 127) // 128) * ((n + 127) // 128 if n > 64 else 1)
+        return max(1, min((4 * 148 + tiles - 1) // tiles, work_items))
+    return _splits(((m + 63) // 64) * ((n + 63) // 64), work_items)
+
+
 def _edge_mlp_forward(pose, w1, b1, w2, b2, out_dtype):
     _lib.require_cuda(pose, w1, b1, w2, b2)
     pose = pose.float().contiguous()          # edge.float(), models.py:153
@@ -269,7 +278,7 @@ def edge_mlp_param_grads(pose, w2, a1, dzp):
                   "rgnn_tc_gemm_nn")
     else:
         _gemm(dzp, (0, 0, f2, 1), w2, (0, 0, hid, 1), da1, (0, hid, 1), e, hid, f2, epi=_lib.EPI_RELU_MASK, aux=a1, tag="mlp2_dx")
-        split = _splits(((f2 + 63) // 64) * ((hid + 63) // 64), max(1, (e + 63) // 64))
+        split = _splits_mn(f2, hid, max(1, (e + 63) // 64))
         partial = torch.empty((split, f2, hid), **f32) if split > 1 else None
         _gemm(dzp, (0, 0, 1, f2), a1, (0, 0, hid, 1), dw2, (0, hid, 1), f2, hid, e, split=split, partial=partial, tag="mlp2_dw")
     db2 = torch.empty((f2,), **f32)
@@ -348,7 +357,7 @@ def _compress_backward(dy, h, gh, wc2, tc, need_dh, need_dgh, need_dw, need_db):
             _gemm(wc2[:, f:], (0, 0, 1, 2 * f), dy, sb, dgh, sc, f, nn, fo, batch=bt, tag="compress_dx")
         if need_dw and dwc is None:
             dwc = torch.empty((fo, 2 * f), **f32)
-            split = _splits(((fo + 63) // 64) * ((f + 63) // 64), n)
+            split = _splits_mn(fo, f, n)
             partial = torch.empty((split, fo, f), **f32) if split > 1 else None
             for half, src in ((0, h), (1, gh)):
                 # dWc[o, k2] = sum_v sum_p dy[v,o,p] * src[v,k2,p]: K = P per node, reduced over the N nodes
@@ -539,7 +548,7 @@ class LinearFn(torch.autograd.Function):
                                                 stream()), "rgnn_tc_gemm_nn")
             elif ctx.needs_input_grad[1]:
                 dw = torch.empty((din, dout), **f32)
-                split = _splits(((din + 63) // 64) * ((dout + 63) // 64), max(1, (rows + 63) // 64))
+                split = _splits_mn(din, dout, max(1, (rows + 63) // 64))
                 partial = torch.empty((split, din, dout), **f32) if split > 1 else None
                 _gemm(x, (0, 0, 1, din), dy, (0, 0, dout, 1), dw, (0, dout, 1), din, dout, rows, split=split, partial=partial,
                       alpha=ctx.alpha)
