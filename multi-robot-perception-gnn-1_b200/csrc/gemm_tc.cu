@@ -46,6 +46,7 @@ struct TcParams {
   int64_t ld0, ld1;     // NCHW: elements per robot in out0/out1; ROW/PARTIAL: ld0 = row stride
   const float* bias; const void* aux;
   float alpha, beta;    // ROW epilogue: v = alpha * acc [+ beta * aux[m,n] with RGNN_EPI_ADD_AUX] (GCN2Conv identity mapping)
+  int n_fast;           // tile order: 1 = the N-tiles of one M-tile group are consecutive work items (A is the big operand: linear layers)
   float* rowsum;        // WGRAD: if non-null, fp32 [splits, M] partial row sums of A (the bias gradient of the 1x1 conv) are written here
 };
 
@@ -53,7 +54,7 @@ struct TcParams {
 // and TMA-multicasts it into both CTAs' shared memory, cutting L2->SM operand traffic per CTA from 48 KB to 32 KB per
 // k-block.  Every stage's empty barrier then collects the tcgen05.commit of BOTH CTAs (multicast commit) before either
 // producer may overwrite the stage.  The MMAs themselves stay cta_group::1 (each CTA owns its accumulator).
-template <int BN, int CL>
+template <int BN, int CL, bool AUX>      // AUX: ROW epilogue with a second operand (identity mapping / ReLU mask)
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
           const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmO0,
@@ -110,7 +111,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int w = w_first; w < work_total; w += w_step) {
-        const int tm = (w % tiles_mc) * CL + crank, tn = (w / tiles_mc) % p.tiles_n, sp = w / (tiles_mc * p.tiles_n);
+        const int tm = (p.n_fast ? (w / p.tiles_n) % tiles_mc : w % tiles_mc) * CL + crank, tn = p.n_fast ? w % p.tiles_n : (w / tiles_mc) % p.tiles_n,
+                  sp = w / (tiles_mc * p.tiles_n);
         const int kb0 = sp * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -216,7 +218,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     int as = 0; uint32_t aphase = 0;
     int rstage = 0; uint32_t rphase = 0;        // rowsum mode: this warp's own walk over the operand ring
     for (int w = w_first; w < work_total; w += w_step) {
-      const int tm = (w % tiles_mc) * CL + crank, tn = (w / tiles_mc) % p.tiles_n, sp = w / (tiles_mc * p.tiles_n);
+      const int tm = (p.n_fast ? (w / p.tiles_n) % tiles_mc : w % tiles_mc) * CL + crank, tn = p.n_fast ? w % p.tiles_n : (w / tiles_mc) % p.tiles_n,
+                sp = w / (tiles_mc * p.tiles_n);
       const int kb0 = sp * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
       const bool empty = kb1 <= kb0;
       if (p.rowsum && eh == 0) {
@@ -245,6 +248,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int64_t mr = (int64_t)tm * BM + row;
         if (mine && mr < p.M) p.rowsum[(int64_t)sp * p.M + mr] = rs;
       }
+      // ROW epilogues that read a second operand (identity mapping / ReLU mask): each aux slab [128 rows x 128 B] is fetched
+      // COALESCED (8 lanes per 128-byte row, 4 rows per warp load) into registers one slab ahead - the tile's first slab while
+      // this warp would only wait for the accumulator, slab j+1 during the arithmetic of slab j - and parked in the warpgroup's
+      // staging buffer at the swizzled positions the results will overwrite; a warp's 32 rows belong to its own 32 threads, so
+      // __syncwarp is the only synchronisation.  (One 16-byte load per thread-row instead: 32 sectors per request, twice the
+      // L2 traffic, and the TN GEMM ran at half speed.)
+      constexpr bool use_aux = AUX;
+      uint4 ua[8];
+      auto aux_fetch = [&](int j) {
+        const int64_t c0 = (int64_t)tn * BN + j * 64 + (lane & 7) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t mr = (int64_t)tm * BM + ew * 32 + i * 4 + (lane >> 3);
+          ua[i] = mr < p.M ? __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.aux) + mr * p.ld0 + c0)) : make_uint4(0, 0, 0, 0);
+        }
+      };
+      if (use_aux && !empty) aux_fetch(eh * (BN / 128));
       mbar_wait(bar_tfull + 8 * as, aphase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(ew * 32) << 16);
@@ -267,19 +287,38 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int j = j_lo; j < j_hi; ++j) {
           const int node = tn * (BN / 64) + j;
           const uint32_t stg = out_stage + (nchw ? (j & 1) : eh) * OUT_STAGE_BYTES;
-          if (ew == 0 && lane == 0) {             // the buffer's previous store has finished reading it
-            if (nchw) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          }
-          epi_bar_sync(bar_id);
-          uint32_t r0[32], r1[32];
-          tmem_ld32_issue(tacc + (2 * j) * 32, r0);
-          tmem_ld32_issue(tacc + (2 * j + 1) * 32, r1);
-          tmem_ld_wait();
           const int64_t n0 = (int64_t)tn * BN + j * 64;
+          if (use_aux) {
+            if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            epi_bar_sync(bar_id);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rl = ew * 32 + i * 4 + (lane >> 3);
+              const uint32_t addr = stg + rl * 128 + (((lane & 7) ^ (rl & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ua[i].x), "r"(ua[i].y), "r"(ua[i].z), "r"(ua[i].w) : "memory");
+            }
+            __syncwarp();
+            if (j + 1 < j_hi) aux_fetch(j + 1);
+          }
+          uint32_t r0[32], r1[AUX ? 1 : 32];
+          uint32_t wq[8][4];                      // the slab row of this thread, packed; staged after the buffer is known to be free
+          if constexpr (!AUX) {
+            tmem_ld32_issue(tacc + (2 * j) * 32, r0);
+            tmem_ld32_issue(tacc + (2 * j + 1) * 32, r1);
+            tmem_ld_wait();
+          }
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const uint32_t* r = q < 4 ? r0 : r1;
+            if constexpr (AUX) {
+              if ((q & 3) == 0) {                 // 32 accumulator columns at a time (the registers are needed for the aux prefetch)
+                tmem_ld32_issue(tacc + (2 * j + (q >> 2)) * 32, r0);
+                tmem_ld_wait();
+              }
+            }
+            const uint32_t* r = (AUX || q < 4) ? r0 : r1;
+            uint4 u = make_uint4(0, 0, 0, 0);     // this thread's aux chunk q (from the staged slab)
+            if (use_aux)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(stg + row * 128 + ((q ^ (row & 7)) << 4)));
             const int b = (q & 3) * 8;
             float v[8];
 #pragma unroll
@@ -290,7 +329,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 for (int i = 0; i < 8; ++i) v[i] *= p.alpha;
               }
               if ((p.epi_flags & RGNN_EPI_ADD_AUX) && m < p.M) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.aux) + m * p.ld0 + n0 + q * 8));
                 const uint32_t ws[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -312,7 +350,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
               }
               if ((p.epi_flags & RGNN_EPI_RELU_MASK) && m < p.M) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.aux) + m * p.ld0 + n0 + q * 8));
                 const uint32_t ws[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {     // bf16 > 0  <=>  sign clear and magnitude non-zero
@@ -321,9 +358,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
               }
             }
-            const uint32_t w0 = pack_bf16(v[0], v[1]), w1 = pack_bf16(v[2], v[3]), w2 = pack_bf16(v[4], v[5]), w3 = pack_bf16(v[6], v[7]);
+            wq[q][0] = pack_bf16(v[0], v[1]); wq[q][1] = pack_bf16(v[2], v[3]); wq[q][2] = pack_bf16(v[4], v[5]); wq[q][3] = pack_bf16(v[6], v[7]);
+          }
+          // only now wait for the staging buffer: the previous store's shared-memory read overlapped the TMEM load and the arithmetic
+          if (!use_aux) {                         // (with an aux operand the buffer was claimed before it was parked there)
+            if (ew == 0 && lane == 0) {
+              if (nchw) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            epi_bar_sync(bar_id);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
             const uint32_t addr = stg + row * 128 + ((q ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(wq[q][0]), "r"(wq[q][1]), "r"(wq[q][2]), "r"(wq[q][3]) : "memory");
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           epi_bar_sync(bar_id);
@@ -403,13 +451,13 @@ __global__ void __launch_bounds__(256) k_cast_weights(const float* __restrict__ 
 // ---------------------------------------------------------------------------------------------------------
 static int g_cluster = -1;    // RGNN_TC_CLUSTER=1 disables the 2-CTA multicast clusters (debug / A-B comparison)
 
-template <int BN, int CL>
+template <int BN, int CL, bool AUX>
 static int launch_cl(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const TcParams& p, cudaStream_t st,
                      const CUtensorMap* o0, const CUtensorMap* o1) {
   constexpr size_t smem = 1024 + (size_t)NSTAGE * (BM * BK * 2 + BN * BK * 2) + NOUT_STAGE * 128 * 128 + 256;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, CL, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_gemm_tc)");
     attr_done = true;
   }
@@ -426,7 +474,7 @@ static int launch_cl(const CUtensorMap& a, const CUtensorMap& b0, const CUtensor
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   count_launch();
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, CL>, a, b0, b1, o0 ? *o0 : a, o1 ? *o1 : (o0 ? *o0 : a), p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, CL, AUX>, a, b0, b1, o0 ? *o0 : a, o1 ? *o1 : (o0 ? *o0 : a), p);
   if (e != cudaSuccess) return cuda_fail(e, "k_gemm_tc launch");
   return 0;
 }
@@ -439,8 +487,9 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap
     g_cluster = (e && e[0] == '1') ? 1 : 2;
   }
   // clusters only pay when there are at least two M-tiles to pair up
-  if (g_cluster == 2 && p.tiles_m >= 2) return launch_cl<BN, 2>(a, b0, b1, p, st, o0, o1);
-  return launch_cl<BN, 1>(a, b0, b1, p, st, o0, o1);
+  const bool aux = p.epi_mode == EPI_ROW && (p.epi_flags & (RGNN_EPI_ADD_AUX | RGNN_EPI_RELU_MASK)) != 0;
+  if (g_cluster == 2 && p.tiles_m >= 2) return aux ? launch_cl<BN, 2, true>(a, b0, b1, p, st, o0, o1) : launch_cl<BN, 2, false>(a, b0, b1, p, st, o0, o1);
+  return aux ? launch_cl<BN, 1, true>(a, b0, b1, p, st, o0, o1) : launch_cl<BN, 1, false>(a, b0, b1, p, st, o0, o1);
 }
 
 }  // namespace tc
@@ -596,6 +645,7 @@ extern "C" int rgnn_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_
   }
   TcParams p = {};
   p.load_mode = LOAD_TN; p.epi_mode = EPI_ROW; p.epi_flags = epi;
+  p.n_fast = 1;          // activations (A, rows = edges / pixels) are the big operand: its N-tile siblings run back to back and hit L2
   p.tiles_m = (int)((M + 127) / 128); p.tiles_n = (int)(N / BN); p.splits = 1;
   p.kblocks = (int)(K / 64); p.kb_per_split = p.kblocks;
   p.M = M; p.N = N; p.out0 = C; p.ld0 = ldc; p.bias = bias; p.aux = aux; p.alpha = alpha; p.beta = beta;
