@@ -217,6 +217,13 @@ int rgnn_sigmoid_grad(int dtype, const void* z, const void* dz, void* dzpre, int
 /* out = a*x + b*y elementwise over n values (GCN2Conv initial residual (1-alpha)*agg + alpha*feat_0) */
 int rgnn_axpby(int dtype, float a, const void* x, float b, const void* y, void* out, int64_t n, void* stream);
 
+/* GCN2Conv on complete K-robot graphs (D^-1/2 A D^-1/2 of a complete graph is the mean over the other K-1
+ * robots): out[v] = sa * mean_{u != v, same graph} x[u] + sb * addend[v] in one streaming pass (addend may be NULL).
+ * Rows of `row` elements per node (node strides ldx / ldadd / ldout); node b*K+i is robot i of graph b (dataloader.py:88-95).
+ * Returns RGNN_E_UNSUPPORTED when robots > 8 or the row is not a multiple of 256 16-byte vectors (caller: rgnn_aggregate + rgnn_axpby). */
+int rgnn_complete_mean_mix(int dtype, const void* x, int64_t ldx, const void* addend, int64_t ldadd, void* out, int64_t ldout,
+                           int64_t num_graphs, int64_t robots, int64_t row, float sa, float sb, void* stream);
+
 /* out[r,c] = x[r,c] + bias[c]  (GraphConv bias after a plain aggregation) */
 int rgnn_bias_add(int dtype, const void* x, const float* bias, void* out, int64_t rows, int64_t cols, void* stream);
 

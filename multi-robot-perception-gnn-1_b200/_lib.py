@@ -39,6 +39,7 @@ SIGNATURES = {
     "rgnn_tc_gemm_nn": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _i64, _vp],
     "rgnn_sigmoid_grad": [_i32, _vp, _vp, _vp, _i64, _vp],
     "rgnn_axpby": [_i32, _f32, _vp, _f32, _vp, _vp, _i64, _vp],
+    "rgnn_complete_mean_mix": [_i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f32, _f32, _vp],
     "rgnn_bias_add": [_i32, _vp, _vp, _vp, _i64, _i64, _vp],
     "rgnn_reduce_sum": [_i32, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp],
 }

@@ -176,6 +176,131 @@ static int launch_fwd_ring(int K, const T* x, int64_t ldx, const T* z, T* out, i
 #undef RGNN_CASE
 }
 
+template <typename T> __device__ __forceinline__ void unpack2(const uint4& v, float2 (&o)[Vec16<T>::N / 2]);
+template <> __device__ __forceinline__ void unpack2<float>(const uint4& v, float2 (&o)[2]) {
+  o[0] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y)); o[1] = make_float2(__uint_as_float(v.z), __uint_as_float(v.w));
+}
+template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(const uint4& v, float2 (&o)[4]) {
+  o[0] = unpack_pair(v.x); o[1] = unpack_pair(v.y); o[2] = unpack_pair(v.z); o[3] = unpack_pair(v.w);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GCNII initial residual on complete graphs (dgl GCN2Conv): out[a] = sa * mean_{u != a} x[u] + sb * addend[a].
+// The symmetric normalisation D^-1/2 A D^-1/2 of a complete K-graph is the mean over the other K-1 robots, and the alpha mix
+// with the initial features rides on the same pass (one kernel instead of aggregation + axpby: 4 instead of 7 tensor passes).
+template <typename T, int K, bool HAS_ADD, int NST>
+__global__ void __launch_bounds__(RING_TPB + 32) k_mean_mix_ring(const T* __restrict__ x, int64_t ldx, const T* __restrict__ addend, int64_t ldadd,
+                                                                 T* __restrict__ out, int64_t ldout, int64_t G, int ipg, float sa, float sb) {
+  using S = RingShape<T, K>;
+  constexpr int VEC = S::VEC, NP = VEC / 2;
+  constexpr int STAGE = (HAS_ADD ? 2 : 1) * K * S::PIECE;
+  constexpr int ROWV = RING_TPB * VEC;                     // elements of one node row per item
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + NST;
+  unsigned char* ring = smem + 128;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t items = G * ipg;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; ++s) { tma::mbar_init(full + s, 1); tma::mbar_init(empty + s, RING_TPB / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid >= RING_TPB) {
+    int s = 0; uint32_t ph = 0;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+      const int64_t g = it / ipg;
+      const int64_t coff = (it - g * ipg) * ROWV;
+      tma::mbar_wait(empty + s, ph ^ 1);
+      unsigned char* st = ring + (size_t)s * STAGE;
+      if (lane == 0) tma::mbar_expect_tx(full + s, STAGE);
+      __syncwarp();
+      if (lane < K) tma::bulk_g2s(st + lane * S::PIECE, x + (g * K + lane) * ldx + coff, S::PIECE, full + s);
+      else if (HAS_ADD && lane < 2 * K) tma::bulk_g2s(st + lane * S::PIECE, addend + (g * K + lane - K) * ldadd + coff, S::PIECE, full + s);
+      if (++s == NST) { s = 0; ph ^= 1; }
+    }
+    return;
+  }
+  const float wa = sa / (K - 1);
+  const float2 wa2 = make_float2(wa, wa), sb2 = make_float2(sb, sb);
+  int s = 0; uint32_t ph = 0;
+  for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+    const int64_t g = it / ipg;
+    const int64_t off = (it - g * ipg) * ROWV + tid * VEC;
+    const unsigned char* st = ring + (size_t)s * STAGE;
+    tma::mbar_wait(full + s, ph);
+    float2 xv[K][NP];
+#pragma unroll
+    for (int u = 0; u < K; ++u) unpack2<T>(*reinterpret_cast<const uint4*>(st + u * S::PIECE + tid * 16), xv[u]);
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+      float2 acc[NP];
+#pragma unroll
+      for (int q = 0; q < NP; ++q) acc[q] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < K; ++u) {
+        if (u == a) continue;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) acc[q] = fadd2(acc[q], xv[u][q]);
+      }
+      float o[VEC];
+      if constexpr (HAS_ADD) {
+        float2 av[NP];
+        unpack2<T>(*reinterpret_cast<const uint4*>(st + (K + a) * S::PIECE + tid * 16), av);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) { const float2 r = ffma2(acc[q], wa2, fmul2(av[q], sb2)); o[2 * q] = r.x; o[2 * q + 1] = r.y; }
+      } else {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) { const float2 r = fmul2(acc[q], wa2); o[2 * q] = r.x; o[2 * q + 1] = r.y; }
+      }
+      Vec16<T>::store(out + (g * K + a) * ldout + off, o);
+    }
+    __syncwarp();
+    if (lane == 0) tma::mbar_arrive(empty + s);
+    if (++s == NST) { s = 0; ph ^= 1; }
+  }
+}
+
+template <typename T, int K, bool HAS_ADD>
+static int launch_mean_mix_k(const T* x, int64_t ldx, const T* addend, int64_t ldadd, T* out, int64_t ldout, int64_t G, int64_t row, float sa,
+                             float sb, cudaStream_t st) {
+  using S = RingShape<T, K>;
+  constexpr int STAGE = (HAS_ADD ? 2 : 1) * K * S::PIECE;
+  constexpr int NST = (96 * 1024) / STAGE >= 6 ? 6 : ((96 * 1024) / STAGE >= 3 ? (96 * 1024) / STAGE : 3);
+  constexpr size_t smem = 128 + (size_t)NST * STAGE;
+  auto kern = k_mean_mix_ring<T, K, HAS_ADD, NST>;
+  static bool done = false;
+  static int per_sm = 1;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_mean_mix_ring)");
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RING_TPB + 32, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(k_mean_mix_ring)");
+    if (per_sm < 1) per_sm = 1;
+    done = true;
+  }
+  const int64_t ipg = row / (RING_TPB * S::VEC);
+  const int64_t items = G * ipg;
+  int64_t blocks = (int64_t)per_sm * kNumSMs;
+  if (blocks > items) blocks = items;
+  if (blocks < 1) return 0;
+  kern<<<(unsigned)blocks, RING_TPB + 32, smem, st>>>(x, ldx, addend, ldadd, out, ldout, G, (int)ipg, sa, sb);
+  RGNN_LAUNCH_CHECK("k_mean_mix_ring");
+  return 0;
+}
+
+template <typename T>
+static int launch_mean_mix(int K, const T* x, int64_t ldx, const T* addend, int64_t ldadd, T* out, int64_t ldout, int64_t G, int64_t row,
+                           float sa, float sb, cudaStream_t st) {
+#define RGNN_CASE(KK)                                                                                              \
+  case KK:                                                                                                         \
+    return addend ? launch_mean_mix_k<T, KK, true>(x, ldx, addend, ldadd, out, ldout, G, row, sa, sb, st)          \
+                  : launch_mean_mix_k<T, KK, false>(x, ldx, addend, ldadd, out, ldout, G, row, sa, sb, st);
+  switch (K) { RGNN_CASE(2) RGNN_CASE(3) RGNN_CASE(4) RGNN_CASE(5) RGNN_CASE(6) RGNN_CASE(7) RGNN_CASE(8) default: return RGNN_E_UNSUPPORTED; }
+#undef RGNN_CASE
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // backward:  dh[u] = addend[u] + w * sum_{a != u} gamma[e(u,a)] * dagg[a]
 //            dz[e(u,a)] = (sig') * w * (sum_p h[u] dagg[a], sum_p dagg[a]),   w = 1/(K-1)
@@ -193,14 +318,6 @@ template <typename T, int K, int TPB> struct RingBwd {
   __host__ __device__ static constexpr int stage(int nkind) { return nkind * K * PIECE + NE * ZPIECE; }
   static constexpr int HEAD = 128 + (8 * CH * K * 4 + 127) / 128 * 128;     // barriers + sum exchange (<= 8 stages)
 };
-
-template <typename T> __device__ __forceinline__ void unpack2(const uint4& v, float2 (&o)[Vec16<T>::N / 2]);
-template <> __device__ __forceinline__ void unpack2<float>(const uint4& v, float2 (&o)[2]) {
-  o[0] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y)); o[1] = make_float2(__uint_as_float(v.z), __uint_as_float(v.w));
-}
-template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(const uint4& v, float2 (&o)[4]) {
-  o[0] = unpack_pair(v.x); o[1] = unpack_pair(v.y); o[2] = unpack_pair(v.z); o[3] = unpack_pair(v.w);
-}
 
 template <typename T, int K, int TPB, int NST>
 __global__ void __launch_bounds__(2 * TPB + 32, 1) k_film_bwd_ring(const T* __restrict__ h, int64_t ldh, const T* __restrict__ dagg, int64_t ldd,
@@ -452,3 +569,25 @@ int film_bwd_ring(int dtype, int K, const void* h, int64_t ldh, const void* dagg
 }
 
 }  // namespace rgnn
+
+extern "C" int rgnn_complete_mean_mix(int dtype, const void* x, int64_t ldx, const void* addend, int64_t ldadd, void* out, int64_t ldout,
+                                      int64_t num_graphs, int64_t robots, int64_t row, float sa, float sb, void* stream) {
+  using namespace rgnn;
+  RGNN_REQUIRE(dtype == RGNN_F32 || dtype == RGNN_BF16, RGNN_E_ARG, "rgnn_complete_mean_mix: bad dtype %d", dtype);
+  RGNN_REQUIRE(num_graphs >= 0 && robots >= 2 && row > 0, RGNN_E_ARG, "rgnn_complete_mean_mix: bad sizes");
+  if (num_graphs == 0) return 0;
+  RGNN_REQUIRE(x && out, RGNN_E_ARG, "rgnn_complete_mean_mix: null pointer");
+  const int es = dtype == RGNN_F32 ? 4 : 2;
+  const int64_t item = (int64_t)RING_TPB * (16 / es);
+  if (robots > 8 || row % item || !aligned16(x) || !aligned16(out) || (addend && !aligned16(addend)) || (ldx * es) % 16 || (ldout * es) % 16 ||
+      (addend && (ldadd * es) % 16) || row / item >= (1ll << 31)) {
+    set_error("rgnn_complete_mean_mix: shape / alignment not covered (robots <= 8, row a multiple of %lld elements, 16-byte rows)", (long long)item);
+    return RGNN_E_UNSUPPORTED;
+  }
+  cudaStream_t st = as_stream(stream);
+  if (dtype == RGNN_F32)
+    return launch_mean_mix<float>((int)robots, static_cast<const float*>(x), ldx, static_cast<const float*>(addend), ldadd, static_cast<float*>(out), ldout,
+                                  num_graphs, row, sa, sb, st);
+  return launch_mean_mix<__nv_bfloat16>((int)robots, static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(addend), ldadd,
+                                        static_cast<__nv_bfloat16*>(out), ldout, num_graphs, row, sa, sb, st);
+}

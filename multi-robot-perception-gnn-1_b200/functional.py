@@ -596,6 +596,64 @@ def axpby(x, y, a, b):
     return AxpbyFn.apply(x, y, a, b)
 
 
+def _mean_mix(ix, x, addend, sa, sb):
+    """sa * mean over the other robots of the graph + sb * addend in one pass; None when the kernel does not cover the shape."""
+    row = x.numel() // max(1, x.shape[0])
+    out = torch.empty_like(x)
+    nbytes = x.element_size() * ix.N * row * (2 + (addend is not None))
+    with _lib.timed("mean_mix", nbytes):
+        rc = lib().rgnn_complete_mean_mix(dtype_code(x), ptr(x), row, ptr(addend), row, ptr(out), row, ix.G, ix.complete_k, row,
+                                          float(sa), float(sb), stream())
+    if rc == -4:          # RGNN_E_UNSUPPORTED
+        return None
+    check(rc, "rgnn_complete_mean_mix")
+    return out
+
+
+class MeanMixFn(torch.autograd.Function):
+    """r = sa * A_hat x + sb * x0 on complete K-robot graphs, where A_hat = D^-1/2 A D^-1/2 is the mean over the other K-1 robots
+    (GCN2Conv's propagation + initial residual) - one streaming kernel forward, one backward (A_hat is symmetric)."""
+
+    @staticmethod
+    def forward(ctx, x, x0, g, sa, sb):
+        ix = g.index()
+        _lib.require_cuda(x, x0)
+        x, x0 = x.contiguous(), x0.contiguous()
+        if x.shape != x0.shape or x.dtype != x0.dtype or x.shape[0] != ix.N:
+            raise ValueError("mean_mix operands must be two [N, ...] tensors of one shape and dtype")
+        with torch.cuda.device(x.device):
+            out = _mean_mix(ix, x, x0, sa, sb)
+            if out is None:
+                agg = torch.empty_like(x)
+                _aggregate(ix, x, None, True, None, _lib.POST_MEAN, None, None, agg, None, False)
+                out = torch.empty_like(x)
+                check(lib().rgnn_axpby(dtype_code(x), float(sa), ptr(agg), float(sb), ptr(x0), ptr(out), x.numel(), stream()), "rgnn_axpby")
+        ctx.g, ctx.sa, ctx.sb = g, float(sa), float(sb)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        ix = ctx.g.index()
+        d = d.contiguous()
+        dx = dx0 = None
+        with torch.cuda.device(d.device):
+            if ctx.needs_input_grad[0]:
+                dx = _mean_mix(ix, d, None, ctx.sa, 0.0)
+                if dx is None:
+                    agg = torch.empty_like(d)
+                    _aggregate(ix, d, None, True, None, _lib.POST_MEAN, None, None, agg, None, False)
+                    dx = torch.empty_like(d)
+                    check(lib().rgnn_axpby(dtype_code(d), ctx.sa, ptr(agg), 0.0, ptr(agg), ptr(dx), d.numel(), stream()), "rgnn_axpby")
+            if ctx.needs_input_grad[1]:
+                dx0 = torch.empty_like(d)
+                check(lib().rgnn_axpby(dtype_code(d), ctx.sb, ptr(d), 0.0, ptr(d), ptr(dx0), d.numel(), stream()), "rgnn_axpby")
+        return dx, dx0, None, None, None
+
+
+def mean_mix(g, x, x0, sa, sb):
+    return MeanMixFn.apply(x, x0, g, sa, sb)
+
+
 class BiasAddFn(torch.autograd.Function):
     """y = x + bias over the last dim (GraphConv bias when no weight transform follows the aggregation)."""
 

@@ -235,6 +235,11 @@ class GCN2Conv(nn.Module):
         ix = graph.index()
         if not self._allow_zero_in_degree and bool((ix.in_deg == 0).any()):
             raise RuntimeError('There are 0-in-degree nodes in the graph, output for those nodes will be invalid.')
+        if self._project_initial_features and 2 <= ix.complete_k <= 8 and ix.N == ix.G * ix.complete_k:
+            # complete K-robot graph: D^-1/2 A D^-1/2 X is the mean over the other robots; the alpha mix rides on the same pass
+            r = Fn.mean_mix(graph, feat, feat_0, 1 - self.alpha, self.alpha)
+            rst = Fn.linear(r, self.weight1, self.bias, alpha=self.beta, ident=1 - self.beta)
+            return rst if self._activation is None else self._activation(rst)
         agg = Fn.copy_u_reduce(graph, feat, "sum", ix.rsqrt_in, ix.rsqrt_in)       # D^-1/2 A D^-1/2 X (in-degree both sides)
         if self._project_initial_features:
             r = Fn.axpby(agg, feat_0, 1 - self.alpha, self.alpha)

@@ -88,3 +88,25 @@ def test_weight_gradient_products(R, nodes, fo, f, split):
     part = torch.empty((sp, fo, f), device="cuda") if sp > 1 else None
     F._gemm(a, (0, 0, 1, fo), b, (0, 0, f, 1), out, (0, f, 1), fo, f, rows, split=sp, partial=part)
     assert nerr(out, a.double().t() @ b.double()) <= TOL
+
+
+@pytest.mark.parametrize("k", [2, 5, 8])
+@pytest.mark.parametrize("dtype,row,tol", [(torch.float32, 2048, 1e-5), (torch.bfloat16, 4096, 2e-2), (torch.float32, 1000, 1e-5)])
+def test_mean_mix_matches_dense_formula(R, k, dtype, row, tol):
+    """GCN2Conv propagation + initial residual on complete graphs, r = sa * A_hat x + sb * x0 with A_hat = D^-1/2 A D^-1/2 (SURVEY
+    App. B), forward and both gradients, against the dense fp64 formula; row = 1000 takes the aggregate + axpby fallback."""
+    g_ = 6
+    gen = torch.Generator(device="cuda").manual_seed(k + row)
+    x = torch.randn((g_ * k, row), generator=gen, device="cuda").to(dtype).requires_grad_()
+    x0 = torch.randn((g_ * k, row), generator=gen, device="cuda").to(dtype).requires_grad_()
+    dy = torch.randn((g_ * k, row), generator=gen, device="cuda").to(dtype)
+    graph = R.robot_batch(g_, k, device="cuda")
+    y = R.functional.mean_mix(graph, x, x0, 0.9, 0.1)
+    y.backward(dy)
+    a_hat = (torch.ones(k, k, dtype=torch.float64, device="cuda") - torch.eye(k, dtype=torch.float64, device="cuda")) / (k - 1)
+    xd = x.detach().double().reshape(g_, k, row)
+    ref = 0.9 * torch.einsum("ab,gbr->gar", a_hat, xd).reshape(g_ * k, row) + 0.1 * x0.detach().double()
+    assert nerr(y.detach(), ref) <= tol
+    dref = 0.9 * torch.einsum("ab,gbr->gar", a_hat, dy.double().reshape(g_, k, row)).reshape(g_ * k, row)
+    assert nerr(x.grad, dref) <= tol
+    assert nerr(x0.grad, 0.1 * dy.double()) <= tol
