@@ -67,8 +67,8 @@ def main():
     print(json.dumps({"workload": f"GCNII stack: {a.layers} x GCN2Conv, [N={n}, P={a.pixels}, F={a.feat}] bf16, fwd+bwd",
                       "ms_per_step": round(ms, 3), "graphs_per_s": round(a.graphs / ms * 1e3, 1), "gemm_tflops": round(flops / ms / 1e9, 1),
                       "kernels": {k: {"calls": v["calls"], "ms_avg": round(v["ms_avg"], 4),
-                                      "achieved": round(v["work_total"] / (v["ms_total"] * 1e-3) / (1e9 if k.startswith("aggregate") else 1e12), 1),
-                                      "unit": "GB/s" if k.startswith("aggregate") else "TFLOP/s"} for k, v in prof.items()}}))
+                                      "achieved": round(v["work_total"] / (v["ms_total"] * 1e-3) / (1e9 if k.startswith(("aggregate", "mean_mix")) else 1e12), 1),
+                                      "unit": "GB/s" if k.startswith(("aggregate", "mean_mix")) else "TFLOP/s"} for k, v in prof.items()}}))
 
 
 if __name__ == "__main__":
