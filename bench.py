@@ -249,7 +249,9 @@ def main():
         h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
 
         def e2e_step():
-            pipe.step(hh, hpose, hdy, out_y, out_dh)
+            # single GPU: steps stream back to back through the pipeline (every step still copies its own inputs in and its own
+            # results out inside the timed region); with gradient all-reduce the calling stream joins after every step
+            pipe.step(hh, hpose, hdy, out_y, out_dh, wait=sync is not None)
             if sync is not None:
                 sync.finish()
 
@@ -257,11 +259,13 @@ def main():
         if sync is not None:
             sync.overlap = False       # gradients accumulate over the chunks; one reduction after the last chunk
         e2e_step(); e2e_step()
+        pipe.wait()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n_e2e):
             e2e_step()
+        pipe.wait()
         e1.record()
         barrier()
         ems = torch.tensor([e0.elapsed_time(e1)], device=dev)

@@ -35,25 +35,30 @@ class HostPipeline:
         self.dy_d = [mk(self.nc, out_feat, *hw) for _ in range(slots)]
         self.pose_d = [mk(self.ec, 9, dt=torch.float32) for _ in range(slots)]
         self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
+        self._slot_done = [None] * slots            # last compute event that read each input slot (carried across steps)
         es, px = self.h_d[0].element_size(), hw[0] * hw[1]
         self.h2d_bytes = num_graphs * robots * (feat + out_feat) * px * es + num_graphs * robots * (robots - 1) * 36
         self.d2h_bytes = num_graphs * robots * (feat + out_feat) * px * es
 
-    def step(self, h, pose, dy, y_out, dh_out):
+    def step(self, h, pose, dy, y_out, dh_out, wait=True):
         """h, dy, y_out, dh_out: pinned host [N, F, 8, 8]; pose: pinned host [E, 9] fp32.  Parameter .grad holds the sum over
-        the whole batch on return (after the caller synchronises, e.g. torch.cuda.current_stream().synchronize())."""
+        the whole batch on return (after the caller synchronises, e.g. torch.cuda.current_stream().synchronize()).
+        wait=False leaves the calling stream untouched, so back-to-back steps stream through the three pipeline streams without
+        a fill/drain bubble between them (the next step's H2D runs under this step's last D2H); call wait() before using the
+        outputs or the gradients on the calling stream."""
         cur = torch.cuda.current_stream(self.dev)
         for s in (self.s_in, self.s_comp, self.s_out):
             s.wait_stream(cur)
-        for p in self.block.parameters():
+        for p in self.block.parameters():           # (allocated on s_comp: the memory goes back to that stream's pool)
             p.grad = None
         ev_comp = [None] * self.chunks
         for i in range(self.chunks):
             sl = i % self.slots
             n0, n1, e0, e1 = i * self.nc, (i + 1) * self.nc, i * self.ec, (i + 1) * self.ec
             with torch.cuda.stream(self.s_in):
-                if i >= self.slots:
-                    self.s_in.wait_event(ev_comp[i - self.slots])      # the slot's previous consumer is done
+                prev = ev_comp[i - self.slots] if i >= self.slots else self._slot_done[sl]
+                if prev is not None:
+                    self.s_in.wait_event(prev)                         # the slot's previous consumer (this or the last step) is done
                 self.h_d[sl].copy_(h[n0:n1], non_blocking=True)
                 self.dy_d[sl].copy_(dy[n0:n1], non_blocking=True)
                 self.pose_d[sl].copy_(pose[e0:e1], non_blocking=True)
@@ -73,6 +78,14 @@ class HostPipeline:
                 dhd.record_stream(self.s_out)
                 y_out[n0:n1].copy_(yd, non_blocking=True)
                 dh_out[n0:n1].copy_(dhd, non_blocking=True)
+        for i in range(max(0, self.chunks - self.slots), self.chunks):
+            self._slot_done[i % self.slots] = ev_comp[i]
+        if wait:
+            self.wait()
+
+    def wait(self):
+        """Make the calling stream wait for every copy and kernel the pipeline has enqueued."""
+        cur = torch.cuda.current_stream(self.dev)
         cur.wait_stream(self.s_out)
         cur.wait_stream(self.s_comp)
 

@@ -37,6 +37,15 @@ def test_host_pipeline_matches_single_shot(R, dtype, tol):
     assert nerr(oy.float(), y_ref) <= tol and nerr(odh.float(), dh_ref) <= tol
     for n, p in blk.named_parameters():
         assert nerr(p.grad, ref[n]) <= 2 * tol, n
+    # streaming mode: three steps back to back without joining the calling stream, then one wait()
+    oy.zero_(); odh.zero_()
+    for _ in range(3):
+        pipe.step(hh, hp, hdy, oy, odh, wait=False)
+    pipe.wait()
+    torch.cuda.current_stream().synchronize()
+    assert nerr(oy.float(), y_ref) <= tol and nerr(odh.float(), dh_ref) <= tol
+    for n, p in blk.named_parameters():
+        assert nerr(p.grad, ref[n]) <= 2 * tol, n
 
 
 @pytest.mark.parametrize("dtype,f", [(torch.bfloat16, 512), (torch.float32, 64)])
