@@ -25,7 +25,7 @@ import torch  # noqa: E402
 
 F_DIM, K_ROBOTS, PIX = 512, 5, 64
 METRIC = "gnn_layer_fwd_bwd_robot_graphs_per_sec"
-MEM_KERNELS = ("aggregate", "film_", "bias_grad")      # HBM-bound kernel families (the rest are tensor-pipe GEMMs)
+MEM_KERNELS = ("aggregate", "film_", "bias_grad", "mean_mix")      # HBM-bound kernel families (the rest are tensor-pipe GEMMs)
 
 
 def parse():
@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="graph chunks the host-buffer pipeline overlaps")
     ap.add_argument("--cpu-graphs", type=int, default=192, help="graphs in the bounded CPU-baseline sample")
+    ap.add_argument("--stack", default="film", choices=["film", "gcnii"],
+                    help="film = the reference's GNN block (FiLM-GCN layers + compress, dgl/model/models.py:180-189); gcnii = the north star's "
+                         "GCN2Conv stack (DGL formula, SURVEY App. B) on channels-last [N, 64, F] features")
     ap.add_argument("--layers", type=int, default=2, choices=[1, 2], help="1 = gcn1 only (-multi_gcn off)")
     ap.add_argument("--no-compress", action="store_true", help="no 1x1 compress conv (-compress_gcn off; single layer only)")
     ap.add_argument("--torch-baseline", action="store_true",
@@ -51,6 +54,9 @@ def parse():
 
 
 def workload_name(a):
+    if a.stack == "gcnii":
+        return (f"GCNII stack ({a.layers}x GCN2Conv: D^-1/2 A D^-1/2 propagation, initial residual alpha=0.1, identity mapping), F={a.feat}, "
+                f"K={a.robots} robots, channels-last [N, 64, F], {a.graphs} graphs/GPU, {a.dtype}")
     width = {512: " (resnet18 width)", 1280: " (mobilenetv2 width)", 2048: " (resnet50 width)"}.get(a.feat, "")
     if a.layers == 2:
         stack = "warehouse gcn2 stack (2x FiLM-GCN + 1x1 compress)"
@@ -76,6 +82,20 @@ def torch_gpu_step_fn(blk, g, a):
         if conv is None:
             return torch.cat((h, agg), 1)
         return Fn.conv2d(torch.cat((h, agg), 1), conv.weight.to(h.dtype), conv.bias.to(h.dtype))
+
+    if a.stack == "gcnii":
+        k = a.robots
+        a_hat = ((torch.ones(k, k, device=src.device) - torch.eye(k, device=src.device)) / (k - 1))
+
+        def fwd_gcnii(h, pose):
+            x0 = h.reshape(h.shape[0], 64, -1)
+            x = x0
+            for l in blk.layers:
+                agg = torch.einsum("ab,gbpf->gapf", a_hat.to(x.dtype), x.reshape(-1, k, 64, x.shape[-1])).reshape(x.shape)
+                r = (1 - l.alpha) * agg + l.alpha * x0
+                x = (1 - l.beta) * r + l.beta * (r @ l.weight1.to(x.dtype)) + l.bias.to(x.dtype)
+            return x.reshape(h.shape)
+        return fwd_gcnii
 
     def fwd(h, pose):
         y = layer(blk.gcn1, None if a.no_compress else blk.conv1, h, pose)
@@ -132,7 +152,10 @@ def cpu_reference_rate(a, reps):
     from oracle import ref_port
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sec = ref_port.time_block(a.feat, a.robots, a.cpu_graphs, not a.no_compress, a.layers == 2, reps=reps, threads=cores)
+    if a.stack == "gcnii":
+        sec = ref_port.time_gcnii(a.feat, a.robots, a.cpu_graphs, layers=a.layers, reps=reps, threads=cores)
+    else:
+        sec = ref_port.time_block(a.feat, a.robots, a.cpu_graphs, not a.no_compress, a.layers == 2, reps=reps, threads=cores)
     return a.cpu_graphs / sec, cores, sec
 
 
@@ -178,7 +201,25 @@ def main():
     torch.manual_seed(1)                 # reference default seed (training.py:24); PyTorch-default init of Linear / Conv2d
     if a.no_compress and a.layers == 2:
         raise SystemExit("two layers need the compress conv (dgl/model/models.py:169)")
-    blk = R.GNNBlock(types.SimpleNamespace(feature_dim=F, compress_gcn=not a.no_compress, multi_gcn=a.layers == 2))
+    if a.stack == "gcnii":
+        class GcniiStack(torch.nn.Module):
+            """x_{l+1} = GCN2Conv_l(g, x_l, x_0) over channels-last [N, 64, F] views of the [N, F, 8, 8]-sized buffers."""
+            def __init__(self):
+                super().__init__()
+                self.layers = torch.nn.ModuleList(R.GCN2Conv(F, layer=i + 1, alpha=0.1, lambda_=1) for i in range(a.layers))
+                for l in self.layers:
+                    torch.nn.init.normal_(l.weight1, std=F ** -0.5)
+
+            def forward(self, g, h, pose=None):
+                x0 = h.reshape(h.shape[0], 64, -1)
+                x = x0
+                for l in self.layers:
+                    x = l(g, x, x0)
+                return x.reshape(h.shape)
+        blk = GcniiStack()
+        a.no_compress = False
+    else:
+        blk = R.GNNBlock(types.SimpleNamespace(feature_dim=F, compress_gcn=not a.no_compress, multi_gcn=a.layers == 2))
     blk.to(dev)
     sync = R.parallel.GradSync(blk) if world > 1 else None
 
@@ -342,14 +383,14 @@ def main():
     if not a.no_cpu_baseline:
         rate, cores, sec = cpu_reference_rate(a, reps=3)
         cpu = {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port",
-               "sample": f"reference CPU path (oracle/ref_port.py over the DGL-semantics shim), fp32, fwd+bwd of {a.cpu_graphs} graphs, "
+               "sample": f"{'reference CPU path' if a.stack == 'film' else 'DGL-formula GCN2Conv stack on CPU'} (oracle/ref_port.py over the DGL-semantics shim), fp32, fwd+bwd of {a.cpu_graphs} graphs, "
                          f"best of 3 after 1 warm-up ({sec * 1e3:.1f} ms)"}
 
     line = {"metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": a.dtype, "data": "synthetic",
             "config": {"workload": workload_name(a), "graphs_per_gpu": G, "robots": K, "feature_dim": F, "pixels": PIX,
-                       "layers": a.layers, "compress": not a.no_compress, "l2_policy": "inputs (1.3 GB/GPU) larger than the 126 MB L2",
+                       "stack": a.stack, "layers": a.layers, "compress": (not a.no_compress) if a.stack == "film" else None, "l2_policy": "inputs (1.3 GB/GPU) larger than the 126 MB L2",
                        "parallelism": f"dp{world}: graphs sharded, NCCL all-reduce of GNN-layer grads only"},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk}

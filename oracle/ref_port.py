@@ -110,3 +110,36 @@ def time_block(f, k, graphs, compress_gcn, multi_gcn, reps=3, threads=None, seed
         if it > 0:
             best = min(best, dt)
     return best
+
+
+def time_gcnii(f, k, graphs, layers=2, reps=3, threads=None, seed=1):
+    """fwd+bwd seconds (best of `reps` after one warm-up) of a stack of DGL-formula GCN2Conv layers (oracle/dgl_shim, SURVEY
+    App. B) on `graphs` complete K-robot graphs, channels-last features [N, 64, F], fp32, all host threads.  The reference imports
+    dgl.nn.pytorch but never runs GCN2Conv; this is the CPU counterpart of the north-star GCNII stack."""
+    import time
+    from . import gnn_oracle as O
+    dgl = _dgl()
+    from dgl.nn.pytorch import GCN2Conv
+    if threads:
+        torch.set_num_threads(threads)
+    sb = O.synthetic_batch(graphs, k, 8, p=64, seed=seed)        # topology only
+    n = graphs * k
+    g = dgl.graph((torch.as_tensor(sb["src"]), torch.as_tensor(sb["dst"])), num_nodes=n)
+    gen = torch.Generator().manual_seed(seed)
+    convs = [GCN2Conv(f, layer=i + 1, alpha=0.1, lambda_=1) for i in range(layers)]
+    x0 = torch.randn((n, 64, f), generator=gen).requires_grad_()
+    dy = torch.randn((n, 64, f), generator=gen)
+    best = float("inf")
+    for it in range(reps + 1):
+        for c in convs:
+            c.zero_grad(set_to_none=True)
+        x0.grad = None
+        t0 = time.perf_counter()
+        x = x0
+        for c in convs:
+            x = c(g, x, x0)
+        x.backward(dy)
+        dt = time.perf_counter() - t0
+        if it > 0:
+            best = min(best, dt)
+    return best
