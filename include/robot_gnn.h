@@ -178,6 +178,11 @@ int rgnn_gemm(int a_dtype, const void* A, int64_t sAz, int64_t sAr, int64_t sAm,
 /* fp32 master weights [rows, cols] -> bf16 copy and/or bf16 transpose [cols, rows] (either may be NULL) */
 int rgnn_tc_cast_weights(const float* w, int64_t rows, int64_t cols, void* out_bf16, void* out_t_bf16, void* stream);
 
+/* Same cast of alpha * w + ident * I (square w when ident != 0): GCN2Conv's identity mapping (1-beta) I + beta W folded
+ * into the bf16 weight operand, so the transform is ONE plain GEMM r . W' with no second operand in its epilogue. */
+int rgnn_tc_cast_weights_affine(const float* w, int64_t rows, int64_t cols, float alpha, float ident, void* out_bf16, void* out_t_bf16,
+                                void* stream);
+
 /* 1x1 convolution over NCHW robot feature maps with P = 64 pixels, concat-free (models.py:182-184 and its dX):
  * out[v,m,:] = sum_{k<c0} W[m,k] x0[v,k,:] + sum_{k<c1} W[m,c0+k] x1[v,k,:] (+ bias[m]);  W bf16 [m0+m1, c0+c1];
  * rows m < m0 land in out0 [nodes, m0, 64], rows >= m0 in out1 [nodes, m1, 64] (x1/out1 optional with c1/m1 = 0). */

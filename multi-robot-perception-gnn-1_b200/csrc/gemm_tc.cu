@@ -428,14 +428,15 @@ __global__ void __launch_bounds__(256) k_sum_partials(const float* __restrict__ 
 }
 
 // fp32 [R, C] -> bf16 [R, C] and (optionally) its transpose [C, R]: per-step cast of the fp32 master weights
+// (alpha * w + ident * I: GCN2Conv's identity mapping (1-beta) I + beta W folded into the weight matrix itself)
 __global__ void __launch_bounds__(256) k_cast_weights(const float* __restrict__ w, int R, int C, __nv_bfloat16* __restrict__ o,
-                                                      __nv_bfloat16* __restrict__ ot) {
+                                                      __nv_bfloat16* __restrict__ ot, float alpha, float ident) {
   __shared__ float t[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
   for (int j = ty; j < 32; j += 8) {
     const int r = r0 + j, c = c0 + tx;
-    const float v = (r < R && c < C) ? w[(int64_t)r * C + c] : 0.f;
+    const float v = (r < R && c < C) ? fmaf(alpha, w[(int64_t)r * C + c], r == c ? ident : 0.f) : 0.f;
     t[j][tx] = v;
     if (o && r < R && c < C) o[(int64_t)r * C + c] = __float2bfloat16_rn(v);
   }
@@ -503,7 +504,19 @@ extern "C" int rgnn_tc_cast_weights(const float* w, int64_t rows, int64_t cols, 
                "rgnn_tc_cast_weights: bad arguments");
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
   k_cast_weights<<<grid, 256, 0, as_stream(stream)>>>(w, (int)rows, (int)cols, static_cast<__nv_bfloat16*>(out_bf16),
-                                                      static_cast<__nv_bfloat16*>(out_t_bf16));
+                                                      static_cast<__nv_bfloat16*>(out_t_bf16), 1.0f, 0.0f);
+  RGNN_LAUNCH_CHECK("k_cast_weights");
+  return 0;
+}
+
+extern "C" int rgnn_tc_cast_weights_affine(const float* w, int64_t rows, int64_t cols, float alpha, float ident, void* out_bf16, void* out_t_bf16,
+                                           void* stream) {
+  RGNN_REQUIRE(w && (out_bf16 || out_t_bf16) && rows > 0 && cols > 0 && rows < (1 << 30) && cols < (1 << 30), RGNN_E_ARG,
+               "rgnn_tc_cast_weights_affine: bad arguments");
+  RGNN_REQUIRE(ident == 0.0f || rows == cols, RGNN_E_ARG, "rgnn_tc_cast_weights_affine: the identity term needs a square matrix");
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  k_cast_weights<<<grid, 256, 0, as_stream(stream)>>>(w, (int)rows, (int)cols, static_cast<__nv_bfloat16*>(out_bf16),
+                                                      static_cast<__nv_bfloat16*>(out_t_bf16), alpha, ident);
   RGNN_LAUNCH_CHECK("k_cast_weights");
   return 0;
 }

@@ -187,12 +187,16 @@ def _gemm(a, sa, b, sb, c, sc, m, n, k, batch=1, red=1, split=1, partial=None, e
                           m, n, k, batch, red, split, ptr(partial), epi, ptr(bias), ptr(aux), alpha, beta, stream()), "rgnn_gemm")
 
 
-def _cast_w(w, transpose=False, both=False):
-    """fp32 master weight [R, C] -> bf16 [R, C] and/or its transpose [C, R] (one small kernel per step)."""
+def _cast_w(w, transpose=False, both=False, alpha=1.0, ident=0.0):
+    """fp32 master weight [R, C] -> bf16 [R, C] and/or its transpose [C, R] (one small kernel per step); with alpha / ident the
+    cast is of alpha * W + ident * I (GCN2Conv's identity mapping folded into the weight operand)."""
     r, c = w.shape
     o = torch.empty((r, c), dtype=torch.bfloat16, device=w.device) if (both or not transpose) else None
     ot = torch.empty((c, r), dtype=torch.bfloat16, device=w.device) if (both or transpose) else None
-    check(lib().rgnn_tc_cast_weights(ptr(w), r, c, ptr(o), ptr(ot), stream()), "rgnn_tc_cast_weights")
+    if alpha == 1.0 and ident == 0.0:
+        check(lib().rgnn_tc_cast_weights(ptr(w), r, c, ptr(o), ptr(ot), stream()), "rgnn_tc_cast_weights")
+    else:
+        check(lib().rgnn_tc_cast_weights_affine(ptr(w), r, c, float(alpha), float(ident), ptr(o), ptr(ot), stream()), "rgnn_tc_cast_weights_affine")
     return (o, ot) if both else (ot if transpose else o)
 
 
@@ -507,11 +511,12 @@ class LinearFn(torch.autograd.Function):
             epi |= _lib.EPI_ADD_AUX
         ctx.tc = bool(_lib.USE_TC and x.dtype == torch.bfloat16 and din % 128 == 0 and dout % 128 == 0 and rows > 0)
         with torch.cuda.device(x.device):
-            if ctx.tc:     # tcgen05 path: W^T in bf16 is the K-major B operand; alpha, identity mapping and bias fused in the epilogue
-                wt = _cast_w(wf, transpose=True)
+            if ctx.tc:     # tcgen05 path: (alpha W + ident I)^T in bf16 is the K-major B operand - the identity mapping lives in the
+                           # weight matrix (one plain GEMM, no second operand to read in the epilogue); bias fused in the epilogue
+                wt = _cast_w(wf, transpose=True, alpha=float(alpha), ident=float(ident))
                 with _lib.timed("linear_fwd", 2.0 * rows * din * dout):
-                    check(lib().rgnn_tc_gemm_tn(ptr(x), din, ptr(wt), din, ptr(y), dout, rows, dout, din, epi, ptr(bf),
-                                                ptr(x) if ident != 0.0 else None, float(alpha), float(ident), stream()), "rgnn_tc_gemm_tn")
+                    check(lib().rgnn_tc_gemm_tn(ptr(x), din, ptr(wt), din, ptr(y), dout, rows, dout, din, epi & ~_lib.EPI_ADD_AUX, ptr(bf),
+                                                None, 1.0, 0.0, stream()), "rgnn_tc_gemm_tn")
             else:
                 _gemm(x, (0, 0, din, 1), wf, (0, 0, dout, 1), y, (0, dout, 1), rows, dout, din, epi=epi, bias=bf,
                       aux=x if ident != 0.0 else None, alpha=float(alpha), beta=float(ident))
@@ -531,11 +536,11 @@ class LinearFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 dx = torch.empty_like(x)
                 epi = _lib.EPI_ADD_AUX if ctx.ident != 0.0 else 0
-                if ctx.tc:     # dX = alpha * dY . W^T (+ ident * dY): W [in, out] in bf16 is already the K-major B operand
-                    wb = _cast_w(wf)
+                if ctx.tc:     # dX = dY . (alpha W + ident I)^T: the [in, out] matrix in bf16 is already the K-major B operand
+                    wb = _cast_w(wf, alpha=ctx.alpha, ident=ctx.ident)
                     with _lib.timed("linear_dx", 2.0 * rows * din * dout):
-                        check(lib().rgnn_tc_gemm_tn(ptr(dy), dout, ptr(wb), dout, ptr(dx), din, rows, din, dout, epi, None,
-                                                    ptr(dy) if ctx.ident != 0.0 else None, ctx.alpha, ctx.ident, stream()), "rgnn_tc_gemm_tn")
+                        check(lib().rgnn_tc_gemm_tn(ptr(dy), dout, ptr(wb), dout, ptr(dx), din, rows, din, dout, 0, None,
+                                                    None, 1.0, 0.0, stream()), "rgnn_tc_gemm_tn")
                 else:
                     _gemm(dy, (0, 0, dout, 1), wf, (0, 0, 1, dout), dx, (0, din, 1), rows, din, dout,
                           epi=epi, aux=dy if ctx.ident != 0.0 else None, alpha=ctx.alpha, beta=ctx.ident)
