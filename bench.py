@@ -191,6 +191,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = R.parallel.bind_to_gpu_numa_node(local) if world > 1 else None     # before any pinned host buffer exists
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     R._lib.check(R._lib.lib().rgnn_device_ok(), "rgnn_device_ok")
@@ -391,7 +392,8 @@ def main():
             "dtype": a.dtype, "data": "synthetic",
             "config": {"workload": workload_name(a), "graphs_per_gpu": G, "robots": K, "feature_dim": F, "pixels": PIX,
                        "stack": a.stack, "layers": a.layers, "compress": (not a.no_compress) if a.stack == "film" else None, "l2_policy": "inputs (1.3 GB/GPU) larger than the 126 MB L2",
-                       "parallelism": f"dp{world}: graphs sharded, NCCL all-reduce of GNN-layer grads only"},
+                       "parallelism": f"dp{world}: graphs sharded, NCCL all-reduce of GNN-layer grads only",
+                       "numa_node_rank0": numa},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk}
     if torch_gpu is not None:

@@ -95,3 +95,28 @@ class GradSync:
     def remove(self):
         for h in self._hooks:
             h.remove()
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs), so that pinned host buffers allocated afterwards
+    are local to the GPU's PCIe root: with one rank per GPU on a two-socket host, host<->device copies otherwise cross the
+    socket interconnect.  Returns the node number, or None when the topology is not exposed (containers, single-node hosts)."""
+    import os
+    import torch
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
