@@ -78,11 +78,11 @@ def test_wgrad_guards(R):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("ks", [[5] * 7, [12] * 3, [3, 5, 2, 4, 1], [20] * 2])
-def test_aggregation_guards(R, dtype, ks):
+@pytest.mark.parametrize("F", [24, 64])        # 64: the streaming ring kernels (whole 16 / 32-channel items); 24: the register-prefetch ones
+@pytest.mark.parametrize("ks", [[5] * 7, [12] * 3, [3, 5, 2, 4, 1], [20] * 2, [8] * 3, [2] * 5])
+def test_aggregation_guards(R, dtype, ks, F):
     import numpy as np
     from oracle import gnn_oracle as O
-    F = 24
     ed = [O.fully_connected_edges(k) for k in ks]
     g = R.RobotGraph(torch.from_numpy(np.concatenate([e[0] for e in ed])).cuda(), torch.from_numpy(np.concatenate([e[1] for e in ed])).cuda(),
                      ks, [len(e[0]) for e in ed], complete_k=ks[0] if len(set(ks)) == 1 else 0)
@@ -108,6 +108,26 @@ def test_aggregation_guards(R, dtype, ks):
     assert rc == 0
     dh.check("film backward dh")
     dz.check("film backward dz", allow_sentinel_inside=(e == 0))
+    # the layout the fused layer uses: dAgg and the direct gradient are the two channel halves of one [N, 2F, 64] buffer
+    dcat = torch.randn((n, 2 * F, 64), generator=gen, device="cuda").to(dtype)
+    dh2 = Guarded((n, F, 64), dtype, 333.0)
+    dz2 = Guarded((e, 2 * F), dtype, 333.0)
+    rc = L.lib().rgnn_film_backward(L.dtype_code(h), L.ptr(h), F * 64, L.ptr(dcat.view(-1)[F * 64:]), 2 * F * 64, L.ptr(z), 1, L.ptr(dcat), 2 * F * 64,
+                                    L.ptr(dh2.view), F * 64, L.ptr(dz2.view), L.ptr(ix.inv_in_deg), L.ptr(ix.ptr32), L.ptr(ix.idx32),
+                                    L.ptr(ix.noff32), ix.G, ix.max_nodes, ix.max_edges, ix.complete_k, n, e, F, 64, L.stream())
+    assert rc == 0
+    dh2.check("film backward dh (strided halves)")
+    dz2.check("film backward dz (strided halves)", allow_sentinel_inside=(e == 0))
+    # and it must equal the un-fused composition: addend + backward without addend on a contiguous copy of the dAgg half
+    d2 = dcat[:, F:].contiguous()
+    dh3, dz3 = torch.empty_like(h), torch.empty_like(z)
+    rc = L.lib().rgnn_film_backward(L.dtype_code(h), L.ptr(h), F * 64, L.ptr(d2), F * 64, L.ptr(z), 1, None, 0, L.ptr(dh3), F * 64,
+                                    L.ptr(dz3), L.ptr(ix.inv_in_deg), L.ptr(ix.ptr32), L.ptr(ix.idx32), L.ptr(ix.noff32), ix.G,
+                                    ix.max_nodes, ix.max_edges, ix.complete_k, n, e, F, 64, L.stream())
+    assert rc == 0
+    assert torch.equal(dz3, dz2.view)
+    ref = dh3.float() + dcat[:, :F].float()
+    assert float((dh2.view.float() - ref).abs().max()) <= (1e-5 if dtype == torch.float32 else 6e-2) * float(ref.abs().max())
 
 
 def test_csr_guards(R):
