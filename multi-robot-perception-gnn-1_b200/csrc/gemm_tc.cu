@@ -54,12 +54,18 @@ struct TcParams {
 // and TMA-multicasts it into both CTAs' shared memory, cutting L2->SM operand traffic per CTA from 48 KB to 32 KB per
 // k-block.  Every stage's empty barrier then collects the tcgen05.commit of BOTH CTAs (multicast commit) before either
 // producer may overwrite the stage.  The MMAs themselves stay cta_group::1 (each CTA owns its accumulator).
-template <int BN, int CL, bool AUX>      // AUX: ROW epilogue with a second operand (identity mapping / ReLU mask)
+// TWO (with CL = 2): the cluster is a tcgen05 CTA PAIR - one cta_group::2 MMA of M = 256 issued by the leader (rank 0) over both SMs.
+// Each CTA then keeps only ITS half of the B tile: 32 KB instead of 48 KB land in shared memory per k-block and each MMA reads
+// 8 KB instead of 12 KB, i.e. ~125 B/clk of shared-memory traffic instead of ~187 B/clk against a 128 B/clk port (the multicast
+// variant caps at ~1.55 PFLOP/s with its stores compiled out), and the ring deepens from 4 to 6 stages.
+template <int BN, int CL, bool AUX, bool TWO>      // AUX: ROW epilogue with a second operand (identity mapping / ReLU mask)
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
           const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmO0,
           const __grid_constant__ CUtensorMap tmO1, const TcParams p) {
-  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  static_assert(!TWO || CL == 2, "a CTA pair is a cluster of two");
+  constexpr int NSTAGE = TWO ? 6 : tc::NSTAGE;
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = (TWO ? BN / 2 : BN) * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;    // 256 or 512: power of two
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: [tiles (1024-aligned)] [barriers]
@@ -86,13 +92,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
   if (warp == 1 && lane == 0) {
     // a stage is free once every CTA's MMAs retired (+ this CTA's 4 epilogue warps when they also read the A tile: rowsum mode)
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, CL + (p.rowsum ? 4 : 0)); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8); }
+    // (CTA pair: only the leader commits, to both CTAs; the leader's accumulator-empty barrier collects both CTAs' epilogue warps)
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, (TWO ? 1 : CL) + (p.rowsum ? 4 : 0)); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, TWO ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (TWO) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -118,6 +130,32 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t fb = bar_full + 8 * stage;
           const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          if constexpr (TWO) {
+            // CTA pair: own A rows + own half of B into this CTA's stage; every byte is counted on the LEADER's barrier
+            if (crank == 0) mbar_expect_tx(fb, 2 * STAGE_BYTES);
+            if (p.load_mode == LOAD_TN) {
+              tma_2d_2sm(sa, &tmA, fb, kb * BK, tm * BM);
+              tma_2d_2sm(sb, &tmB0, fb, kb * BK, tn * BN + crank * (BN / 2));
+            } else if (p.load_mode == LOAD_CONV) {
+              tma_2d_2sm(sa, &tmA, fb, kb * BK, tm * BM);
+              const CUtensorMap* mb = kb < p.kb_b0 ? &tmB0 : &tmB1;
+              const int kc = (kb < p.kb_b0 ? kb : kb - p.kb_b0) * BK;
+              tma_3d_2sm(sb, mb, fb, 0, kc, tn * (BN / 64) + crank * (BN / 128));
+            } else if (p.load_mode == LOAD_WGRAD) {
+              tma_2d_2sm(sa, &tmA, fb, 0, kb * p.rows_a + tm * BM);
+              const int n0 = tn * BN;
+              const CUtensorMap* mb = n0 < p.n_b0 ? &tmB0 : &tmB1;
+              const int rowb = n0 < p.n_b0 ? kb * p.rows_b0 + n0 : kb * p.rows_b1 + (n0 - p.n_b0);
+              tma_2d_2sm(sb, mb, fb, 0, rowb + crank * (BN / 2));
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_2d_2sm(sa + j * (BK * 128), &tmA, fb, tm * BM + j * 64, kb * BK);
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j) tma_2d_2sm(sb + j * (BK * 128), &tmB0, fb, tn * BN + (crank * (BN / 128) + j) * 64, kb * BK);
+            }
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(fb, STAGE_BYTES);
           // A: this CTA's own 128 rows.  B: tensor maps carry HALF-tile boxes; a lone CTA fetches both halves, a cluster CTA
           // fetches half `crank` and multicasts it to every CTA of the cluster.
@@ -173,11 +211,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
+  } else if (warp == 1 && !(TWO && crank != 0)) {
+    // ================================ MMA issuer (CTA pair: the leader only) ================================
     // instruction descriptor: D fp32, A/B bf16, majors, N>>3, M>>4 (cute::UMMA::InstrDescriptor)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TWO ? 2 * BM : BM) >> 4) << 24);
     const uint32_t a_lbo = a_mn ? BK * 128 : 0, b_lbo = b_mn ? BK * 128 : 0;
     const uint32_t a_kstep = a_mn ? 2048 : 32, b_kstep = b_mn ? 2048 : 32;   // bytes per 16 k
     int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
@@ -196,16 +234,24 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = make_desc(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t db = make_desc(sb + k * b_kstep, b_lbo, 1024);
-            umma(tacc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (TWO) umma2(tacc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma(tacc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
+          if constexpr (TWO) {
+            umma_commit2_mc(bar_empty + 8 * stage, MC_MASK);                     // the stage is free in both CTAs
+            if (kb == kb1 - 1) umma_commit2_mc(bar_tfull + 8 * as, MC_MASK);     // both halves of the accumulator are complete
+          } else {
           if (CL > 1) umma_commit_mc(bar_empty + 8 * stage, MC_MASK);   // both CTAs' producers wait for both consumers
           else umma_commit(bar_empty + 8 * stage);            // stage reusable once these MMAs retire
           if (kb == kb1 - 1) umma_commit(bar_tfull + 8 * as); // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
-      if (kb1 <= kb0 && elect_one()) umma_commit(bar_tfull + 8 * as);   // empty split: hand over (epilogue writes zeros)
+      if (kb1 <= kb0 && elect_one()) {                                  // empty split: hand over (epilogue writes zeros)
+        if constexpr (TWO) umma_commit2_mc(bar_tfull + 8 * as, MC_MASK); else umma_commit(bar_tfull + 8 * as);
+      }
       __syncwarp();
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -402,7 +448,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+      if (lane == 0) {
+        if (TWO && crank != 0) mbar_arrive_cluster(bar_tempty + 8 * as, 0);  // the leader's MMA warp waits for both CTAs' epilogues
+        else mbar_arrive(bar_tempty + 8 * as);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive its readers (both warpgroups)
@@ -413,7 +462,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (CL > 1) cluster_sync_all();       // nobody leaves while a peer may still multicast into it or signal its barriers
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -452,13 +502,13 @@ __global__ void __launch_bounds__(256) k_cast_weights(const float* __restrict__ 
 // ---------------------------------------------------------------------------------------------------------
 static int g_cluster = -1;    // RGNN_TC_CLUSTER=1 disables the 2-CTA multicast clusters (debug / A-B comparison)
 
-template <int BN, int CL, bool AUX>
+template <int BN, int CL, bool AUX, bool TWO = false>
 static int launch_cl(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const TcParams& p, cudaStream_t st,
                      const CUtensorMap* o0, const CUtensorMap* o1) {
-  constexpr size_t smem = 1024 + (size_t)NSTAGE * (BM * BK * 2 + BN * BK * 2) + NOUT_STAGE * 128 * 128 + 256;
+  constexpr size_t smem = 1024 + (TWO ? (size_t)6 * (BM * BK * 2 + BN / 2 * BK * 2) : (size_t)NSTAGE * (BM * BK * 2 + BN * BK * 2)) + NOUT_STAGE * 128 * 128 + 256;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, CL, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, CL, AUX, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_gemm_tc)");
     attr_done = true;
   }
@@ -475,7 +525,7 @@ static int launch_cl(const CUtensorMap& a, const CUtensorMap& b0, const CUtensor
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   count_launch();
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, CL, AUX>, a, b0, b1, o0 ? *o0 : a, o1 ? *o1 : (o0 ? *o0 : a), p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, CL, AUX, TWO>, a, b0, b1, o0 ? *o0 : a, o1 ? *o1 : (o0 ? *o0 : a), p);
   if (e != cudaSuccess) return cuda_fail(e, "k_gemm_tc launch");
   return 0;
 }
@@ -489,6 +539,11 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap
   }
   // clusters only pay when there are at least two M-tiles to pair up
   const bool aux = p.epi_mode == EPI_ROW && (p.epi_flags & (RGNN_EPI_ADD_AUX | RGNN_EPI_RELU_MASK)) != 0;
+  static int two = -1;          // cta_group::2 CTA pairs for the 256-wide tiles without an in-kernel row sum; RGNN_TC_2CTA=0: multicast pairs
+  if (two < 0) { const char* e = getenv("RGNN_TC_2CTA"); two = (e && e[0] == '0') ? 0 : 1; }
+  if constexpr (BN == 256) {
+    if (two == 1 && g_cluster == 2 && p.tiles_m >= 2 && !aux && !p.rowsum) return launch_cl<BN, 2, false, true>(a, b0, b1, p, st, o0, o1);
+  }
   if (g_cluster == 2 && p.tiles_m >= 2) return aux ? launch_cl<BN, 2, true>(a, b0, b1, p, st, o0, o1) : launch_cl<BN, 2, false>(a, b0, b1, p, st, o0, o1);
   return aux ? launch_cl<BN, 1, true>(a, b0, b1, p, st, o0, o1) : launch_cl<BN, 1, false>(a, b0, b1, p, st, o0, o1);
 }
