@@ -77,6 +77,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NSTAGE);
   const uint32_t bar_tfull = smem_u32(bars + 2 * NSTAGE), bar_tempty = smem_u32(bars + 2 * NSTAGE + 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+  // CTA pair + row sums: the peer never sees its own operand bytes land (they are counted on the leader's barrier), so the row-sum
+  // warps of BOTH CTAs read the A tile after the leader's MMAs on it have retired (multicast commit -> mdone) and only their
+  // four arrivals free the stage.
+  const uint32_t bar_mdone = smem_u32(bars + 2 * NSTAGE + 5);
+  const bool rs_after_mma = TWO && p.rowsum != nullptr;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
@@ -93,7 +98,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 1 && lane == 0) {
     // a stage is free once every CTA's MMAs retired (+ this CTA's 4 epilogue warps when they also read the A tile: rowsum mode)
     // (CTA pair: only the leader commits, to both CTAs; the leader's accumulator-empty barrier collects both CTAs' epilogue warps)
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, (TWO ? 1 : CL) + (p.rowsum ? 4 : 0)); }
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, rs_after_mma ? 4 : (TWO ? 1 : CL) + (p.rowsum ? 4 : 0));
+      mbar_init(bar_mdone + 8 * i, 1);
+    }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, TWO ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -238,7 +247,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             else umma(tacc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           if constexpr (TWO) {
-            umma_commit2_mc(bar_empty + 8 * stage, MC_MASK);                     // the stage is free in both CTAs
+            umma_commit2_mc((rs_after_mma ? bar_mdone : bar_empty) + 8 * stage, MC_MASK);   // the stage is free (or ready for the row sums) in both CTAs
             if (kb == kb1 - 1) umma_commit2_mc(bar_tfull + 8 * as, MC_MASK);     // both halves of the accumulator are complete
           } else {
           if (CL > 1) umma_commit_mc(bar_empty + 8 * stage, MC_MASK);   // both CTAs' producers wait for both consumers
@@ -276,7 +285,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         float rs = 0.f;
         const bool mine = tn == 0;              // every N-tile of an M-tile loads the same A: only one of them sums it
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(bar_full + 8 * rstage, rphase);
+          mbar_wait((rs_after_mma ? bar_mdone : bar_full) + 8 * rstage, rphase);
           if (mine) {
             const uint32_t rowaddr = tiles + rstage * STAGE_BYTES + row * 128;
 #pragma unroll
@@ -505,7 +514,7 @@ static int g_cluster = -1;    // RGNN_TC_CLUSTER=1 disables the 2-CTA multicast 
 template <int BN, int CL, bool AUX, bool TWO = false>
 static int launch_cl(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const TcParams& p, cudaStream_t st,
                      const CUtensorMap* o0, const CUtensorMap* o1) {
-  constexpr size_t smem = 1024 + (TWO ? (size_t)6 * (BM * BK * 2 + BN / 2 * BK * 2) : (size_t)NSTAGE * (BM * BK * 2 + BN * BK * 2)) + NOUT_STAGE * 128 * 128 + 256;
+  constexpr size_t smem = 1024 + (TWO ? (size_t)6 * (BM * BK * 2 + BN / 2 * BK * 2) : (size_t)NSTAGE * (BM * BK * 2 + BN * BK * 2)) + NOUT_STAGE * 128 * 128 + 384;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, CL, AUX, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -542,7 +551,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap
   static int two = -1;          // cta_group::2 CTA pairs for the 256-wide tiles without an in-kernel row sum; RGNN_TC_2CTA=0: multicast pairs
   if (two < 0) { const char* e = getenv("RGNN_TC_2CTA"); two = (e && e[0] == '0') ? 0 : 1; }
   if constexpr (BN == 256) {
-    if (two == 1 && g_cluster == 2 && p.tiles_m >= 2 && !aux && !p.rowsum) return launch_cl<BN, 2, false, true>(a, b0, b1, p, st, o0, o1);
+    if (two == 1 && g_cluster == 2 && p.tiles_m >= 2 && !aux) return launch_cl<BN, 2, false, true>(a, b0, b1, p, st, o0, o1);
   }
   if (g_cluster == 2 && p.tiles_m >= 2) return aux ? launch_cl<BN, 2, true>(a, b0, b1, p, st, o0, o1) : launch_cl<BN, 2, false>(a, b0, b1, p, st, o0, o1);
   return aux ? launch_cl<BN, 1, true>(a, b0, b1, p, st, o0, o1) : launch_cl<BN, 1, false>(a, b0, b1, p, st, o0, o1);
