@@ -46,6 +46,7 @@ struct TcParams {
   int64_t ld0, ld1;     // NCHW: elements per robot in out0/out1; ROW/PARTIAL: ld0 = row stride
   const float* bias; const void* aux;
   float alpha, beta;    // ROW epilogue: v = alpha * acc [+ beta * aux[m,n] with RGNN_EPI_ADD_AUX] (GCN2Conv identity mapping)
+  int nchw_split;       // NCHW epilogue: 1 = the two warpgroups take two slabs each (one staging buffer per warpgroup)
   int n_fast;           // tile order: 1 = the N-tiles of one M-tile group are consecutive work items (A is the big operand: linear layers)
   float* rowsum;        // WGRAD: if non-null, fp32 [splits, M] partial row sums of A (the bias gradient of the 1x1 conv) are written here
 };
@@ -337,11 +338,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // NCHW (conv) tiles are limited by the output write traffic, not by these warps: one warpgroup walks all slabs with both
         // staging buffers (store of slab j overlaps the staging of slab j+1).  ROW tiles (edge-MLP, short K, sigmoid) are limited
         // by epilogue issue: the two warpgroups take one column half each, one buffer per warpgroup.
-        const int j_lo = nchw ? 0 : eh * (BN / 128), j_hi = nchw ? (eh == 0 ? BN / 64 : 0) : (eh + 1) * (BN / 128);
+        const bool split_wg = !nchw || p.nchw_split;
+        const int j_lo = split_wg ? eh * (BN / 128) : 0, j_hi = split_wg ? (eh + 1) * (BN / 128) : (eh == 0 ? BN / 64 : 0);
 #pragma unroll 1
         for (int j = j_lo; j < j_hi; ++j) {
           const int node = tn * (BN / 64) + j;
-          const uint32_t stg = out_stage + (nchw ? (j & 1) : eh) * OUT_STAGE_BYTES;
+          const uint32_t stg = out_stage + (split_wg ? eh : (j & 1)) * OUT_STAGE_BYTES;
           const int64_t n0 = (int64_t)tn * BN + j * 64;
           if (use_aux) {
             if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -418,7 +420,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           // only now wait for the staging buffer: the previous store's shared-memory read overlapped the TMEM load and the arithmetic
           if (!use_aux) {                         // (with an aux operand the buffer was claimed before it was parked there)
             if (ew == 0 && lane == 0) {
-              if (nchw) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              if (!split_wg) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
               else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             }
             epi_bar_sync(bar_id);
@@ -615,7 +617,8 @@ extern "C" int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const 
     int rc = make_map(&tb1, x1, 3, d, s, b); if (rc) return rc;
   } else tb1 = tb0;
   TcParams p = {};
-  p.load_mode = LOAD_CONV; p.epi_mode = EPI_NCHW; p.epi_flags = bias ? RGNN_EPI_BIAS_M : 0; p.alpha = 1.0f;
+  p.load_mode = LOAD_CONV; p.epi_mode = EPI_NCHW;
+  { static int sp = -1; if (sp < 0) { const char* e = getenv("RGNN_TC_NCHW_SPLIT"); sp = e ? atoi(e) : 0; } p.nchw_split = sp; } p.epi_flags = bias ? RGNN_EPI_BIAS_M : 0; p.alpha = 1.0f;
   p.tiles_m = (int)(M / 128); p.tiles_n = (int)((nodes + BN / 64 - 1) / (BN / 64)); p.splits = 1;
   p.kblocks = (int)(K / 64); p.kb_per_split = p.kblocks; p.kb_b0 = (int)(c0 / 64);
   p.nodes = (int)nodes; p.M = M; p.N = nodes * 64;
