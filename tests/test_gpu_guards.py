@@ -45,6 +45,11 @@ def test_conv1x1_guards(R, nodes, c0, c1, m0, m1):
     o0.check("conv out0")
     if o1:
         o1.check("conv out1")
+    # values too (odd M-tile counts leave the second CTA of the last pair without a tile)
+    x = torch.cat([x0] + ([x1] if c1 else []), 1).float()
+    ref = torch.einsum("ok,vkp->vop", w.float(), x)
+    got = torch.cat([o0.view] + ([o1.view] if o1 else []), 1).float()
+    assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
 
 
 @pytest.mark.parametrize("m,n,k", [(77, 128, 64), (300, 256, 128), (129, 384, 64)])
@@ -54,6 +59,8 @@ def test_gemm_tn_and_nn_guards(R, m, n, k):
     c = Guarded((m, n), torch.bfloat16, 555.0)
     L.check(L.lib().rgnn_tc_gemm_tn(L.ptr(a), k, L.ptr(b), k, L.ptr(c.view), n, m, n, k, 0, None, None, 1.0, 0.0, L.stream()), "tn")
     c.check("gemm_tn")
+    ref = a.float() @ b.float().t()
+    assert float((c.view.float() - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
     kk = 130
     at, bt = bf(kk, 256, seed=6), bf(kk, n, seed=7)
     cf = Guarded((256, n), torch.float32, 9e9)
