@@ -618,7 +618,11 @@ extern "C" int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const 
   } else tb1 = tb0;
   TcParams p = {};
   p.load_mode = LOAD_CONV; p.epi_mode = EPI_NCHW;
-  { static int sp = -1; if (sp < 0) { const char* e = getenv("RGNN_TC_NCHW_SPLIT"); sp = e ? atoi(e) : 0; } p.nchw_split = sp; } p.epi_flags = bias ? RGNN_EPI_BIAS_M : 0; p.alpha = 1.0f;
+  // short reductions (dX at F = 512: 8 k-blocks per tile) are paced by the epilogue, not the MMAs: both warpgroups then take two
+  // slabs each (dX 1.25 -> 1.12 ms); long ones keep one warpgroup with both staging buffers (the split costs the forward 0.05 ms).
+  // RGNN_TC_NCHW_SPLIT=0|1 forces either.
+  { static int sp = -2; if (sp == -2) { const char* e = getenv("RGNN_TC_NCHW_SPLIT"); sp = e ? atoi(e) : -1; }
+    p.nchw_split = sp >= 0 ? sp : (K / 64 <= 12); } p.epi_flags = bias ? RGNN_EPI_BIAS_M : 0; p.alpha = 1.0f;
   p.tiles_m = (int)(M / 128); p.tiles_n = (int)((nodes + BN / 64 - 1) / (BN / 64)); p.splits = 1;
   p.kblocks = (int)(K / 64); p.kb_per_split = p.kblocks; p.kb_b0 = (int)(c0 / 64);
   p.nodes = (int)nodes; p.M = M; p.N = nodes * 64;
