@@ -8,10 +8,12 @@
 //   nn.Linear(F,2F)+Sigmoid      dgl/model/models.py:149-150      -> gemm_tn  : Z = sigmoid(A1 . W2^T + b2)
 //   its autograd                                                  -> gemm_tn  : dA1 = (dZ . W2) * [A1>0] ;  gemm_nn : dW2 = dZ^T . A1
 //
-// One persistent, warp-specialised kernel (1 CTA / SM, 384 threads):
-//   warp 0   TMA producer   (4-stage ring of {A 128x64, B BNx64} bf16 tiles, mbarrier full/empty)
-//   warp 1   MMA issuer     (one elected lane; 4 x tcgen05.mma 128xBNx16 per stage; tcgen05.commit frees the stage)
+// One persistent, warp-specialised kernel (1 CTA / SM, 384 threads), launched as clusters of two CTAs = one tcgen05 CTA pair:
+//   warp 0   TMA producer   (6-stage ring of {A 128x64, own half of B (BN/2)x64} bf16 tiles; all bytes counted on the leader's mbarrier)
+//   warp 1   MMA issuer     (leader CTA only, one elected lane; 4 x tcgen05.mma.cta_group::2 256xBNx16 per stage over both SMs;
+//                            multicast tcgen05.commit frees the stage in both CTAs)
 //   warp 2   TMEM allocator (2 x BN fp32 columns = double-buffered accumulator, epilogue overlaps the next tile)
+//   (RGNN_TC_2CTA=0 / AUX epilogues: cta_group::1 MMAs per CTA, 4-stage ring of {A, whole B}, the B halves TMA-multicast)
 //   warps 4-11 epilogue     (two warpgroups, one per column half: tcgen05.ld 32x32b.x32 -> bias / sigmoid / relu-mask ->
 //                            bf16 slabs staged in swizzled shared memory and written by TMA stores, or fp32 split partials)
 // NCHW feature maps are consumed where they lie: a [64 ch x 64 px] slab of one robot is exactly one MN-major
