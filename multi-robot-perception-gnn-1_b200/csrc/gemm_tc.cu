@@ -13,7 +13,7 @@
 //   warp 1   MMA issuer     (leader CTA only, one elected lane; 4 x tcgen05.mma.cta_group::2 256xBNx16 per stage over both SMs;
 //                            multicast tcgen05.commit frees the stage in both CTAs)
 //   warp 2   TMEM allocator (2 x BN fp32 columns = double-buffered accumulator, epilogue overlaps the next tile)
-//   (RGNN_TC_2CTA=0 / AUX epilogues: cta_group::1 MMAs per CTA, 4-stage ring of {A, whole B}, the B halves TMA-multicast)
+//   (RGNN_TC_2CTA=0: cta_group::1 MMAs per CTA, 4-stage ring of {A, whole B}, the B halves TMA-multicast)
 //   warps 4-11 epilogue     (two warpgroups, one per column half: tcgen05.ld 32x32b.x32 -> bias / sigmoid / relu-mask ->
 //                            bf16 slabs staged in swizzled shared memory and written by TMA stores, or fp32 split partials)
 // NCHW feature maps are consumed where they lie: a [64 ch x 64 px] slab of one robot is exactly one MN-major
@@ -555,7 +555,8 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap
   static int two = -1;          // cta_group::2 CTA pairs for the 256-wide tiles without an in-kernel row sum; RGNN_TC_2CTA=0: multicast pairs
   if (two < 0) { const char* e = getenv("RGNN_TC_2CTA"); two = (e && e[0] == '0') ? 0 : 1; }
   if constexpr (BN == 256) {
-    if (two == 1 && g_cluster == 2 && p.tiles_m >= 2 && !aux) return launch_cl<BN, 2, false, true>(a, b0, b1, p, st, o0, o1);
+    if (two == 1 && g_cluster == 2 && p.tiles_m >= 2)
+      return aux ? launch_cl<BN, 2, true, true>(a, b0, b1, p, st, o0, o1) : launch_cl<BN, 2, false, true>(a, b0, b1, p, st, o0, o1);
   }
   if (g_cluster == 2 && p.tiles_m >= 2) return aux ? launch_cl<BN, 2, true>(a, b0, b1, p, st, o0, o1) : launch_cl<BN, 2, false>(a, b0, b1, p, st, o0, o1);
   return aux ? launch_cl<BN, 1, true>(a, b0, b1, p, st, o0, o1) : launch_cl<BN, 1, false>(a, b0, b1, p, st, o0, o1);
