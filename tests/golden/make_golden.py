@@ -275,6 +275,31 @@ def golden_script_shape():
     npz("script_shape_cases.npz", **out)
 
 
+def golden_script_c1():
+    """C1 as the script runs it (train_camera_warehouse_gcn.sh: mobilenetv2 F=1280, one layer, NO compress conv, fp32):
+    G=8, K=5, P=8x8.  The block output is cat((h, g_h), 1) (models.py:182); strided samples + checksums only."""
+    f = 1280
+    sb = O.synthetic_batch(8, 5, f, p=64, seed=1)
+    p = O.init_layer_params(f, compress_gcn=False, seed=1)
+    gcn = ref.GCN(types.SimpleNamespace(feature_dim=f))
+    load_layer(gcn, None, p)
+    g = ref_graph(sb)
+    h = sb["h"].reshape(40, f, 8, 8).clone().requires_grad_()
+    g_h = run_ref_layer(gcn, g, h, sb["pose"])
+    y = torch.cat((h, g_h), dim=1)                                    # models.py:182, compress_gcn off
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(101))
+    y.backward(dy)
+    idx = np.arange(0, 40 * 2 * f * 64, 997)
+    idx_h = np.arange(0, 40 * f * 64, 997)
+    l0, l2 = gcn.edge_encoder.layers[0], gcn.edge_encoder.layers[2]
+    npz("script_c1_nocompress.npz", idx=idx, idx_h=idx_h, h_sum=np.float64(sb["h"].double().sum().item()),
+        dy_sum=np.float64(dy.double().sum().item()),
+        y_s=y.detach().reshape(-1).numpy()[idx], y_absmax=np.float32(y.detach().abs().max().item()),
+        dh_s=h.grad.reshape(-1).numpy()[idx_h], dh_absmax=np.float32(h.grad.abs().max().item()),
+        dw2_s=l2.weight.grad.reshape(-1).numpy()[::1009], dw2_absmax=np.float32(l2.weight.grad.abs().max().item()),
+        dw1=l0.weight.grad.numpy(), db1=l0.bias.grad.numpy(), db2=l2.bias.grad.numpy())
+
+
 def golden_pose():
     """dgl/utils.py:80-85 self-check inputs; expected values printed by the reference."""
     sys.path.insert(0, "/root/reference/dgl")
@@ -310,7 +335,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
     a = ap.parse_args()
-    todo = dict(csr=golden_csr, layers=golden_layers, blocks=golden_blocks, script=golden_script_shape, pose=golden_pose, keys=golden_model_keys)
+    todo = dict(csr=golden_csr, layers=golden_layers, blocks=golden_blocks, script=golden_script_shape, c1=golden_script_c1, pose=golden_pose, keys=golden_model_keys)
     for k, fn_ in todo.items():
         if a.only in (None, k):
             print("==", k)

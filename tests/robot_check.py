@@ -1,4 +1,4 @@
-"""Shared checker used by __graft_entry__.smoke() and bench.py: run the CUDA GNN block and the CPU oracle on the
+"""Shared checker used by __graft_entry__.smoke() and the GPU tests: run the CUDA GNN block and the CPU oracle on the
 same seeded inputs and compare outputs + every gradient (normalised max error)."""
 import types
 

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
 def test_host_pipeline_matches_single_shot(R, dtype, tol):
-    from multi_robot_check import make_block
+    from robot_check import make_block
     from oracle import gnn_oracle as O
     G, K, F = 24, 5, 128
     blk, _ = make_block(R, O, F, True, True)
@@ -51,7 +51,7 @@ def test_host_pipeline_matches_single_shot(R, dtype, tol):
 @pytest.mark.parametrize("dtype,f", [(torch.bfloat16, 512), (torch.float32, 64)])
 def test_cuda_graph_replay_matches_eager(R, dtype, f):
     """Script shape (G=8, K=5): the captured step must reproduce the eager step bit for bit, for fresh inputs on every replay."""
-    from multi_robot_check import make_block
+    from robot_check import make_block
     from oracle import gnn_oracle as O
     G, K = 8, 5
     blk, _ = make_block(R, O, f, True, True)

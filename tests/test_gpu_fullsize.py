@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 
 def make(R, f, comp=True, multi=True, seed=1):
-    from multi_robot_check import make_block
+    from robot_check import make_block
     from oracle import gnn_oracle as O
     blk, _ = make_block(R, O, f, comp, multi, seed=seed)
     return blk.cuda()

@@ -26,11 +26,12 @@ def _free_port():
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import robot_gnn_b200 as R
-    from multi_robot_check import make_block
+    from robot_check import make_block
     from oracle import gnn_oracle as O
     G, K, F = 16, 5, 128
     blk, _ = make_block(R, O, F, True, True)
@@ -52,7 +53,7 @@ def _worker(rank, world, port, q):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 def test_two_rank_gradients_equal_single_rank(R):
     import torch.multiprocessing as mp
-    from multi_robot_check import make_block
+    from robot_check import make_block
     from oracle import gnn_oracle as O
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

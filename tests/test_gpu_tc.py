@@ -97,7 +97,7 @@ def test_cast_weights(R):
 @pytest.mark.parametrize("g_,k,f", [(6, 5, 256), (8, 5, 512), (3, 4, 384), (2, 7, 640), (1, 2, 128)])
 def test_block_tc_matches_cuda_core_path_and_oracle(R, g_, k, f):
     """Whole 2-layer block in bf16: tensor-core path vs the CUDA-core rgnn_gemm path (same bf16 operands) and vs the fp64 oracle."""
-    from multi_robot_check import check_block, make_block
+    from robot_check import check_block, make_block
     from oracle import gnn_oracle as O
     errs = check_block(R, O, g_, k, f, torch.bfloat16, 2e-2)
     assert max(errs.values()) <= 4e-2
@@ -203,7 +203,7 @@ def test_fused_film_conv_forward(R, k, gN, f, fo):
 def test_block_with_fused_prologue_matches_unfused(R, train):
     """The opt-in fused path (USE_FUSED) inside the whole block: same outputs / gradients as the default path; in eval the
     aggregated features are never written."""
-    from multi_robot_check import make_block
+    from robot_check import make_block
     from oracle import gnn_oracle as O
     G, K, F = 6, 5, 256
     sb = O.synthetic_batch(G, K, F, p=64, seed=4)
