@@ -33,13 +33,20 @@ def save_graphs(filename, g_list, labels=None):
 
 def load_graphs(filename, idx_list=None):
     """-> (list of graphs, labels dict) like dgl.load_graphs (dataloader.py:174)."""
-    blob = torch.load(filename, weights_only=False)
+    try:        # the payload is tensors / lists / dicts / numbers only: the safe unpickler suffices (a tampered cache cannot run code)
+        blob = torch.load(filename, weights_only=True)
+    except Exception as exc:
+        raise ValueError(f"{filename} is not a robot-gnn graph cache (caches written by real DGL must be rebuilt): {exc}") from exc
     if not isinstance(blob, dict) or blob.get("format") != "robot-gnn-graphs-v1":
         raise ValueError(f"{filename} is not a robot-gnn graph cache (caches written by real DGL must be rebuilt)")
     items = blob["graphs"] if idx_list is None else [blob["graphs"][i] for i in idx_list]
     out = []
     for it in items:
-        g = _rg.RobotGraph(it["src"], it["dst"], it["bnn"], it["bne"], it.get("complete_k", 0))
+        # complete_k is re-derived from the edge lists on the host, never trusted from the file (a wrong value would route the
+        # batch to the compiled-topology kernels)
+        src, dst, bnn = it["src"].to(torch.int64).reshape(-1), it["dst"].to(torch.int64).reshape(-1), [int(v) for v in it["bnn"]]
+        ck = _rg.complete_k_of(src, dst, bnn)
+        g = _rg.RobotGraph(src, dst, bnn, it["bne"], ck)
         g.ndata, g.edata = dict(it["ndata"]), dict(it["edata"])
         out.append(g)
     return out, (blob.get("labels") or {})

@@ -5,13 +5,13 @@ Import name: the directory is called ``multi-robot-perception-gnn-1_b200`` (not 
 ``import robot_gnn_b200`` (repo-root alias module) loads it.
 """
 from . import _lib
-from .graph import RobotGraph, graph, batch, robot_batch, function, relative_pose_edges
+from .graph import RobotGraph, graph, batch, robot_batch, function, relative_pose_edges, complete_k_of
 from . import functional
 from . import parallel
 from .engine import HostPipeline, GraphedStep
 from .functional import film_mean, film_mean_cat, copy_u_reduce, edge_mlp, compress, linear, axpby
 from .layers import edge_encoder, GCN, GNNBlock, GraphConv, GCN2Conv, gnn_slice
 
-__all__ = ["RobotGraph", "graph", "batch", "robot_batch", "function", "relative_pose_edges", "functional", "film_mean", "film_mean_cat",
+__all__ = ["RobotGraph", "graph", "batch", "robot_batch", "function", "relative_pose_edges", "complete_k_of", "functional", "film_mean", "film_mean_cat",
            "copy_u_reduce", "edge_mlp", "compress", "linear", "axpby", "edge_encoder", "GCN", "GNNBlock",
            "GraphConv", "GCN2Conv", "HostPipeline", "GraphedStep", "gnn_slice"]

@@ -491,7 +491,7 @@ extern "C" int rgnn_aggregate(int dtype, const void* x, int64_t ldx, const void*
     RGNN_REQUIRE(!z || (reinterpret_cast<uintptr_t>(z) & (2 * es - 1)) == 0, RGNN_E_ALIGN, "rgnn_aggregate: z not pair-aligned");
     const int64_t total = N * F * P;
     int64_t blocks = (total + 255) / 256;
-    if (blocks > 32 * kNumSMs) blocks = 32 * kNumSMs;
+    if (blocks > 32 * num_sms()) blocks = 32 * num_sms();
     if (dtype == RGNN_F32) k_agg_generic<float, 1><<<(unsigned)blocks, 256, 0, st>>>(p);
     else k_agg_generic<__nv_bfloat16, 1><<<(unsigned)blocks, 256, 0, st>>>(p);
     RGNN_LAUNCH_CHECK("k_agg_generic<1>");
@@ -547,7 +547,7 @@ extern "C" int rgnn_aggregate(int dtype, const void* x, int64_t ldx, const void*
   }
   const int64_t total = N * (F * P / vec);
   int64_t blocks = (total + 255) / 256;
-  if (blocks > 32 * kNumSMs) blocks = 32 * kNumSMs;
+  if (blocks > 32 * num_sms()) blocks = 32 * num_sms();
   if (dtype == RGNN_F32) k_agg_generic<float, 4><<<(unsigned)blocks, 256, 0, st>>>(p);
   else k_agg_generic<__nv_bfloat16, 8><<<(unsigned)blocks, 256, 0, st>>>(p);
   RGNN_LAUNCH_CHECK("k_agg_generic");
@@ -573,7 +573,7 @@ extern "C" int rgnn_film_edge_grad(int dtype, const void* x, int64_t ldx, const 
   const int cpw = 32 / lpc;
   const int64_t warps = E * ((F + cpw - 1) / cpw);
   int64_t blocks = (warps + 7) / 8;
-  if (blocks > 64 * kNumSMs) blocks = 64 * kNumSMs;
+  if (blocks > 64 * num_sms()) blocks = 64 * num_sms();
   cudaStream_t st = as_stream(stream);
 #define LAUNCH(T, V)                                                                                              \
   k_film_edge_grad<T, V><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const T*>(x), ldx, static_cast<const T*>(dagg), ldd, \
@@ -638,13 +638,13 @@ extern "C" int rgnn_film_backward(int dtype, const void* h, int64_t ldh, const v
   p.noff = noff32; p.F = (int)F; p.P = (int)P; p.fuse_sig = fuse_sigmoid_grad;
   const size_t smem = (size_t)tile_off + 2 * (size_t)maxK * CT * row_bytes_per_ch + (size_t)maxE * 4 * CT * es;
   cudaStream_t st = as_stream(stream);
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[dtype]) {
+  static DeviceOnce once[2];
+  if (once[dtype].need()) {
     cudaError_t e = dtype == RGNN_F32
         ? cudaFuncSetAttribute(k_film_bwd_staged<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)
         : cudaFuncSetAttribute(k_film_bwd_staged<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_film_bwd_staged)");
-    attr_done[dtype] = true;
+    once[dtype].mark();
   }
   if (dtype == RGNN_F32) k_film_bwd_staged<float><<<(unsigned)blocks, 256, smem, st>>>(p, (int)CT, maxK, maxE, tile_off);
   else k_film_bwd_staged<__nv_bfloat16><<<(unsigned)blocks, 256, smem, st>>>(p, (int)CT, maxK, maxE, tile_off);

@@ -20,6 +20,18 @@ int cuda_fail(cudaError_t e, const char* what) {
   return (int)e;
 }
 
+int num_sms() {
+  static std::atomic<int> cache[64];
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return 148;
+  int n = cache[d].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n <= 0) n = 148;
+    cache[d].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include "../../include/robot_gnn.h"
 
 namespace rgnn {
@@ -30,7 +31,25 @@ void count_launch();
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-constexpr int kNumSMs = 148;  // B200
+// SM count of the CURRENT device (148 on B200), cached per device: grids are sized in multiples of it.
+int num_sms();
+
+// One-time per-DEVICE setup guard.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and occupancy answers belong to a device /
+// context, and autograd runs backward on one thread per device: a process that drives several GPUs must opt in on each of them
+// (a process-wide `static bool` would skip the second GPU and every launch above 48 KB would fail there).  Bit d = device d done.
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool need() const {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d < 0 || d >= 64 || !((mask.load(std::memory_order_acquire) >> d) & 1ull);
+  }
+  void mark() {
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d >= 0 && d < 64) mask.fetch_or(1ull << d, std::memory_order_release);
+  }
+};
 
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

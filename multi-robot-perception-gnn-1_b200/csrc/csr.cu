@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(128) k_build_csr(const int64_t* __restrict__ s
       if (d >= 0 && (md & lt) == 0) cin[d] += __popc(md);
       __syncwarp();
     }
-    if (__any_sync(0xffffffffu, bad)) { if (lane == 0) atomicOr(o.status, 1); }
+    const bool any_bad = __any_sync(0xffffffffu, bad);
+    if (any_bad && lane == 0) atomicOr(o.status, 1);
     // ---- phase 2: exclusive scan over the graph's nodes
     int carry_in = (int)e0, carry_out = (int)e0;
     for (int64_t base = n0; base < n1; base += 32) {
@@ -142,8 +143,11 @@ __global__ void __launch_bounds__(128) k_build_csr(const int64_t* __restrict__ s
       const int64_t e = base + lane;
       const bool act = e < e1;
       int64_t s = act ? src[e] : -1, d = act ? dst[e] : -1;
-      if (act) { o.src32[e] = (int32_t)s; o.dst32[e] = (int32_t)d; }
-      if (act && (s < n0 || s >= n1 || d < n0 || d >= n1)) s = d = -1;
+      const bool out_of_graph = act && (s < n0 || s >= n1 || d < n0 || d >= n1);
+      // an edge that leaves its graph (status bit 0; DGL raises at construction) is kept IN BOUNDS for the kernels that walk the
+      // edge list: both endpoints collapse onto the graph's first node, so nothing is gathered from another graph or past N
+      if (act) { o.src32[e] = (int32_t)(out_of_graph ? (n1 > n0 ? n0 : 0) : s); o.dst32[e] = (int32_t)(out_of_graph ? (n1 > n0 ? n0 : 0) : d); }
+      if (out_of_graph) s = d = -1;
       const unsigned ms = __match_any_sync(0xffffffffu, s), md = __match_any_sync(0xffffffffu, d);
       if (s >= 0) {
         const int pos = cout[s] + __popc(ms & lt);
@@ -160,6 +164,24 @@ __global__ void __launch_bounds__(128) k_build_csr(const int64_t* __restrict__ s
       __syncwarp();
       if (s >= 0 && (ms & lt) == 0) cout[s] += __popc(ms);
       if (d >= 0 && (md & lt) == 0) cin[d] += __popc(md);
+      __syncwarp();
+    }
+    if (any_bad && n1 > n0) {
+      // dropped edges leave unplaced slots at the end of this graph's CSR slice, and the last node's range runs up to the next
+      // graph's first slot: fill them with (the last node itself, the graph's first edge) - in-bounds by construction instead
+      // of uninitialised memory.  The batch is still flagged invalid (status bit 0, RobotGraph.validate()).
+      __syncwarp();
+      const int end_in = cin[n1 - 1], end_out = cout[n1 - 1];
+      for (int64_t pos = end_in + lane; pos < e1; pos += 32) {
+        o.in_src32[pos] = (int32_t)(n1 - 1); o.in_eid32[pos] = (int32_t)e0;
+        if (o.in_src) o.in_src[pos] = n1 - 1;
+        if (o.in_eid) o.in_eid[pos] = e0;
+      }
+      for (int64_t pos = end_out + lane; pos < e1; pos += 32) {
+        o.out_dst32[pos] = (int32_t)(n1 - 1); o.out_eid32[pos] = (int32_t)e0;
+        if (o.out_dst) o.out_dst[pos] = n1 - 1;
+        if (o.out_eid) o.out_eid[pos] = e0;
+      }
       __syncwarp();
     }
     // ---- restore ptr32 from the advanced cursors: cursor[v] is now ptr[v+1]; shift right by one node
@@ -197,7 +219,7 @@ extern "C" int rgnn_batch_graphs(const int64_t* local_src, const int64_t* local_
   if (E > 0 && G > 0) {
     const int wpb = 8;
     int64_t blocks = (G + wpb - 1) / wpb;
-    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
     k_shift_ids<<<(unsigned)blocks, wpb * 32, 0, st>>>(local_src, local_dst, noff, eoff, G, src, dst);
     RGNN_LAUNCH_CHECK("k_shift_ids");
   }
@@ -234,7 +256,7 @@ extern "C" int rgnn_build_batched_csr(const int64_t* src, const int64_t* dst, in
   }
   const int wpb = 4;
   int64_t blocks = (G + wpb - 1) / wpb;
-  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
   k_build_csr<<<(unsigned)blocks, wpb * 32, 0, st>>>(src, dst, noff, eoff, G, N, E, o);
   RGNN_LAUNCH_CHECK("k_build_csr");
   return 0;

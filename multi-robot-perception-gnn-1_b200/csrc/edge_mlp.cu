@@ -288,7 +288,7 @@ extern "C" int rgnn_edge_mlp1_bwd(int dtype, const float* pose, const void* da1,
     int cv = 32;
     while (cv < fvn && cv < 256) cv <<= 1;
     const int fbx = (fvn + cv - 1) / cv;
-    int64_t chunks2 = (4 * kNumSMs + fbx - 1) / fbx;          // ~4 blocks of 256 threads per SM
+    int64_t chunks2 = (4 * num_sms() + fbx - 1) / fbx;          // ~4 blocks of 256 threads per SM
     const int64_t maxc = (E + 63) / 64;
     if (chunks2 > maxc) chunks2 = maxc;
     if (chunks2 < 1) chunks2 = 1;
@@ -302,7 +302,7 @@ extern "C" int rgnn_edge_mlp1_bwd(int dtype, const float* pose, const void* da1,
     return 0;
   }
   const int fb = vec_ok ? (int)((F / vec + 63) / 64) : (int)((F + 63) / 64);
-  int64_t chunks = (8 * kNumSMs + fb - 1) / fb;
+  int64_t chunks = (8 * num_sms() + fb - 1) / fb;
   const int64_t max_chunks = (E + 63) / 64;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;

@@ -420,7 +420,7 @@ static int launch_fwd(int K, const T* x, int64_t ldx, const T* z, T* out, int64_
                       cudaStream_t st) {
   const int64_t total = G * ((int64_t)F * P / Vec16<T>::N);
   int64_t blocks = (total + 255) / 256;
-  const int64_t resident = (K <= 5 ? 2 : 1) * kNumSMs;   // persistent: pipelined CTAs, as many as stay resident
+  const int64_t resident = (K <= 5 ? 2 : 1) * num_sms();   // persistent: pipelined CTAs, as many as stay resident
   if (blocks > resident) blocks = resident;
   if (blocks < 1) return 0;
 #define RGNN_CASE(KK) case KK: k_film_fwd_complete<T, KK, HAS_Z><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, z, out, ldout, copy_to, G, F, P); break;
@@ -440,14 +440,14 @@ static int launch_bwd_lpc(int K, const T* h, int64_t ldh, const T* dagg, int64_t
   if (g_bwd_tma == 1 && F * LPC >= TMA_TPB && total > 0) {
     const size_t smem = 128 + (size_t)3 * K * TMA_TPB * 16;
     int64_t tblocks = (total + TMA_TPB - 1) / TMA_TPB;
-    if (tblocks > kNumSMs) tblocks = kNumSMs;
+    if (tblocks > num_sms()) tblocks = num_sms();
 #define RGNN_CASE(KK)                                                                                                                   \
   case KK: {                                                                                                                           \
-    static bool done = false;                                                                                                          \
-    if (!done) {                                                                                                                       \
+    static DeviceOnce once;                                                                                                          \
+    if (once.need()) {                                                                                                                       \
       cudaError_t e = cudaFuncSetAttribute(k_film_bwd_complete_tma<T, KK, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_film_bwd_complete_tma)");                                      \
-      done = true;                                                                                                                     \
+      once.mark();                                                                                                                     \
     }                                                                                                                                  \
     k_film_bwd_complete_tma<T, KK, LPC><<<(unsigned)tblocks, TMA_TPB, smem, st>>>(h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sig); \
   } break;
@@ -457,7 +457,7 @@ static int launch_bwd_lpc(int K, const T* h, int64_t ldh, const T* dagg, int64_t
     return 0;
   }
   int64_t blocks = (total + 255) / 256;
-  if (blocks > kNumSMs) blocks = kNumSMs;        // persistent: one pipelined CTA per SM
+  if (blocks > num_sms()) blocks = num_sms();        // persistent: one pipelined CTA per SM
   if (blocks < 1) return 0;
 #define RGNN_CASE(KK) case KK: k_film_bwd_complete<T, KK, LPC><<<(unsigned)blocks, 256, 0, st>>>(h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sig); break;
   switch (K) { RGNN_CASE(2) RGNN_CASE(3) RGNN_CASE(4) RGNN_CASE(5) RGNN_CASE(6) RGNN_CASE(7) RGNN_CASE(8) default: return RGNN_E_UNSUPPORTED; }
@@ -543,7 +543,7 @@ extern "C" int rgnn_check_complete(const int64_t* src, const int64_t* dst, int64
   if (num_edges == 0) return 0;
   RGNN_REQUIRE(src && dst, RGNN_E_ARG, "rgnn_check_complete: null edges");
   int64_t blocks = (num_edges + 255) / 256;
-  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   k_check_complete<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, dst, num_edges, (int)robots, status);
   RGNN_LAUNCH_CHECK("k_check_complete");
   return 0;

@@ -314,11 +314,11 @@ static int fwd_dense_t(int K, const T* x, int64_t ldx, const T* z, T* out, int64
   if (blocks >= (1ll << 31)) return RGNN_E_RANGE;
 #define RGNN_GO(RR, ZZ)                                                                                                    \
   do {                                                                                                                     \
-    static bool done = false;                                                                                              \
-    if (!done) {                                                                                                           \
+    static DeviceOnce once;                                                                                              \
+    if (once.need()) {                                                                                                           \
       cudaError_t e = cudaFuncSetAttribute(dense::k_film_fwd_dense<T, LPC, RR, ZZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_film_fwd_dense)");                                 \
-      done = true;                                                                                                         \
+      once.mark();                                                                                                         \
     }                                                                                                                      \
     dense::k_film_fwd_dense<T, LPC, RR, ZZ><<<(unsigned)blocks, 256, smem, st>>>(x, ldx, z, out, ldout, copy_to, K, F, P);  \
   } while (0)
@@ -338,11 +338,11 @@ static int bwd_dense_t(int K, const T* h, int64_t ldh, const T* dagg, int64_t ld
   if (smem > 200 * 1024) return RGNN_E_UNSUPPORTED;
   const int64_t blocks = G * (F / CT);
   if (blocks >= (1ll << 31)) return RGNN_E_RANGE;
-  static bool done = false;
-  if (!done) {
+  static DeviceOnce once;
+  if (once.need()) {
     cudaError_t e = cudaFuncSetAttribute(dense::k_film_bwd_dense<T, LPC, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_film_bwd_dense)");
-    done = true;
+    once.mark();
   }
   dense::k_film_bwd_dense<T, LPC, LPC><<<(unsigned)blocks, 256, smem, st>>>(h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, K, F, P, fuse_sig);
   RGNN_LAUNCH_CHECK("k_film_bwd_dense");

@@ -150,18 +150,19 @@ static int launch_fwd_ring_k(const T* x, int64_t ldx, const T* z, T* out, int64_
   constexpr int NST = ring_fwd_stages<K>();
   constexpr size_t smem = 128 + (size_t)NST * (K * S::PIECE + (HAS_Z ? S::NE * S::ZPIECE : 0));
   auto kern = k_film_fwd_ring<T, K, HAS_Z, NST>;
-  static bool done = false;
+  static DeviceOnce once;
   static int per_sm = 1;
-  if (!done) {
+  if (once.need()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_film_fwd_ring)");
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RING_TPB + 32, smem);
+    int occ = 1;          // (same answer on every B200: concurrent per-device threads store the same value)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RING_TPB + 32, smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(k_film_fwd_ring)");
-    if (per_sm < 1) per_sm = 1;
-    done = true;
+    per_sm = occ < 1 ? 1 : occ;
+    once.mark();
   }
   const int64_t items = G * (F / S::CH);
-  int64_t blocks = (int64_t)per_sm * kNumSMs;
+  int64_t blocks = (int64_t)per_sm * num_sms();
   if (blocks > items) blocks = items;
   if (blocks < 1) return 0;
   kern<<<(unsigned)blocks, RING_TPB + 32, smem, st>>>(x, ldx, z, out, ldout, copy_to, G, F);
@@ -270,19 +271,20 @@ static int launch_mean_mix_k(const T* x, int64_t ldx, const T* addend, int64_t l
   constexpr int NST = (96 * 1024) / STAGE >= 6 ? 6 : ((96 * 1024) / STAGE >= 3 ? (96 * 1024) / STAGE : 3);
   constexpr size_t smem = 128 + (size_t)NST * STAGE;
   auto kern = k_mean_mix_ring<T, K, HAS_ADD, NST>;
-  static bool done = false;
+  static DeviceOnce once;
   static int per_sm = 1;
-  if (!done) {
+  if (once.need()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_mean_mix_ring)");
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RING_TPB + 32, smem);
+    int occ = 1;          // (same answer on every B200: concurrent per-device threads store the same value)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RING_TPB + 32, smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(k_mean_mix_ring)");
-    if (per_sm < 1) per_sm = 1;
-    done = true;
+    per_sm = occ < 1 ? 1 : occ;
+    once.mark();
   }
   const int64_t ipg = row / (RING_TPB * S::VEC);
   const int64_t items = G * ipg;
-  int64_t blocks = (int64_t)per_sm * kNumSMs;
+  int64_t blocks = (int64_t)per_sm * num_sms();
   if (blocks > items) blocks = items;
   if (blocks < 1) return 0;
   kern<<<(unsigned)blocks, RING_TPB + 32, smem, st>>>(x, ldx, addend, ldadd, out, ldout, G, (int)ipg, sa, sb);
@@ -503,15 +505,15 @@ static int launch_bwd_ring_k(const T* h, int64_t ldh, const T* dagg, int64_t ldd
   constexpr int NST = (200 * 1024) / S::stage(3) >= 4 ? 4 : ((200 * 1024) / S::stage(3) >= 3 ? 3 : 2);
   const size_t smem = S::HEAD + (size_t)NST * S::stage(addend ? 3 : 2);
   auto kern = k_film_bwd_ring<T, K, TPB, NST>;
-  static bool done = false;
-  if (!done) {
+  static DeviceOnce once;
+  if (once.need()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::HEAD + NST * S::stage(3));
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_film_bwd_ring)");
-    done = true;
+    once.mark();
   }
   if (F % S::CH) return RGNN_E_UNSUPPORTED;
   const int64_t items = G * (F / S::CH);
-  int64_t blocks = kNumSMs;
+  int64_t blocks = num_sms();
   if (blocks > items) blocks = items;
   if (blocks < 1) return 0;
   kern<<<(unsigned)blocks, 2 * TPB + 32, smem, st>>>(h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, fuse_sig);

@@ -343,18 +343,18 @@ static int launch_fused(const void* W, const void* h, const void* z, const float
     const uint32_t b[2] = {64, 128};
     int rc = make_map(&ty, y, 2, d, s, b); if (rc) return rc;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce once;
+  if (once.need()) {
     cudaError_t e = cudaFuncSetAttribute(k_conv_film_fused<KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_conv_film_fused)");
-    attr_done = true;
+    once.mark();
   }
   FusedParams p = {};
   p.tiles_m = (int)(Fo / BM); p.graphs = graphs; p.F = (int)F; p.Fo = (int)Fo; p.kblocks = (int)(F / BKF);
   p.bias = bias; p.store_g = gout != nullptr;
   { const char* e = getenv("RGNN_FUSED_DEBUG"); p.debug = e ? atoi(e) : 0; }
   const int64_t work = graphs * p.tiles_m;
-  const int grid = (int)(work < kNumSMs ? work : kNumSMs);
+  const int grid = (int)(work < num_sms() ? work : num_sms());
   if (grid < 1) return 0;
   k_conv_film_fused<KR><<<grid, NTHR, C::SMEM, st>>>(tw, th, tz, ty, tg, p);
   RGNN_LAUNCH_CHECK("k_conv_film_fused");

@@ -326,11 +326,11 @@ static int launch_sgemm_v(GemmParams& p, cudaStream_t st) {
   const size_t smem = 2 * VK * VA_LD * sizeof(float2) + 2 * VK * (bn2 + 4) * sizeof(float);
 #define RGNN_SG(AK, BNF, W)                                                                                            \
   {                                                                                                                    \
-    static bool done = false;                                                                                          \
-    if (!done) {                                                                                                       \
+    static DeviceOnce once;                                                                                          \
+    if (once.need()) {                                                                                                       \
       cudaError_t e = cudaFuncSetAttribute(k_sgemm_v<AK, BNF, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_sgemm_v)");                                    \
-      done = true;                                                                                                     \
+      once.mark();                                                                                                     \
     }                                                                                                                  \
     k_sgemm_v<AK, BNF, W><<<(unsigned)blocks, 256, smem, st>>>(p);                                                     \
   }
@@ -541,7 +541,7 @@ extern "C" int rgnn_gemm(int a_dtype, const void* A, int64_t sAz, int64_t sAr, i
   }
   if (p.split > 1) {
     int64_t rb = (M * N + 255) / 256;
-    if (rb > 16 * kNumSMs) rb = 16 * kNumSMs;
+    if (rb > 16 * num_sms()) rb = 16 * num_sms();
     k_splitk_reduce<<<(unsigned)rb, 256, 0, st>>>(p);
     RGNN_LAUNCH_CHECK("k_splitk_reduce");
   }
@@ -562,7 +562,7 @@ extern "C" int rgnn_sigmoid_grad(int dtype, const void* z, const void* dz, void*
   if (n == 0) return 0;
   RGNN_REQUIRE(z && dz && dzpre, RGNN_E_ARG, "rgnn_sigmoid_grad: null pointer");
   int64_t blocks = (n + 255) / 256;
-  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
   cudaStream_t st = as_stream(stream);
   if (dtype == RGNN_F32) k_sigmoid_grad<float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(z), static_cast<const float*>(dz), static_cast<float*>(dzpre), n);
   else k_sigmoid_grad<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(z), static_cast<const __nv_bfloat16*>(dz), static_cast<__nv_bfloat16*>(dzpre), n);
@@ -585,7 +585,7 @@ extern "C" int rgnn_axpby(int dtype, float a, const void* x, float b, const void
   if (n == 0) return 0;
   RGNN_REQUIRE(x && y && out, RGNN_E_ARG, "rgnn_axpby: null pointer");
   int64_t blocks = (n + 255) / 256;
-  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
   cudaStream_t st = as_stream(stream);
   if (dtype == RGNN_F32) k_axpby<float><<<(unsigned)blocks, 256, 0, st>>>(a, static_cast<const float*>(x), b, static_cast<const float*>(y), static_cast<float*>(out), n);
   else k_axpby<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(a, static_cast<const __nv_bfloat16*>(x), b, static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(out), n);
@@ -606,7 +606,7 @@ extern "C" int rgnn_bias_add(int dtype, const void* x, const float* bias, void* 
   if (rows == 0 || cols == 0) return 0;
   RGNN_REQUIRE(x && bias && out, RGNN_E_ARG, "rgnn_bias_add: null pointer");
   int64_t blocks = (rows * cols + 255) / 256;
-  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
   cudaStream_t st = as_stream(stream);
   if (dtype == RGNN_F32) k_bias_add<float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(x), bias, static_cast<float*>(out), rows, cols);
   else k_bias_add<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), bias, static_cast<__nv_bfloat16*>(out), rows, cols);
@@ -632,7 +632,7 @@ extern "C" int rgnn_reduce_sum(int dtype, const void* x, int64_t outer, int64_t 
         (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && inner < (1 << 20)) {
       const int64_t row_vecs = len * inner / vec;
       const int64_t bx = (row_vecs + 255) / 256;
-      int64_t chunks = (8 * kNumSMs + bx - 1) / bx;
+      int64_t chunks = (8 * num_sms() + bx - 1) / bx;
       if (chunks > outer) chunks = outer;
       if (chunks > 65535) chunks = 65535;
       const int64_t chunk = (outer + chunks - 1) / chunks;
@@ -653,7 +653,7 @@ extern "C" int rgnn_reduce_sum(int dtype, const void* x, int64_t outer, int64_t 
         int cv = 32;
         while (cv < cvs && cv < 256) cv <<= 1;
         const int64_t bx2 = (cvs + cv - 1) / cv;
-        int64_t chunks2 = (4 * kNumSMs + bx2 - 1) / bx2;
+        int64_t chunks2 = (4 * num_sms() + bx2 - 1) / bx2;
         if (chunks2 > 65535) chunks2 = 65535;
         if (chunks2 < 1) chunks2 = 1;
         const int64_t chunk2 = (outer + chunks2 - 1) / chunks2;
@@ -666,7 +666,7 @@ extern "C" int rgnn_reduce_sum(int dtype, const void* x, int64_t outer, int64_t 
       }
       const int threads = 64;                      // few columns, many rows: small blocks, many row chunks
       const int64_t bx = (cvs + threads - 1) / threads;
-      int64_t chunks = (16 * kNumSMs + bx - 1) / bx;
+      int64_t chunks = (16 * num_sms() + bx - 1) / bx;
       if (chunks > (outer + 15) / 16) chunks = (outer + 15) / 16;
       if (chunks > 65535) chunks = 65535;
       if (chunks < 1) chunks = 1;
@@ -681,7 +681,7 @@ extern "C" int rgnn_reduce_sum(int dtype, const void* x, int64_t outer, int64_t 
   }
   const bool jfast = (s_j == 1 || inner == 1);
   const int64_t bx = jfast ? (len + 255) / 256 : (len + 7) / 8;
-  int64_t chunks = (8 * kNumSMs + bx - 1) / bx;
+  int64_t chunks = (8 * num_sms() + bx - 1) / bx;
   if (chunks > outer) chunks = outer;
   if (chunks > 65535) chunks = 65535;
   if (chunks < 1) chunks = 1;

@@ -519,14 +519,14 @@ template <int BN, int CL, bool AUX, bool TWO = false>
 static int launch_cl(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const TcParams& p, cudaStream_t st,
                      const CUtensorMap* o0, const CUtensorMap* o1) {
   constexpr size_t smem = 1024 + (TWO ? (size_t)6 * (BM * BK * 2 + BN / 2 * BK * 2) : (size_t)NSTAGE * (BM * BK * 2 + BN * BK * 2)) + NOUT_STAGE * 128 * 128 + 384;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce once;
+  if (once.need()) {
     cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, CL, AUX, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_gemm_tc)");
-    attr_done = true;
+    once.mark();
   }
   const int64_t work = (int64_t)((p.tiles_m + CL - 1) / CL) * p.tiles_n * p.splits;
-  int64_t groups = work < kNumSMs / CL ? work : kNumSMs / CL;
+  int64_t groups = work < num_sms() / CL ? work : num_sms() / CL;
   if (groups < 1) return 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(groups * CL));
@@ -692,7 +692,7 @@ extern "C" int rgnn_tc_conv1x1_wgrad(const void* dy, int64_t M, const void* x0, 
   if (rc) return rc;
   const int64_t n = M * Nn;
   int64_t blocks = (n + 255) / 256;
-  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   k_sum_partials<<<(unsigned)blocks, 256, 0, st>>>(partial, (int)splits, n, dW, ldw, Nn, 1.0f);
   RGNN_LAUNCH_CHECK("k_sum_partials");
   if (dbias) {
@@ -785,7 +785,7 @@ extern "C" int rgnn_tc_gemm_nn(const void* A, int64_t lda, const void* B, int64_
   if (rc) return rc;
   const int64_t n = M * N;
   int64_t blocks = (n + 255) / 256;
-  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   k_sum_partials<<<(unsigned)blocks, 256, 0, st>>>(partial, (int)splits, n, C, ldc, N, alpha);
   RGNN_LAUNCH_CHECK("k_sum_partials");
   return 0;

@@ -55,7 +55,7 @@ extern "C" int rgnn_relative_pose(int pose_is_f64, const void* poses, float* edg
   if (total == 0) return 0;
   RGNN_REQUIRE(poses && edge_pose, RGNN_E_ARG, "rgnn_relative_pose: null pointer");
   int64_t blocks = (total + 255) / 256;
-  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   cudaStream_t st = as_stream(stream);
   if (pose_is_f64) k_relative_pose<double><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const double*>(poses), edge_pose, num_graphs, (int)robots);
   else k_relative_pose<float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(poses), edge_pose, num_graphs, (int)robots);

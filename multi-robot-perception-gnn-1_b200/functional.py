@@ -10,6 +10,8 @@ import torch
 from . import _lib
 from ._lib import lib, check, ptr, stream, dtype_code
 
+FOLD_IDENTITY_MIN_BETA = 0.25   # GCN2Conv: fold (1-beta) I + beta W into one bf16 operand only for beta >= this (layers 1-3 at lambda = 1)
+
 _POST = {"none": _lib.POST_NONE, "sum": _lib.POST_NONE, "mean": _lib.POST_MEAN, "scale": _lib.POST_SCALE}
 
 
@@ -230,7 +232,7 @@ def _edge_mlp_forward(pose, w1, b1, w2, b2, out_dtype):
     z = torch.empty((e, f2), dtype=out_dtype, device=pose.device)
     with torch.cuda.device(pose.device):
         check(lib().rgnn_edge_mlp1_fwd(dtype_code(a1), ptr(pose), ptr(w1), ptr(b1), ptr(a1), e, hid, stream()), "rgnn_edge_mlp1_fwd")
-        if _lib.USE_TC and out_dtype == torch.bfloat16 and hid % 64 == 0 and f2 % 128 == 0:
+        if _lib.USE_TC and out_dtype == torch.bfloat16 and hid % 64 == 0 and f2 % 128 == 0 and e > 0:
             w2b = _cast_w(w2)
             with _lib.timed("mlp2_fwd", 2.0 * e * f2 * hid):
                 check(lib().rgnn_tc_gemm_tn(ptr(a1), hid, ptr(w2b), hid, ptr(z), f2, e, f2, hid,
@@ -511,12 +513,22 @@ class LinearFn(torch.autograd.Function):
             epi |= _lib.EPI_ADD_AUX
         ctx.tc = bool(_lib.USE_TC and x.dtype == torch.bfloat16 and din % 128 == 0 and dout % 128 == 0 and rows > 0)
         with torch.cuda.device(x.device):
-            if ctx.tc:     # tcgen05 path: (alpha W + ident I)^T in bf16 is the K-major B operand - the identity mapping lives in the
-                           # weight matrix (one plain GEMM, no second operand to read in the epilogue); bias fused in the epilogue
+            # the identity mapping is folded into the bf16 weight operand only while beta (= alpha here) is large enough for
+            # beta * w_ii to survive next to 1 - beta in a bf16 diagonal; deep GCNII layers (beta = log(lambda/l + 1) -> 0) keep the
+            # residual as the fp32 epilogue term alpha * acc + ident * x, like the CUDA-core path and DGL do
+            ctx.fold = bool(ident == 0.0 or alpha >= FOLD_IDENTITY_MIN_BETA)
+            if ctx.tc and ctx.fold:
+                # tcgen05 path: (alpha W + ident I)^T in bf16 is the K-major B operand - the identity mapping lives in the
+                # weight matrix (one plain GEMM, no second operand to read in the epilogue); bias fused in the epilogue
                 wt = _cast_w(wf, transpose=True, alpha=float(alpha), ident=float(ident))
                 with _lib.timed("linear_fwd", 2.0 * rows * din * dout):
                     check(lib().rgnn_tc_gemm_tn(ptr(x), din, ptr(wt), din, ptr(y), dout, rows, dout, din, epi & ~_lib.EPI_ADD_AUX, ptr(bf),
                                                 None, 1.0, 0.0, stream()), "rgnn_tc_gemm_tn")
+            elif ctx.tc:
+                wt = _cast_w(wf, transpose=True)
+                with _lib.timed("linear_fwd", 2.0 * rows * din * dout):
+                    check(lib().rgnn_tc_gemm_tn(ptr(x), din, ptr(wt), din, ptr(y), dout, rows, dout, din, epi, ptr(bf),
+                                                ptr(x), float(alpha), float(ident), stream()), "rgnn_tc_gemm_tn")
             else:
                 _gemm(x, (0, 0, din, 1), wf, (0, 0, dout, 1), y, (0, dout, 1), rows, dout, din, epi=epi, bias=bf,
                       aux=x if ident != 0.0 else None, alpha=float(alpha), beta=float(ident))
@@ -536,11 +548,16 @@ class LinearFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 dx = torch.empty_like(x)
                 epi = _lib.EPI_ADD_AUX if ctx.ident != 0.0 else 0
-                if ctx.tc:     # dX = dY . (alpha W + ident I)^T: the [in, out] matrix in bf16 is already the K-major B operand
+                if ctx.tc and ctx.fold:     # dX = dY . (alpha W + ident I)^T: the [in, out] matrix in bf16 is already the K-major B operand
                     wb = _cast_w(wf, alpha=ctx.alpha, ident=ctx.ident)
                     with _lib.timed("linear_dx", 2.0 * rows * din * dout):
                         check(lib().rgnn_tc_gemm_tn(ptr(dy), dout, ptr(wb), dout, ptr(dx), din, rows, din, dout, 0, None,
                                                     None, 1.0, 0.0, stream()), "rgnn_tc_gemm_tn")
+                elif ctx.tc:                # small beta: dX = alpha * dY . W^T + ident * dY with the residual in the fp32 epilogue
+                    wb = _cast_w(wf)
+                    with _lib.timed("linear_dx", 2.0 * rows * din * dout):
+                        check(lib().rgnn_tc_gemm_tn(ptr(dy), dout, ptr(wb), dout, ptr(dx), din, rows, din, dout, epi, None,
+                                                    ptr(dy), ctx.alpha, ctx.ident, stream()), "rgnn_tc_gemm_tn")
                 else:
                     _gemm(dy, (0, 0, dout, 1), wf, (0, 0, 1, dout), dx, (0, din, 1), rows, din, dout,
                           epi=epi, aux=dy if ctx.ident != 0.0 else None, alpha=ctx.alpha, beta=ctx.ident)

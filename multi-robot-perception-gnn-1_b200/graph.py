@@ -228,6 +228,21 @@ def _host_complete_k(src, dst, k):
     return k if torch.equal(src, ii[keep]) and torch.equal(dst, jj[keep]) else 0
 
 
+def complete_k_of(local_src, local_dst, batch_num_nodes):
+    """K if EVERY graph of a batch given by host-side local edge lists is the reference's complete K-robot enumeration
+    (dataloader.py:88-95), else 0 - for callers that rebuild a RobotGraph from stored arrays (graph caches)."""
+    bnn = [int(v) for v in batch_num_nodes]
+    if not bnn or len(set(bnn)) != 1 or bnn[0] < 2 or local_src.is_cuda:
+        return 0
+    k, g = bnn[0], len(bnn)
+    e = k * (k - 1)
+    src, dst = local_src.to(torch.int64).reshape(-1), local_dst.to(torch.int64).reshape(-1)
+    if src.numel() != g * e or dst.numel() != g * e or not _host_complete_k(src[:e], dst[:e], k):
+        return 0
+    same = bool((src.view(g, e) == src[:e]).all()) and bool((dst.view(g, e) == dst[:e]).all())
+    return k if same else 0
+
+
 def batch(graphs):
     """dgl.batch - dgl/training.py:57-58: node ids of graph i shift by sum_{j<i} num_nodes_j, edges and every
     ndata/edata key concatenate in graph order."""

@@ -21,6 +21,7 @@ def compat(monkeypatch):
     import dgl
     from model import models
     yield dgl, models
+    sys.modules["model"].disable_legacy_checkpoint_load()      # the torch.load default the package installs must not leak into other tests
     for k in [k for k in sys.modules if k == "dgl" or k.startswith("dgl.") or k == "model" or k.startswith("model.")]:
         sys.modules.pop(k, None)
 
@@ -52,6 +53,54 @@ def test_checkpoint_keys_match_reference(compat, name, kw):
     golden = json.load(open(os.path.join(GOLDEN, "model_state_keys.json")))[name]
     sd = models.multi_view_dgl_model(make_opt(**kw)).state_dict()
     assert {k: list(v.shape) for k, v in sd.items()} == golden
+
+
+def test_whole_module_checkpoint_round_trip_like_the_scripts(compat, tmp_path):
+    """dgl/training.py:345-355 pickles the whole module; :291 and dgl/eval.py:251 read it back with a bare torch.load(path), which
+    torch >= 2.6 refuses (weights_only=True).  Importing compat's `model` package restores the scripts' behaviour."""
+    import model as model_pkg
+    _, models = compat
+    try:
+        m = models.multi_view_dgl_model(make_opt())
+        opt_ = torch.optim.Adam(m.parameters(), 0.005)
+        path = str(tmp_path / "ckpt.model")
+        torch.save({'model': m, 'optimizer': opt_.state_dict(), 'n_iter': 3}, path)          # training.py:352-355
+        ck = torch.load(path)                                                                 # training.py:291 - no weights_only
+        m2 = ck['model']
+        assert type(m2).__name__ == "multi_view_dgl_model" and ck['n_iter'] == 3
+        for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+            assert k1 == k2 and torch.equal(v1, v2)
+        with pytest.raises(Exception):                                                        # an explicit request stays strict
+            torch.load(path, weights_only=True)
+    finally:
+        model_pkg.disable_legacy_checkpoint_load()
+    assert getattr(torch.load, "__wrapped_by_robot_gnn__", None) is None
+
+
+def test_graph_cache_rejects_pickled_code_and_rederives_topology(compat, tmp_path):
+    """load_graphs uses the safe unpickler and never trusts complete_k from the file."""
+    dgl, _ = compat
+    import robot_gnn_b200 as R
+    g = R.robot_batch(3, 4)
+    g.ndata["x"] = torch.arange(12.0)
+    path = str(tmp_path / "g.bin")
+    dgl.save_graphs(path, [g])
+    blob = torch.load(path, weights_only=True)
+    blob["graphs"][0]["complete_k"] = 7                 # a lie in the file
+    torch.save(blob, path)
+    (g2,), _ = dgl.load_graphs(path)
+    assert g2.complete_k == 4 and torch.equal(g2.ndata["x"], g.ndata["x"])
+    blob["graphs"][0]["dst"] = blob["graphs"][0]["dst"].flip(0)      # no longer the reference enumeration
+    torch.save(blob, path)
+    (g3,), _ = dgl.load_graphs(path)
+    assert g3.complete_k == 0
+
+    class Evil:
+        def __reduce__(self):
+            return (print, ("pwned",))
+    torch.save({"format": "robot-gnn-graphs-v1", "graphs": [Evil()], "labels": None}, path)
+    with pytest.raises(ValueError):
+        dgl.load_graphs(path)
 
 
 def test_dataset_protocol_and_graph_cache(compat, tmp_path):
