@@ -51,6 +51,14 @@ struct TcParams {
   int nchw_split;       // NCHW epilogue: 1 = the two warpgroups take two slabs each (one staging buffer per warpgroup)
   int n_fast;           // tile order: 1 = the N-tiles of one M-tile group are consecutive work items (A is the big operand: linear layers)
   float* rowsum;        // WGRAD: if non-null, fp32 [splits, M] partial row sums of A (the bias gradient of the 1x1 conv) are written here
+  // ---- fp32 operands as three bf16 planes (x = x0 + x1 + x2, 8 significand bits each; profiles/r02_fp32_split_study.jsonl) ----
+  // The reduction then runs `nprod` times over the k-blocks, product j taking plane pa[j] of A and plane pb[j] of B, the
+  // 2^-16 terms first and x0.y0 last, all into ONE fp32 TMEM accumulator: A.B = sum_{i+j<=2} A_i.B_j to ~3e-7 (fp32 products),
+  // provided a single accumulator sees no more than ~4096 elements of the original K (the accumulator truncates on alignment).
+  int nprod;            // 0 / 1 = plain bf16 operands
+  int pa[6], pb[6];
+  int plane_a, plane_b0, plane_b1;   // distance between planes in the operand's OUTER tensor-map coordinate (rows / robots)
+  int out_f32;          // NCHW / ROW epilogues write fp32 (two 128-byte slabs per 64 accumulator columns; exact sigmoid)
 };
 
 // CL = 2: the two CTAs of a cluster work on the two M-tiles that share one B tile (same tn); each loads HALF of the B tile
@@ -127,6 +135,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int tiles_mc = (p.tiles_m + CL - 1) / CL;     // M-tile groups: the CTAs of a cluster take consecutive M-tiles
   const int work_total = tiles_mc * p.tiles_n * p.splits;
   const int w_first = blockIdx.x / CL, w_step = gridDim.x / CL;
+  const int nprod = p.nprod > 1 ? p.nprod : 1;
   const bool a_mn = p.load_mode == LOAD_NN;
   const bool b_mn = p.load_mode == LOAD_CONV || p.load_mode == LOAD_NN;
 
@@ -138,6 +147,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int tm = (p.n_fast ? (w / p.tiles_n) % tiles_mc : w % tiles_mc) * CL + crank, tn = p.n_fast ? w % p.tiles_n : (w / tiles_mc) % p.tiles_n,
                   sp = w / (tiles_mc * p.tiles_n);
         const int kb0 = sp * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+        for (int pj = 0; pj < nprod; ++pj) {
+        // split-plane products: the same k-blocks again with another (A plane, B plane) pair - only an outer coordinate moves
+        const int oa = p.nprod > 1 ? p.pa[pj] * p.plane_a : 0, ob0 = p.nprod > 1 ? p.pb[pj] * p.plane_b0 : 0,
+                  ob1 = p.nprod > 1 ? p.pb[pj] * p.plane_b1 : 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t fb = bar_full + 8 * stage;
@@ -146,24 +159,24 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             // CTA pair: own A rows + own half of B into this CTA's stage; every byte is counted on the LEADER's barrier
             if (crank == 0) mbar_expect_tx(fb, 2 * STAGE_BYTES);
             if (p.load_mode == LOAD_TN) {
-              tma_2d_2sm(sa, &tmA, fb, kb * BK, tm * BM);
-              tma_2d_2sm(sb, &tmB0, fb, kb * BK, tn * BN + crank * (BN / 2));
+              tma_2d_2sm(sa, &tmA, fb, kb * BK, tm * BM + oa);
+              tma_2d_2sm(sb, &tmB0, fb, kb * BK, tn * BN + crank * (BN / 2) + ob0);
             } else if (p.load_mode == LOAD_CONV) {
-              tma_2d_2sm(sa, &tmA, fb, kb * BK, tm * BM);
+              tma_2d_2sm(sa, &tmA, fb, kb * BK, tm * BM + oa);
               const CUtensorMap* mb = kb < p.kb_b0 ? &tmB0 : &tmB1;
               const int kc = (kb < p.kb_b0 ? kb : kb - p.kb_b0) * BK;
-              tma_3d_2sm(sb, mb, fb, 0, kc, tn * (BN / 64) + crank * (BN / 128));
+              tma_3d_2sm(sb, mb, fb, 0, kc, tn * (BN / 64) + crank * (BN / 128) + (kb < p.kb_b0 ? ob0 : ob1));
             } else if (p.load_mode == LOAD_WGRAD) {
-              tma_2d_2sm(sa, &tmA, fb, 0, kb * p.rows_a + tm * BM);
+              tma_2d_2sm(sa, &tmA, fb, 0, kb * p.rows_a + tm * BM + oa);
               const int n0 = tn * BN;
               const CUtensorMap* mb = n0 < p.n_b0 ? &tmB0 : &tmB1;
-              const int rowb = n0 < p.n_b0 ? kb * p.rows_b0 + n0 : kb * p.rows_b1 + (n0 - p.n_b0);
+              const int rowb = n0 < p.n_b0 ? kb * p.rows_b0 + n0 + ob0 : kb * p.rows_b1 + (n0 - p.n_b0) + ob1;
               tma_2d_2sm(sb, mb, fb, 0, rowb + crank * (BN / 2));
             } else {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_2d_2sm(sa + j * (BK * 128), &tmA, fb, tm * BM + j * 64, kb * BK);
+              for (int j = 0; j < BM / 64; ++j) tma_2d_2sm(sa + j * (BK * 128), &tmA, fb, tm * BM + j * 64, kb * BK + oa);
 #pragma unroll
-              for (int j = 0; j < BN / 128; ++j) tma_2d_2sm(sb + j * (BK * 128), &tmB0, fb, tn * BN + (crank * (BN / 128) + j) * 64, kb * BK);
+              for (int j = 0; j < BN / 128; ++j) tma_2d_2sm(sb + j * (BK * 128), &tmB0, fb, tn * BN + (crank * (BN / 128) + j) * 64, kb * BK + ob0);
             }
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             continue;
@@ -174,15 +187,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           constexpr uint32_t HALF_B = B_BYTES / 2;
           const int h0 = CL > 1 ? crank : 0, h1 = CL > 1 ? crank + 1 : 2;
           if (p.load_mode == LOAD_TN) {
-            tma_2d(sa, &tmA, fb, kb * BK, tm * BM);
+            tma_2d(sa, &tmA, fb, kb * BK, tm * BM + oa);
             for (int hb = h0; hb < h1; ++hb) {
-              if (CL > 1) tma_2d_mc(sb + hb * HALF_B, &tmB0, fb, kb * BK, tn * BN + hb * (BN / 2), MC_MASK);
-              else tma_2d(sb + hb * HALF_B, &tmB0, fb, kb * BK, tn * BN + hb * (BN / 2));
+              if (CL > 1) tma_2d_mc(sb + hb * HALF_B, &tmB0, fb, kb * BK, tn * BN + hb * (BN / 2) + ob0, MC_MASK);
+              else tma_2d(sb + hb * HALF_B, &tmB0, fb, kb * BK, tn * BN + hb * (BN / 2) + ob0);
             }
           } else if (p.load_mode == LOAD_CONV) {
-            tma_2d(sa, &tmA, fb, kb * BK, tm * BM);
+            tma_2d(sa, &tmA, fb, kb * BK, tm * BM + oa);
             const CUtensorMap* mb = kb < p.kb_b0 ? &tmB0 : &tmB1;
             const int kc = (kb < p.kb_b0 ? kb : kb - p.kb_b0) * BK;
+            const int ob = kb < p.kb_b0 ? ob0 : ob1;
             if (PREFETCH_L2 && crank == 0 && (w % tiles_mc) == 0 && w + w_step < work_total) {
               // the activation tile of this CTA's NEXT work item (one whole tile of lead time); the M-tile siblings reuse it from L2
               const int tn2 = ((w + w_step) / tiles_mc) % p.tiles_n;
@@ -190,14 +204,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               tma_prefetch_3d(mb, 0, kc, tn2 * (BN / 64) + BN / 128);
             }
             for (int hb = h0; hb < h1; ++hb) {
-              if (CL > 1) tma_3d_mc(sb + hb * HALF_B, mb, fb, 0, kc, tn * (BN / 64) + hb * (BN / 128), MC_MASK);
-              else tma_3d(sb + hb * HALF_B, mb, fb, 0, kc, tn * (BN / 64) + hb * (BN / 128));
+              if (CL > 1) tma_3d_mc(sb + hb * HALF_B, mb, fb, 0, kc, tn * (BN / 64) + hb * (BN / 128) + ob, MC_MASK);
+              else tma_3d(sb + hb * HALF_B, mb, fb, 0, kc, tn * (BN / 64) + hb * (BN / 128) + ob);
             }
           } else if (p.load_mode == LOAD_WGRAD) {   // k-block == robot kb; both operands K-major (pixels contiguous)
-            tma_2d(sa, &tmA, fb, 0, kb * p.rows_a + tm * BM);
+            tma_2d(sa, &tmA, fb, 0, kb * p.rows_a + tm * BM + oa);
             const int n0 = tn * BN;
             const CUtensorMap* mb = n0 < p.n_b0 ? &tmB0 : &tmB1;
-            const int rowb = n0 < p.n_b0 ? kb * p.rows_b0 + n0 : kb * p.rows_b1 + (n0 - p.n_b0);
+            const int rowb = n0 < p.n_b0 ? kb * p.rows_b0 + n0 + ob0 : kb * p.rows_b1 + (n0 - p.n_b0) + ob1;
             if (PREFETCH_L2 && kb + PF_AHEAD < kb1) {     // robots further down this split: dY rows by the tn == 0 CTAs, X rows by tm == 0
               if (tn == 0) tma_prefetch_2d(&tmA, 0, (kb + PF_AHEAD) * p.rows_a + tm * BM);
               if (tm == 0) {
@@ -212,14 +226,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
           } else {                                   // LOAD_NN: both operands MN-major, 64-wide boxes
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_2d(sa + j * (BK * 128), &tmA, fb, tm * BM + j * 64, kb * BK);
+            for (int j = 0; j < BM / 64; ++j) tma_2d(sa + j * (BK * 128), &tmA, fb, tm * BM + j * 64, kb * BK + oa);
             for (int hb = h0; hb < h1; ++hb)
               for (int j = hb * (BN / 128); j < (hb + 1) * (BN / 128); ++j) {
-                if (CL > 1) tma_2d_mc(sb + j * (BK * 128), &tmB0, fb, tn * BN + j * 64, kb * BK, MC_MASK);
-                else tma_2d(sb + j * (BK * 128), &tmB0, fb, tn * BN + j * 64, kb * BK);
+                if (CL > 1) tma_2d_mc(sb + j * (BK * 128), &tmB0, fb, tn * BN + j * 64, kb * BK + ob0, MC_MASK);
+                else tma_2d(sb + j * (BK * 128), &tmB0, fb, tn * BN + j * 64, kb * BK + ob0);
               }
           }
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
         }
       }
     }
@@ -237,7 +252,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + as * BN;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      const int nit = nprod * (kb1 - kb0);                 // split-plane products: the k-block range is walked nprod times
+      for (int it = 0; it < nit; ++it) {
         mbar_wait(bar_full + 8 * stage, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
@@ -246,16 +262,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = make_desc(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t db = make_desc(sb + k * b_kstep, b_lbo, 1024);
-            if constexpr (TWO) umma2(tacc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma(tacc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (TWO) umma2(tacc, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            else umma(tacc, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
           if constexpr (TWO) {
             umma_commit2_mc((rs_after_mma ? bar_mdone : bar_empty) + 8 * stage, MC_MASK);   // the stage is free (or ready for the row sums) in both CTAs
-            if (kb == kb1 - 1) umma_commit2_mc(bar_tfull + 8 * as, MC_MASK);     // both halves of the accumulator are complete
+            if (it == nit - 1) umma_commit2_mc(bar_tfull + 8 * as, MC_MASK);     // both halves of the accumulator are complete
           } else {
           if (CL > 1) umma_commit_mc(bar_empty + 8 * stage, MC_MASK);   // both CTAs' producers wait for both consumers
           else umma_commit(bar_empty + 8 * stage);            // stage reusable once these MMAs retire
-          if (kb == kb1 - 1) umma_commit(bar_tfull + 8 * as); // accumulator complete
+          if (it == nit - 1) umma_commit(bar_tfull + 8 * as); // accumulator complete
           }
         }
         __syncwarp();
@@ -341,7 +357,65 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // staging buffers (store of slab j overlaps the staging of slab j+1).  ROW tiles (edge-MLP, short K, sigmoid) are limited
         // by epilogue issue: the two warpgroups take one column half each, one buffer per warpgroup.
         const bool split_wg = !nchw || p.nchw_split;
-        const int j_lo = split_wg ? eh * (BN / 128) : 0, j_hi = split_wg ? (eh + 1) * (BN / 128) : (eh == 0 ? BN / 64 : 0);
+        bool f32_done = false;
+        if constexpr (!AUX) {
+          if (p.out_f32) {
+            // fp32 outputs (split-plane products of the fp32 parity mode): the same staging slab (128 rows x 128 B, 128B swizzle)
+            // now holds 32 fp32 columns, so a 64-column group (one robot's 64 pixels / 64 matrix columns) leaves as two slabs;
+            // the output tensor maps describe the fp32 tensor as pairs of 16-bit elements (TMA moves bytes, it does no arithmetic).
+            f32_done = true;
+            constexpr int NSLAB = BN / 32;
+            const int f_lo = split_wg ? eh * (NSLAB / 2) : 0, f_hi = split_wg ? (eh + 1) * (NSLAB / 2) : (eh == 0 ? NSLAB : 0);
+#pragma unroll 1
+            for (int j = f_lo; j < f_hi; ++j) {
+              const int node = tn * (BN / 64) + (j >> 1);
+              const uint32_t stg = out_stage + (split_wg ? eh : (j & 1)) * OUT_STAGE_BYTES;
+              const int64_t n0 = (int64_t)tn * BN + j * 32;          // first fp32 column of the slab (ROW)
+              uint32_t r0[32];
+              tmem_ld32_issue(tacc + j * 32, r0);
+              tmem_ld_wait();
+              float v[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]) + bias_m;
+              if (!nchw) {
+                if (p.alpha != 1.0f) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+                }
+                if (p.epi_flags & RGNN_EPI_BIAS_N) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + q * 4));
+                    v[4 * q] += b0.x; v[4 * q + 1] += b0.y; v[4 * q + 2] += b0.z; v[4 * q + 3] += b0.w;
+                  }
+                }
+                if (p.epi_flags & RGNN_EPI_SIGMOID) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) v[i] = __fdividef(1.0f, 1.0f + __expf(-v[i]));   // parity mode: ~2 ulp, not the bf16-grade tanh.approx
+                }
+              }
+              if (ew == 0 && lane == 0) {
+                if (!split_wg) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              }
+              epi_bar_sync(bar_id);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const uint32_t addr = stg + row * 128 + ((q ^ (row & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(__float_as_uint(v[4 * q])), "r"(__float_as_uint(v[4 * q + 1])),
+                             "r"(__float_as_uint(v[4 * q + 2])), "r"(__float_as_uint(v[4 * q + 3])) : "memory");
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              epi_bar_sync(bar_id);
+              if (ew == 0 && lane == 0) {
+                if (nchw) { if (node < p.nodes && (int64_t)tm * BM < p.M) tma_store_2d(second ? &tmO1 : &tmO0, stg, (j & 1) * 64, node * rows_per_node + row0); }
+                else if (n0 < p.N) tma_store_2d(&tmO0, stg, (int)(2 * n0), tm * BM);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            }
+          }
+        }
+        const int j_lo = f32_done ? 0 : (split_wg ? eh * (BN / 128) : 0), j_hi = f32_done ? 0 : (split_wg ? (eh + 1) * (BN / 128) : (eh == 0 ? BN / 64 : 0));
 #pragma unroll 1
         for (int j = j_lo; j < j_hi; ++j) {
           const int node = tn * (BN / 64) + j;
