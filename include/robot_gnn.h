@@ -216,6 +216,43 @@ int rgnn_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void
 int rgnn_tc_gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
                     int64_t M, int64_t N, int64_t K, float alpha, float* partial, int64_t splits, void* stream);
 
+/* ---- the fp32 PARITY mode on the tensor cores: split-bf16 products (SURVEY §7 "fp32 parity vs tensor cores") ----------------
+ * An fp32 operand x is stored as three bf16 planes with x = x0 + x1 + x2 (8 significand bits each).  A.B is then the sum of the six
+ * plane-pair products A_i.B_j, i + j <= 2 (the three dropped ones are ~2^-24 relative), run as ONE bf16 tcgen05 GEMM whose k-loop
+ * walks the k-blocks six times - 2^-16 terms first, A_0.B_0 last - into one fp32 TMEM accumulator; outputs are fp32.  Measured
+ * against fp64 (profiles/r02_fp32_split_study.jsonl): <= 2.5e-6 normalised max error up to K = 2560 per accumulator (cuBLAS fp32 on
+ * CUDA cores: 1.7e-6; one bf16 pass: 2.5e-3; one TF32 pass: 3e-4), so the reference's fp32 nn.Linear(F,2F)+Sigmoid (models.py:149-150),
+ * Conv2d(2F,F,1) (models.py:164) and their autograd stay inside the 1e-5 contract.  Reductions longer than ~4096 (the weight
+ * gradients) must be split (`splits`): the accumulator truncates when a small addend is aligned to a large running sum. */
+
+/* x fp32 [n] -> out bf16 [3, plane]: planes x0, x1, x2; elements [n, plane) of every plane are zeroed.  n %% 4 == 0, plane %% 8 == 0. */
+int rgnn_tc_split3(const float* x, int64_t n, int64_t plane, void* out_bf16, void* stream);
+
+/* fp32 master weights [rows, cols] -> planes [3, rows, cols] and/or planes of the transpose [3, cols, rows] (either may be NULL) */
+int rgnn_tc_split3_weights(const float* w, int64_t rows, int64_t cols, void* out3, void* out3_t, void* stream);
+
+/* rgnn_tc_conv1x1 on split planes: W3 [3, m0+m1, c0+c1]; x0_3 [3, plane_nodes, c0, 64], x1_3 [3, plane_nodes, c1, 64] (plane_nodes >= nodes);
+ * out0 / out1 fp32 [nodes, m, 64].  (models.py:182-184 in fp32 and its dX.) */
+int rgnn_tc3_conv1x1(const void* W3, const void* x0_3, int64_t c0, const void* x1_3, int64_t c1, int64_t plane_nodes,
+                     float* out0, int64_t m0, float* out1, int64_t m1, const float* bias, int64_t nodes, void* stream);
+
+/* rgnn_tc_conv1x1_wgrad on split planes: dy3 [3, plane_nodes, M, 64], x0_3 / x1_3 as above; dW fp32.  Choose splits >= nodes / 64 so that
+ * one accumulator sums at most 64 robots x 64 pixels.  (The bias gradient is a separate rgnn_reduce_sum in this mode.) */
+int rgnn_tc3_conv1x1_wgrad(const void* dy3, int64_t M, const void* x0_3, int64_t c0, const void* x1_3, int64_t c1, int64_t plane_nodes,
+                           float* dW, int64_t ldw, float* partial, int64_t splits, int64_t nodes, void* stream);
+
+/* rgnn_tc_gemm_tn on split planes: A3 [3, plane_a, lda] (plane_a >= M rows), B3 [3, plane_b, ldb] (plane_b >= N); C fp32 [M, ldc];
+ * epi = bit-or of RGNN_EPI_BIAS_N | RGNN_EPI_SIGMOID (exact exp-based sigmoid).  C = epi(alpha * A . B^T). */
+int rgnn_tc3_gemm_tn(const void* A3, int64_t lda, int64_t plane_a, const void* B3, int64_t ldb, int64_t plane_b, float* C, int64_t ldc,
+                     int64_t M, int64_t N, int64_t K, int epi, const float* bias, float alpha, void* stream);
+
+/* rgnn_tc_gemm_nn on split planes: A3 [3, plane_a, lda], B3 [3, plane_b, ldb] with plane rows = K padded to a multiple of 64 (zero rows). */
+int rgnn_tc3_gemm_nn(const void* A3, int64_t lda, int64_t plane_a, const void* B3, int64_t ldb, int64_t plane_b, float* C, int64_t ldc,
+                     int64_t M, int64_t N, int64_t K, float alpha, float* partial, int64_t splits, void* stream);
+
+/* out = a > 0 ? da : 0 elementwise over n values (ReLU backward, models.py:148; the bf16 path fuses it into the dA1 GEMM epilogue) */
+int rgnn_relu_grad(int dtype, const void* a, const void* da, void* out, int64_t n, void* stream);
+
 /* dzpre = dz * z * (1 - z)  elementwise over n values (sigmoid backward, models.py:150) */
 int rgnn_sigmoid_grad(int dtype, const void* z, const void* dz, void* dzpre, int64_t n, void* stream);
 

@@ -38,6 +38,13 @@ SIGNATURES = {
     "rgnn_tc_conv1x1_wgrad": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _vp],
     "rgnn_tc_gemm_tn": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _f32, _f32, _vp],
     "rgnn_tc_gemm_nn": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _i64, _vp],
+    "rgnn_tc_split3": [_vp, _i64, _i64, _vp, _vp],
+    "rgnn_tc_split3_weights": [_vp, _i64, _i64, _vp, _vp, _vp],
+    "rgnn_tc3_conv1x1": [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp],
+    "rgnn_tc3_conv1x1_wgrad": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _i64, _vp],
+    "rgnn_tc3_gemm_tn": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _f32, _vp],
+    "rgnn_tc3_gemm_nn": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _i64, _vp],
+    "rgnn_relu_grad": [_i32, _vp, _vp, _vp, _i64, _vp],
     "rgnn_sigmoid_grad": [_i32, _vp, _vp, _vp, _i64, _vp],
     "rgnn_axpby": [_i32, _f32, _vp, _f32, _vp, _vp, _i64, _vp],
     "rgnn_complete_mean_mix": [_i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f32, _f32, _vp],
@@ -49,6 +56,8 @@ _lib = None
 USE_FUSED = False  # FiLM aggregation fused into the compress GEMM's prologue (rgnn_tc_conv_film_fused; complete graphs of 2..8 robots,
                    # bf16, P = 64).  Correct and tested, but measured SLOWER than aggregation kernel + GEMM at F = 512 (2.13 vs 1.71 ms
                    # with the aggregate stored for the backward, 1.74 vs 1.71 ms in eval), so it is opt-in.
+USE_TC3 = True     # fp32 (parity mode) transforms as split-bf16 products on the tcgen05 path when the shape allows (rgnn_tc3_*); False:
+                   # the CUDA-core FFMA GEMMs (rgnn_gemm)
 USE_TC = True      # bf16 transforms on the tcgen05 path when the shape allows (tests flip it to compare with rgnn_gemm)
 
 

@@ -571,6 +571,26 @@ extern "C" int rgnn_sigmoid_grad(int dtype, const void* z, const void* dz, void*
 }
 
 template <typename T>
+__global__ void __launch_bounds__(256) k_relu_grad(const T* __restrict__ a, const T* __restrict__ da, T* __restrict__ o, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    o[i] = rgnn::to_f32<T>(a[i]) > 0.f ? da[i] : rgnn::from_f32<T>(0.f);
+}
+
+extern "C" int rgnn_relu_grad(int dtype, const void* a, const void* da, void* out, int64_t n, void* stream) {
+  RGNN_REQUIRE(dtype == RGNN_F32 || dtype == RGNN_BF16, RGNN_E_ARG, "rgnn_relu_grad: bad dtype %d", dtype);
+  RGNN_REQUIRE(n >= 0, RGNN_E_ARG, "rgnn_relu_grad: negative size");
+  if (n == 0) return 0;
+  RGNN_REQUIRE(a && da && out, RGNN_E_ARG, "rgnn_relu_grad: null pointer");
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
+  cudaStream_t st = as_stream(stream);
+  if (dtype == RGNN_F32) k_relu_grad<float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(a), static_cast<const float*>(da), static_cast<float*>(out), n);
+  else k_relu_grad<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(da), static_cast<__nv_bfloat16*>(out), n);
+  RGNN_LAUNCH_CHECK("k_relu_grad");
+  return 0;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256) k_axpby(float a, const T* __restrict__ x, float b, const T* __restrict__ y, T* __restrict__ o, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = a * rgnn::to_f32<T>(x[i]);

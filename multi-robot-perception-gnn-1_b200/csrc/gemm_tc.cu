@@ -586,6 +586,82 @@ __global__ void __launch_bounds__(256) k_cast_weights(const float* __restrict__ 
   }
 }
 
+// fp32 -> three bf16 planes with x = x0 + x1 + x2 (each term the round-to-nearest bf16 of what is left: 3 x 8 significand bits
+// cover fp32's 24).  Plane p of element i lives at out[p * plane + i]; elements [n, plane) of every plane are zeroed (K tails of
+// MN-major operands must contribute nothing).  4 elements per thread: one 16-byte load, three 8-byte stores.
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
+  a = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(a);        // exact: a keeps the leading bits of x
+  b = __float2bfloat16_rn(r1);
+  c = __float2bfloat16_rn(r1 - __bfloat162float(b));
+}
+__global__ void __launch_bounds__(256) k_split3(const float* __restrict__ x, int64_t n4, int64_t plane4, __nv_bfloat16* __restrict__ out) {
+  // n4 / plane4: counts in units of 4 elements
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane4; i += (int64_t)gridDim.x * blockDim.x) {
+    uint2 w[3] = {make_uint2(0, 0), make_uint2(0, 0), make_uint2(0, 0)};
+    if (i < n4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+      const float f[4] = {v.x, v.y, v.z, v.w};
+      __nv_bfloat16 h[3][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) split3(f[k], h[0][k], h[1][k], h[2][k]);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        __nv_bfloat162 lo = __halves2bfloat162(h[q][0], h[q][1]), hi = __halves2bfloat162(h[q][2], h[q][3]);
+        w[q] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) reinterpret_cast<uint2*>(out + q * plane4 * 4)[i] = w[q];
+  }
+}
+// weights [R, C] fp32 -> planes [3, R, C] and/or planes of the transpose [3, C, R]
+__global__ void __launch_bounds__(256) k_split3_weights(const float* __restrict__ w, int R, int C, __nv_bfloat16* __restrict__ o,
+                                                        __nv_bfloat16* __restrict__ ot) {
+  __shared__ float t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t plane = (int64_t)R * C;
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    const float v = (r < R && c < C) ? w[(int64_t)r * C + c] : 0.f;
+    t[j][tx] = v;
+    if (o && r < R && c < C) {
+      __nv_bfloat16 a, b, d;
+      split3(v, a, b, d);
+      const int64_t i = (int64_t)r * C + c;
+      o[i] = a; o[plane + i] = b; o[2 * plane + i] = d;
+    }
+  }
+  __syncthreads();
+  if (ot) {
+    for (int j = ty; j < 32; j += 8) {
+      const int c = c0 + j, r = r0 + tx;
+      if (r < R && c < C) {
+        __nv_bfloat16 a, b, d;
+        split3(t[tx][j], a, b, d);
+        const int64_t i = (int64_t)c * R + r;
+        ot[i] = a; ot[plane + i] = b; ot[2 * plane + i] = d;
+      }
+    }
+  }
+}
+
+// Operand planes of a split-bf16 product (host side of TcParams::nprod / pa / pb / plane_*): nullptr = plain bf16 operands.
+struct Split3 {
+  int64_t plane_a, plane_b0, plane_b1;    // outer-coordinate distance between the three planes of A / B0 / B1
+};
+static void set_split3(TcParams& p, const Split3* s3) {
+  if (!s3) { p.nprod = 1; return; }
+  // plane pairs (i, j), i + j <= 2, smallest terms first, x0.y0 last (profiles/r02_fp32_split_study.jsonl: 2.5e-6 at K = 2560 in this
+  // order against 2.6e-5 largest-first)
+  static const int PA[6] = {2, 1, 0, 1, 0, 0}, PB[6] = {0, 1, 2, 0, 1, 0};
+  p.nprod = 6;
+  for (int j = 0; j < 6; ++j) { p.pa[j] = PA[j]; p.pb[j] = PB[j]; }
+  p.plane_a = (int)s3->plane_a; p.plane_b0 = (int)s3->plane_b0; p.plane_b1 = (int)s3->plane_b1;
+  p.out_f32 = 1;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 static int g_cluster = -1;    // RGNN_TC_CLUSTER=1 disables the 2-CTA multicast clusters (debug / A-B comparison)
 
@@ -666,8 +742,8 @@ extern "C" int rgnn_tc_cast_weights_affine(const float* w, int64_t rows, int64_t
 
 // out[v, m, p] = sum_{k<c0} W[m,k] x0[v,k,p] + sum_{k<c1} W[m,c0+k] x1[v,k,p] (+ bias[m]);  rows m < m0 -> out0 [nodes, m0, 64],
 // rows >= m0 -> out1 [nodes, m1, 64].  All bf16, P = 64 pixels.
-extern "C" int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const void* x1, int64_t c1,
-                               void* out0, int64_t m0, void* out1, int64_t m1, const float* bias, int64_t nodes, void* stream) {
+static int conv1x1_impl(const void* W, const void* x0, int64_t c0, const void* x1, int64_t c1,
+                        void* out0, int64_t m0, void* out1, int64_t m1, const float* bias, int64_t nodes, void* stream, const Split3* s3) {
   RGNN_REQUIRE(W && x0 && out0 && c0 > 0 && m0 > 0 && nodes >= 0 && c1 >= 0 && m1 >= 0, RGNN_E_ARG, "rgnn_tc_conv1x1: bad arguments");
   RGNN_REQUIRE((c1 == 0 || x1) && (m1 == 0 || out1), RGNN_E_ARG, "rgnn_tc_conv1x1: missing second operand/output");
   RGNN_REQUIRE(c0 % 64 == 0 && c1 % 64 == 0 && m0 % 128 == 0 && m1 % 128 == 0, RGNN_E_UNSUPPORTED,
@@ -677,29 +753,35 @@ extern "C" int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const 
   if (nodes == 0) return 0;
   const int64_t K = c0 + c1, M = m0 + m1;
   constexpr int BN = 256;
+  // split-plane operands: W is [3, M, K]; x0 / x1 are [3, plane_b, c, 64] (plane_b >= nodes robots per plane)
+  const int64_t np = s3 ? 3 : 1;
+  const int64_t nodes_b0 = s3 ? 2 * s3->plane_b0 + nodes : nodes, nodes_b1 = s3 ? 2 * s3->plane_b1 + nodes : nodes;
+  RGNN_REQUIRE(!s3 || (s3->plane_a == M && s3->plane_b0 >= nodes && s3->plane_b1 >= nodes && 3 * s3->plane_b0 < (1ll << 30) && 3 * M < (1ll << 30)),
+               RGNN_E_ARG, "rgnn_tc3_conv1x1: bad plane strides");
   CUtensorMap ta, tb0, tb1;
   {
-    const uint64_t d[2] = {(uint64_t)K, (uint64_t)M}, s[1] = {(uint64_t)K * 2};
+    const uint64_t d[2] = {(uint64_t)K, (uint64_t)(np * M)}, s[1] = {(uint64_t)K * 2};
     const uint32_t b[2] = {64, 128};
     int rc = make_map(&ta, W, 2, d, s, b); if (rc) return rc;
   }
   {
-    const uint64_t d[3] = {64, (uint64_t)c0, (uint64_t)nodes}, s[2] = {128, (uint64_t)c0 * 128};
+    const uint64_t d[3] = {64, (uint64_t)c0, (uint64_t)nodes_b0}, s[2] = {128, (uint64_t)c0 * 128};
     const uint32_t b[3] = {64, 64, BN / 128};        // half of the tile's robots per box (see k_gemm_tc, CL)
     int rc = make_map(&tb0, x0, 3, d, s, b); if (rc) return rc;
   }
   if (c1 > 0) {
-    const uint64_t d[3] = {64, (uint64_t)c1, (uint64_t)nodes}, s[2] = {128, (uint64_t)c1 * 128};
+    const uint64_t d[3] = {64, (uint64_t)c1, (uint64_t)nodes_b1}, s[2] = {128, (uint64_t)c1 * 128};
     const uint32_t b[3] = {64, 64, BN / 128};
     int rc = make_map(&tb1, x1, 3, d, s, b); if (rc) return rc;
   } else tb1 = tb0;
   TcParams p = {};
+  set_split3(p, s3);
   p.load_mode = LOAD_CONV; p.epi_mode = EPI_NCHW;
   // short reductions (dX at F = 512: 8 k-blocks per tile) are paced by the epilogue, not the MMAs: both warpgroups then take two
   // slabs each (dX 1.25 -> 1.12 ms); long ones keep one warpgroup with both staging buffers (the split costs the forward 0.05 ms).
   // RGNN_TC_NCHW_SPLIT=0|1 forces either.
   { static int sp = -2; if (sp == -2) { const char* e = getenv("RGNN_TC_NCHW_SPLIT"); sp = e ? atoi(e) : -1; }
-    p.nchw_split = sp >= 0 ? sp : (K / 64 <= 12); } p.epi_flags = bias ? RGNN_EPI_BIAS_M : 0; p.alpha = 1.0f;
+    p.nchw_split = sp >= 0 ? sp : ((K / 64) * (s3 ? 6 : 1) <= 12); } p.epi_flags = bias ? RGNN_EPI_BIAS_M : 0; p.alpha = 1.0f;
   p.tiles_m = (int)(M / 128); p.tiles_n = (int)((nodes + BN / 64 - 1) / (BN / 64)); p.splits = 1;
   p.kblocks = (int)(K / 64); p.kb_per_split = p.kblocks; p.kb_b0 = (int)(c0 / 64);
   p.nodes = (int)nodes; p.M = M; p.N = nodes * 64;
@@ -707,22 +789,34 @@ extern "C" int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const 
   RGNN_REQUIRE((int64_t)p.tiles_m * p.tiles_n < (1ll << 31), RGNN_E_RANGE, "rgnn_tc_conv1x1: too many tiles");
   RGNN_REQUIRE(nodes * (m0 > m1 ? m0 : m1) < (1ll << 31), RGNN_E_RANGE, "rgnn_tc_conv1x1: too many output rows for a tensor map coordinate");
   CUtensorMap to0, to1;
+  const uint64_t orow = s3 ? 128 : 64;      // fp32 outputs: a 64-pixel row is 128 16-bit units (256 B), stored as two 128-byte boxes
   {
-    const uint64_t d[2] = {64, (uint64_t)(nodes * m0)}, s[1] = {128};
+    const uint64_t d[2] = {orow, (uint64_t)(nodes * m0)}, s[1] = {orow * 2};
     const uint32_t b[2] = {64, 128};
     int rc = make_map(&to0, out0, 2, d, s, b); if (rc) return rc;
   }
   if (m1 > 0) {
-    const uint64_t d[2] = {64, (uint64_t)(nodes * m1)}, s[1] = {128};
+    const uint64_t d[2] = {orow, (uint64_t)(nodes * m1)}, s[1] = {orow * 2};
     const uint32_t b[2] = {64, 128};
     int rc = make_map(&to1, out1, 2, d, s, b); if (rc) return rc;
   } else to1 = to0;
   return launch<BN>(ta, tb0, tb1, p, as_stream(stream), &to0, &to1);
 }
 
+extern "C" int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const void* x1, int64_t c1,
+                               void* out0, int64_t m0, void* out1, int64_t m1, const float* bias, int64_t nodes, void* stream) {
+  return conv1x1_impl(W, x0, c0, x1, c1, out0, m0, out1, m1, bias, nodes, stream, nullptr);
+}
+
+extern "C" int rgnn_tc3_conv1x1(const void* W3, const void* x0_3, int64_t c0, const void* x1_3, int64_t c1, int64_t plane_nodes,
+                                float* out0, int64_t m0, float* out1, int64_t m1, const float* bias, int64_t nodes, void* stream) {
+  const Split3 s3 = {m0 + m1, plane_nodes, plane_nodes};
+  return conv1x1_impl(W3, x0_3, c0, x1_3, c1, out0, m0, out1, m1, bias, nodes, stream, &s3);
+}
+
 // dW[m, k] = sum_v sum_p dy[v,m,p] * x[v,k,p], x = x0 (k < c0) | x1;  dW fp32 [M, c0+c1] (row stride ldw), partial fp32 [splits, M, c0+c1].
-extern "C" int rgnn_tc_conv1x1_wgrad(const void* dy, int64_t M, const void* x0, int64_t c0, const void* x1, int64_t c1,
-                                     float* dW, int64_t ldw, float* dbias, float* partial, int64_t splits, int64_t nodes, void* stream) {
+static int wgrad_impl(const void* dy, int64_t M, const void* x0, int64_t c0, const void* x1, int64_t c1,
+                      float* dW, int64_t ldw, float* dbias, float* partial, int64_t splits, int64_t nodes, void* stream, const Split3* s3) {
   RGNN_REQUIRE(dy && x0 && dW && partial && M > 0 && c0 > 0 && c1 >= 0 && nodes >= 0 && splits >= 1, RGNN_E_ARG, "rgnn_tc_conv1x1_wgrad: bad arguments");
   RGNN_REQUIRE(c1 == 0 || x1, RGNN_E_ARG, "rgnn_tc_conv1x1_wgrad: missing x1");
   constexpr int BN = 256;
@@ -736,24 +830,35 @@ extern "C" int rgnn_tc_conv1x1_wgrad(const void* dy, int64_t M, const void* x0, 
     if (e == cudaSuccess && dbias) e = cudaMemsetAsync(dbias, 0, M * 4, st);
     return e == cudaSuccess ? 0 : cuda_fail(e, "memset dW");
   }
+  // split-plane operands: dy is [3, plane_a robots, M, 64], x0 / x1 are [3, plane_b robots, c, 64]; the plane strides handed to the
+  // kernel are in ROWS of the 2-D maps (robots x channels)
+  RGNN_REQUIRE(!s3 || (!dbias && s3->plane_a >= nodes && s3->plane_b0 >= nodes && s3->plane_b1 >= nodes), RGNN_E_ARG, "rgnn_tc3_conv1x1_wgrad: bad plane strides");
+  RGNN_REQUIRE(!s3 || (3 * s3->plane_a * M < (1ll << 31) && 3 * s3->plane_b0 * (c0 > c1 ? c0 : c1) < (1ll << 31)), RGNN_E_RANGE,
+               "rgnn_tc3_conv1x1_wgrad: too many rows for a tensor map coordinate");
+  const int64_t na = s3 ? 2 * s3->plane_a + nodes : nodes, nb0 = s3 ? 2 * s3->plane_b0 + nodes : nodes, nb1 = s3 ? 2 * s3->plane_b1 + nodes : nodes;
   CUtensorMap ta, tb0, tb1;
   {
-    const uint64_t d[2] = {64, (uint64_t)(nodes * M)}, s[1] = {128};
+    const uint64_t d[2] = {64, (uint64_t)(na * M)}, s[1] = {128};
     const uint32_t b[2] = {64, 128};
     int rc = make_map(&ta, dy, 2, d, s, b); if (rc) return rc;
   }
   {
-    const uint64_t d[2] = {64, (uint64_t)(nodes * c0)}, s[1] = {128};
+    const uint64_t d[2] = {64, (uint64_t)(nb0 * c0)}, s[1] = {128};
     const uint32_t b[2] = {64, BN / 2};
     int rc = make_map(&tb0, x0, 2, d, s, b); if (rc) return rc;
   }
   if (c1 > 0) {
-    const uint64_t d[2] = {64, (uint64_t)(nodes * c1)}, s[1] = {128};
+    const uint64_t d[2] = {64, (uint64_t)(nb1 * c1)}, s[1] = {128};
     const uint32_t b[2] = {64, BN / 2};
     int rc = make_map(&tb1, x1, 2, d, s, b); if (rc) return rc;
   } else tb1 = tb0;
   if (splits > nodes) splits = nodes;
   TcParams p = {};
+  if (s3) {
+    const Split3 rows = {s3->plane_a * M, s3->plane_b0 * c0, s3->plane_b1 * c1};
+    set_split3(p, &rows);
+    p.out_f32 = 0;                 // partials are fp32 anyway
+  } else p.nprod = 1;
   p.load_mode = LOAD_WGRAD; p.epi_mode = EPI_PARTIAL;
   p.tiles_m = (int)(M / 128); p.tiles_n = (int)(Nn / BN); p.splits = (int)splits;
   p.kblocks = (int)nodes; p.kb_per_split = (int)((nodes + splits - 1) / splits);
@@ -776,11 +881,22 @@ extern "C" int rgnn_tc_conv1x1_wgrad(const void* dy, int64_t M, const void* x0, 
   return 0;
 }
 
+extern "C" int rgnn_tc_conv1x1_wgrad(const void* dy, int64_t M, const void* x0, int64_t c0, const void* x1, int64_t c1,
+                                     float* dW, int64_t ldw, float* dbias, float* partial, int64_t splits, int64_t nodes, void* stream) {
+  return wgrad_impl(dy, M, x0, c0, x1, c1, dW, ldw, dbias, partial, splits, nodes, stream, nullptr);
+}
+
+extern "C" int rgnn_tc3_conv1x1_wgrad(const void* dy3, int64_t M, const void* x0_3, int64_t c0, const void* x1_3, int64_t c1, int64_t plane_nodes,
+                                      float* dW, int64_t ldw, float* partial, int64_t splits, int64_t nodes, void* stream) {
+  const Split3 s3 = {plane_nodes, plane_nodes, plane_nodes};
+  return wgrad_impl(dy3, M, x0_3, c0, x1_3, c1, dW, ldw, nullptr, partial, splits, nodes, stream, &s3);
+}
+
 // C[M,N] = epi(A[M,K] . B[N,K]^T): A, B bf16 K-major (row strides lda, ldb elements); C bf16 row-major (ldc); bias fp32 [N];
 // aux bf16 [M, ldc] for RGNN_EPI_RELU_MASK.  epi: bit-or of RGNN_EPI_BIAS_N | RGNN_EPI_SIGMOID | RGNN_EPI_RELU_MASK.
-extern "C" int rgnn_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
-                               int64_t M, int64_t N, int64_t K, int epi, const float* bias, const void* aux, float alpha, float beta,
-                               void* stream) {
+static int gemm_tn_impl(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                        int64_t M, int64_t N, int64_t K, int epi, const float* bias, const void* aux, float alpha, float beta,
+                        void* stream, const Split3* s3) {
   RGNN_REQUIRE(A && B && C && M >= 0 && N > 0 && K > 0, RGNN_E_ARG, "rgnn_tc_gemm_tn: bad arguments");
   RGNN_REQUIRE((epi & ~(RGNN_EPI_BIAS_N | RGNN_EPI_SIGMOID | RGNN_EPI_RELU_MASK | RGNN_EPI_ADD_AUX)) == 0, RGNN_E_UNSUPPORTED, "rgnn_tc_gemm_tn: unsupported epilogue");
   RGNN_REQUIRE(!((epi & RGNN_EPI_RELU_MASK) && (epi & RGNN_EPI_ADD_AUX)), RGNN_E_ARG, "rgnn_tc_gemm_tn: aux is either the ReLU mask or the addend");
@@ -793,18 +909,22 @@ extern "C" int rgnn_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_
   if (M == 0) return 0;
   const bool wide = N % 256 == 0;
   const int BN = wide ? 256 : 128;
+  // split-plane operands: A is [3, plane_a rows, lda], B is [3, plane_b0 rows, ldb]; C fp32
+  RGNN_REQUIRE(!s3 || (!(epi & (RGNN_EPI_RELU_MASK | RGNN_EPI_ADD_AUX)) && s3->plane_a >= M && s3->plane_b0 >= N && 3 * s3->plane_a < (1ll << 31) && ldc % 4 == 0),
+               RGNN_E_ARG, "rgnn_tc3_gemm_tn: bad plane strides / unsupported epilogue");
   CUtensorMap ta, tb;
   {
-    const uint64_t d[2] = {(uint64_t)K, (uint64_t)M}, s[1] = {(uint64_t)lda * 2};
+    const uint64_t d[2] = {(uint64_t)K, (uint64_t)(s3 ? 2 * s3->plane_a + M : M)}, s[1] = {(uint64_t)lda * 2};
     const uint32_t b[2] = {64, 128};
     int rc = make_map(&ta, A, 2, d, s, b); if (rc) return rc;
   }
   {
-    const uint64_t d[2] = {(uint64_t)K, (uint64_t)N}, s[1] = {(uint64_t)ldb * 2};
+    const uint64_t d[2] = {(uint64_t)K, (uint64_t)(s3 ? 2 * s3->plane_b0 + N : N)}, s[1] = {(uint64_t)ldb * 2};
     const uint32_t b[2] = {64, (uint32_t)BN / 2};
     int rc = make_map(&tb, B, 2, d, s, b); if (rc) return rc;
   }
   TcParams p = {};
+  set_split3(p, s3);
   p.load_mode = LOAD_TN; p.epi_mode = EPI_ROW; p.epi_flags = epi;
   p.n_fast = 1;          // activations (A, rows = edges / pixels) are the big operand: its N-tile siblings run back to back and hit L2
   p.tiles_m = (int)((M + 127) / 128); p.tiles_n = (int)(N / BN); p.splits = 1;
@@ -813,17 +933,30 @@ extern "C" int rgnn_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_
   RGNN_REQUIRE(!bias || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0, RGNN_E_ALIGN, "rgnn_tc_gemm_tn: bias must be 16-byte aligned");
   CUtensorMap to;
   {
-    const uint64_t d[2] = {(uint64_t)N, (uint64_t)M}, s[1] = {(uint64_t)ldc * 2};
+    const uint64_t ou = s3 ? 2 : 1;         // fp32 C described as pairs of 16-bit units
+    const uint64_t d[2] = {(uint64_t)N * ou, (uint64_t)M}, s[1] = {(uint64_t)ldc * 2 * ou};
     const uint32_t b[2] = {64, 128};
     int rc = make_map(&to, C, 2, d, s, b); if (rc) return rc;
   }
   return wide ? launch<256>(ta, tb, tb, p, as_stream(stream), &to, &to) : launch<128>(ta, tb, tb, p, as_stream(stream), &to, &to);
 }
 
+extern "C" int rgnn_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                               int64_t M, int64_t N, int64_t K, int epi, const float* bias, const void* aux, float alpha, float beta,
+                               void* stream) {
+  return gemm_tn_impl(A, lda, B, ldb, C, ldc, M, N, K, epi, bias, aux, alpha, beta, stream, nullptr);
+}
+
+extern "C" int rgnn_tc3_gemm_tn(const void* A3, int64_t lda, int64_t plane_a, const void* B3, int64_t ldb, int64_t plane_b, float* C, int64_t ldc,
+                                int64_t M, int64_t N, int64_t K, int epi, const float* bias, float alpha, void* stream) {
+  const Split3 s3 = {plane_a, plane_b, plane_b};
+  return gemm_tn_impl(A3, lda, B3, ldb, C, ldc, M, N, K, epi, bias, nullptr, alpha, 0.0f, stream, &s3);
+}
+
 // C[M,N] fp32 = A^T . B with A bf16 [K, M] (row stride lda), B bf16 [K, N] (row stride ldb): both operands MN-major.
 // Split over K; partial fp32 [splits, M, N].  (dW2 = dZ^T . A1 of the edge encoder.)
-extern "C" int rgnn_tc_gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
-                               int64_t M, int64_t N, int64_t K, float alpha, float* partial, int64_t splits, void* stream) {
+static int gemm_nn_impl(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                        int64_t M, int64_t N, int64_t K, float alpha, float* partial, int64_t splits, void* stream, const Split3* s3) {
   RGNN_REQUIRE(A && B && C && partial && M > 0 && N > 0 && K >= 0 && splits >= 1, RGNN_E_ARG, "rgnn_tc_gemm_nn: bad arguments");
   RGNN_REQUIRE(M % 128 == 0 && N % 128 == 0 && lda % 8 == 0 && ldb % 8 == 0, RGNN_E_UNSUPPORTED, "rgnn_tc_gemm_nn: M, N %% 128 and 16-byte row strides required");
   RGNN_REQUIRE(al16(A) && al16(B) && al16(partial), RGNN_E_ALIGN, "rgnn_tc_gemm_nn: 16-byte alignment");
@@ -835,20 +968,25 @@ extern "C" int rgnn_tc_gemm_nn(const void* A, int64_t lda, const void* B, int64_
   }
   const bool wide = N % 256 == 0;
   const int BN = wide ? 256 : 128;
+  // split-plane operands: A is [3, plane_a rows (K, zero beyond K up to a multiple of 64), lda], B likewise
+  RGNN_REQUIRE(!s3 || (s3->plane_a >= ((K + 63) / 64) * 64 && s3->plane_b0 >= ((K + 63) / 64) * 64 && 3 * s3->plane_a < (1ll << 31) && 3 * s3->plane_b0 < (1ll << 31)),
+               RGNN_E_ARG, "rgnn_tc3_gemm_nn: planes must be padded (zero-filled) to a multiple of 64 rows");
   CUtensorMap ta, tb;
   {
-    const uint64_t d[2] = {(uint64_t)M, (uint64_t)K}, s[1] = {(uint64_t)lda * 2};
+    const uint64_t d[2] = {(uint64_t)M, (uint64_t)(s3 ? 3 * s3->plane_a : K)}, s[1] = {(uint64_t)lda * 2};
     const uint32_t b[2] = {64, 64};
     int rc = make_map(&ta, A, 2, d, s, b); if (rc) return rc;
   }
   {
-    const uint64_t d[2] = {(uint64_t)N, (uint64_t)K}, s[1] = {(uint64_t)ldb * 2};
+    const uint64_t d[2] = {(uint64_t)N, (uint64_t)(s3 ? 3 * s3->plane_b0 : K)}, s[1] = {(uint64_t)ldb * 2};
     const uint32_t b[2] = {64, 64};
     int rc = make_map(&tb, B, 2, d, s, b); if (rc) return rc;
   }
   const int64_t kblocks = (K + 63) / 64;
   if (splits > kblocks) splits = kblocks;
   TcParams p = {};
+  set_split3(p, s3);
+  p.out_f32 = 0;
   p.load_mode = LOAD_NN; p.epi_mode = EPI_PARTIAL;
   p.tiles_m = (int)(M / 128); p.tiles_n = (int)(N / BN); p.splits = (int)splits;
   p.kblocks = (int)kblocks; p.kb_per_split = (int)((kblocks + splits - 1) / splits);
@@ -862,5 +1000,38 @@ extern "C" int rgnn_tc_gemm_nn(const void* A, int64_t lda, const void* B, int64_
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   k_sum_partials<<<(unsigned)blocks, 256, 0, st>>>(partial, (int)splits, n, C, ldc, N, alpha);
   RGNN_LAUNCH_CHECK("k_sum_partials");
+  return 0;
+}
+
+extern "C" int rgnn_tc_gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                               int64_t M, int64_t N, int64_t K, float alpha, float* partial, int64_t splits, void* stream) {
+  return gemm_nn_impl(A, lda, B, ldb, C, ldc, M, N, K, alpha, partial, splits, stream, nullptr);
+}
+
+extern "C" int rgnn_tc3_gemm_nn(const void* A3, int64_t lda, int64_t plane_a, const void* B3, int64_t ldb, int64_t plane_b, float* C, int64_t ldc,
+                                int64_t M, int64_t N, int64_t K, float alpha, float* partial, int64_t splits, void* stream) {
+  const Split3 s3 = {plane_a, plane_b, plane_b};
+  return gemm_nn_impl(A3, lda, B3, ldb, C, ldc, M, N, K, alpha, partial, splits, stream, &s3);
+}
+
+// x fp32 [n] -> bf16 planes [3, plane] with x = x0 + x1 + x2; elements [n, plane) of every plane are zero.  n %% 4 == 0, plane %% 8 == 0.
+extern "C" int rgnn_tc_split3(const float* x, int64_t n, int64_t plane, void* out_bf16, void* stream) {
+  RGNN_REQUIRE(x && out_bf16 && n >= 0 && plane >= n, RGNN_E_ARG, "rgnn_tc_split3: bad arguments");
+  RGNN_REQUIRE(n % 4 == 0 && plane % 8 == 0 && al16(x) && al16(out_bf16), RGNN_E_ALIGN, "rgnn_tc_split3: n %% 4, plane %% 8 and 16-byte alignment required");
+  if (plane == 0) return 0;
+  int64_t blocks = (plane / 4 + 255) / 256;
+  if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
+  k_split3<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, n / 4, plane / 4, static_cast<__nv_bfloat16*>(out_bf16));
+  RGNN_LAUNCH_CHECK("k_split3");
+  return 0;
+}
+
+// fp32 master weights [rows, cols] -> bf16 planes [3, rows, cols] and/or planes of the transpose [3, cols, rows] (either may be NULL)
+extern "C" int rgnn_tc_split3_weights(const float* w, int64_t rows, int64_t cols, void* out3, void* out3_t, void* stream) {
+  RGNN_REQUIRE(w && (out3 || out3_t) && rows > 0 && cols > 0 && rows < (1 << 30) && cols < (1 << 30), RGNN_E_ARG,
+               "rgnn_tc_split3_weights: bad arguments");
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  k_split3_weights<<<grid, 256, 0, as_stream(stream)>>>(w, (int)rows, (int)cols, static_cast<__nv_bfloat16*>(out3), static_cast<__nv_bfloat16*>(out3_t));
+  RGNN_LAUNCH_CHECK("k_split3_weights");
   return 0;
 }

@@ -202,8 +202,35 @@ def _cast_w(w, transpose=False, both=False, alpha=1.0, ident=0.0):
     return (o, ot) if both else (ot if transpose else o)
 
 
+def _split3(x, n_valid=None, plane=None):
+    """fp32 tensor -> bf16 planes [3, plane] with x = x0 + x1 + x2 (rgnn_tc_split3); elements [n_valid, plane) are zero."""
+    n = x.numel() if n_valid is None else n_valid
+    plane = n if plane is None else plane
+    out = torch.empty((3, plane), dtype=torch.bfloat16, device=x.device)
+    check(lib().rgnn_tc_split3(ptr(x), n, plane, ptr(out), stream()), "rgnn_tc_split3")
+    return out
+
+
+def _split3_w(w, transpose=False):
+    """fp32 master weight [R, C] -> bf16 planes [3, R, C] (or of the transpose, [3, C, R])."""
+    r, c = w.shape
+    out = torch.empty((3, c, r) if transpose else (3, r, c), dtype=torch.bfloat16, device=w.device)
+    check(lib().rgnn_tc_split3_weights(ptr(w), r, c, None if transpose else ptr(out), ptr(out) if transpose else None, stream()),
+          "rgnn_tc_split3_weights")
+    return out
+
+
 def _tc_splits(tiles, items):
     return max(1, min(items, 148 // max(1, tiles)))
+
+
+TC3_MAX_K_PER_ACC = 4096      # split-bf16 products: elements of the original K one TMEM accumulator may sum (error study, DESIGN §4)
+
+
+def _tc3_splits(tiles, kblocks, k_per_block=64):
+    """Split count of a split-plane weight-gradient GEMM: fill the SMs AND keep every accumulator's reduction short."""
+    need = (kblocks * k_per_block + TC3_MAX_K_PER_ACC - 1) // TC3_MAX_K_PER_ACC
+    return max(1, min(kblocks, max(_tc_splits(tiles, kblocks), need)))
 
 
 def _splits(tiles, work_items):
@@ -237,6 +264,13 @@ def _edge_mlp_forward(pose, w1, b1, w2, b2, out_dtype):
             with _lib.timed("mlp2_fwd", 2.0 * e * f2 * hid):
                 check(lib().rgnn_tc_gemm_tn(ptr(a1), hid, ptr(w2b), hid, ptr(z), f2, e, f2, hid,
                                             _lib.EPI_BIAS_N | _lib.EPI_SIGMOID, ptr(b2), None, 1.0, 0.0, stream()), "rgnn_tc_gemm_tn")
+        elif _lib.USE_TC3 and out_dtype == torch.float32 and hid % 64 == 0 and f2 % 128 == 0 and e > 0:
+            # fp32 parity mode on the tensor cores: split-bf16 planes, six plane-pair products, fp32 accumulate and output
+            prow = (e + 63) // 64 * 64
+            a1p, w2p = _split3(a1, e * hid, prow * hid), _split3_w(w2)
+            with _lib.timed("mlp2_fwd", 2.0 * e * f2 * hid):
+                check(lib().rgnn_tc3_gemm_tn(ptr(a1p), hid, prow, ptr(w2p), hid, f2, ptr(z), f2, e, f2, hid,
+                                             _lib.EPI_BIAS_N | _lib.EPI_SIGMOID, ptr(b2), 1.0, stream()), "rgnn_tc3_gemm_tn")
         else:
             _gemm(a1, (0, 0, hid, 1), w2, (0, 0, 1, hid), z, (0, f2, 1), e, f2, hid,
                   epi=_lib.EPI_BIAS_N | _lib.EPI_SIGMOID, bias=b2, tag="mlp2_fwd")
@@ -282,6 +316,19 @@ def edge_mlp_param_grads(pose, w2, a1, dzp):
         with _lib.timed("mlp2_dw", 2.0 * e * f2 * hid):
             check(lib().rgnn_tc_gemm_nn(ptr(dzp), f2, ptr(a1), hid, ptr(dw2), hid, f2, hid, e, 1.0, ptr(partial), split, stream()),
                   "rgnn_tc_gemm_nn")
+    elif _lib.USE_TC3 and a1.dtype == torch.float32 and dzp.dtype == torch.float32 and hid % 128 == 0 and f2 % 128 == 0 and e > 0:
+        prow = (e + 63) // 64 * 64                              # rows beyond E are zero planes: they are the K tail of dW2 = dZ^T . A1
+        dzp3, a13 = _split3(dzp, e * f2, prow * f2), _split3(a1, e * hid, prow * hid)
+        w2t3 = _split3_w(w2, transpose=True)                    # [3, hid, f2]: K-major for dA1 = dZ . W2
+        with _lib.timed("mlp2_dx", 2.0 * e * f2 * hid):
+            check(lib().rgnn_tc3_gemm_tn(ptr(dzp3), f2, prow, ptr(w2t3), f2, hid, ptr(da1), hid, e, hid, f2, 0, None, 1.0, stream()),
+                  "rgnn_tc3_gemm_tn")
+        check(lib().rgnn_relu_grad(dtype_code(a1), ptr(a1), ptr(da1), ptr(da1), a1.numel(), stream()), "rgnn_relu_grad")
+        split = _tc3_splits((f2 // 128) * (hid // (256 if hid % 256 == 0 else 128)), prow // 64)
+        partial = torch.empty((split, f2, hid), **f32)
+        with _lib.timed("mlp2_dw", 2.0 * e * f2 * hid):
+            check(lib().rgnn_tc3_gemm_nn(ptr(dzp3), f2, prow, ptr(a13), hid, prow, ptr(dw2), hid, f2, hid, e, 1.0, ptr(partial), split,
+                                         stream()), "rgnn_tc3_gemm_nn")
     else:
         _gemm(dzp, (0, 0, f2, 1), w2, (0, 0, hid, 1), da1, (0, hid, 1), e, hid, f2, epi=_lib.EPI_RELU_MASK, aux=a1, tag="mlp2_dx")
         split = _splits_mn(f2, hid, max(1, (e + 63) // 64))
@@ -299,7 +346,8 @@ def edge_mlp(pose, w1, b1, w2, b2, out_dtype=torch.float32):
 
 
 def _compress_forward(h, gh, wc, bc):
-    """-> (y, wc2 fp32 [Fo, 2F], used_tensor_cores)."""
+    """-> (y, wc2 fp32 [Fo, 2F], mode, planes): mode 0 = CUDA-core products, 1 = bf16 tcgen05, 3 = fp32 as split-bf16 planes on
+    tcgen05 (planes = (h3, g3), kept for the weight gradient; (None, None) otherwise)."""
     _lib.require_cuda(h, gh, wc, bc)
     n, f = h.shape[0], h.shape[1]
     _, p = _row_shape(h)
@@ -309,12 +357,20 @@ def _compress_forward(h, gh, wc, bc):
         raise ValueError("compress expects h, g_h [N,F,...] and weight [Fo, 2F(,1,1)]")
     bcf = bc.detach().float().contiguous()
     y = torch.empty((n, fo) + tuple(h.shape[2:]), dtype=h.dtype, device=h.device)
-    tc = bool(_lib.USE_TC and h.dtype == torch.bfloat16 and p == 64 and f % 64 == 0 and fo % 128 == 0 and n > 0)
+    shape_ok = p == 64 and f % 64 == 0 and fo % 128 == 0 and n > 0
+    tc = 1 if (_lib.USE_TC and h.dtype == torch.bfloat16 and shape_ok) else (3 if (_lib.USE_TC3 and h.dtype == torch.float32 and shape_ok) else 0)
+    planes = (None, None)
     with torch.cuda.device(h.device):
-        if tc:
+        if tc == 1:
             wb = _cast_w(wc2)
             with _lib.timed("compress_fwd", 2.0 * fo * 2 * f * n * p):
                 check(lib().rgnn_tc_conv1x1(ptr(wb), ptr(h), f, ptr(gh), f, ptr(y), fo, None, 0, ptr(bcf), n, stream()), "rgnn_tc_conv1x1")
+        elif tc == 3:
+            planes = (_split3(h), _split3(gh))
+            w3 = _split3_w(wc2)
+            with _lib.timed("compress_fwd", 2.0 * fo * 2 * f * n * p):
+                check(lib().rgnn_tc3_conv1x1(ptr(w3), ptr(planes[0]), f, ptr(planes[1]), f, n, ptr(y), fo, None, 0, ptr(bcf), n, stream()),
+                      "rgnn_tc3_conv1x1")
         else:
             if p == 1:    # [N,F,1,1] maps: the nodes form the N dimension of one product
                 sb, sc, bt, nn = (0, 0, 1, f), (0, 1, fo), 1, n
@@ -322,10 +378,10 @@ def _compress_forward(h, gh, wc, bc):
                 sb, sc, bt, nn = (f * p, 0, p, 1), (fo * p, p, 1), n, p
             _gemm(wc2, (0, 0, 2 * f, 1), h, sb, y, sc, fo, nn, f, batch=bt, epi=_lib.EPI_BIAS_M, bias=bcf, tag="compress_fwd")
             _gemm(wc2[:, f:], (0, 0, 2 * f, 1), gh, sb, y, sc, fo, nn, f, batch=bt, epi=_lib.EPI_ADD_AUX, aux=y, beta=1.0, tag="compress_fwd")
-    return y, wc2, tc
+    return y, wc2, tc, planes
 
 
-def _compress_backward(dy, h, gh, wc2, tc, need_dh, need_dgh, need_dw, need_db):
+def _compress_backward(dy, h, gh, wc2, tc, need_dh, need_dgh, need_dw, need_db, planes=(None, None)):
     """Autograd of the concat + 1x1 conv: dh (direct), dg_h, dWc [Fo, 2F] fp32, dbc [Fo] fp32."""
     n, f = h.shape[0], h.shape[1]
     _, p = _row_shape(h)
@@ -333,9 +389,25 @@ def _compress_backward(dy, h, gh, wc2, tc, need_dh, need_dgh, need_dw, need_db):
     dev = dy.device
     f32 = dict(dtype=torch.float32, device=dev)
     dh = dgh = dwc = dbc = None
-    tc_dx = tc and f % 128 == 0 and fo % 64 == 0
-    tc_dw = tc and f % 256 == 0 and fo % 128 == 0
+    tc_dx = tc == 1 and f % 128 == 0 and fo % 64 == 0
+    tc_dw = tc == 1 and f % 256 == 0 and fo % 128 == 0
+    tc3_dx = tc == 3 and f % 128 == 0 and fo % 64 == 0
+    tc3_dw = tc == 3 and f % 256 == 0 and fo % 128 == 0 and planes[0] is not None
     with torch.cuda.device(dev):
+        if (tc3_dx and (need_dh or need_dgh)) or (tc3_dw and need_dw):
+            dy3 = _split3(dy)
+        if tc3_dx and (need_dh or need_dgh):
+            wt3 = _split3_w(wc2, transpose=True)            # [3, 2F, Fo]
+            dh, dgh = torch.empty_like(h), torch.empty_like(gh)
+            with _lib.timed("compress_dx", 2.0 * fo * 2 * f * n * p):
+                check(lib().rgnn_tc3_conv1x1(ptr(wt3), ptr(dy3), fo, None, 0, n, ptr(dh), f, ptr(dgh), f, None, n, stream()), "rgnn_tc3_conv1x1")
+        if tc3_dw and need_dw:
+            dwc = torch.empty((fo, 2 * f), **f32)
+            split = _tc3_splits((fo // 128) * (2 * f // 256), n)
+            partial = torch.empty((split * fo * 2 * f,), **f32)
+            with _lib.timed("compress_dw", 2.0 * fo * 2 * f * n * p):
+                check(lib().rgnn_tc3_conv1x1_wgrad(ptr(dy3), fo, ptr(planes[0]), f, ptr(planes[1]), f, n, ptr(dwc), 2 * f, ptr(partial), split, n,
+                                                   stream()), "rgnn_tc3_conv1x1_wgrad")
         if tc_dx and (need_dh or need_dgh):
             wt = _cast_w(wc2, transpose=True)               # [2F, Fo] K-major: dX_v = Wc^T . dY_v
             dh, dgh = torch.empty_like(h), torch.empty_like(gh)
@@ -383,15 +455,16 @@ class CompressFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, gh, wc, bc):
         h, gh = h.contiguous(), gh.contiguous()
-        y, wc2, ctx.tc = _compress_forward(h, gh, wc, bc)
-        ctx.save_for_backward(h, gh, wc2)
+        y, wc2, ctx.tc, planes = _compress_forward(h, gh, wc, bc)
+        ctx.save_for_backward(h, gh, wc2, *[t for t in planes if t is not None])
         ctx.wshape = tuple(wc.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        h, gh, wc2 = ctx.saved_tensors
-        dh, dgh, dwc, dbc = _compress_backward(dy.contiguous(), h, gh, wc2, ctx.tc, *ctx.needs_input_grad)
+        h, gh, wc2 = ctx.saved_tensors[:3]
+        planes = tuple(ctx.saved_tensors[3:5]) if len(ctx.saved_tensors) >= 5 else (None, None)
+        dh, dgh, dwc, dbc = _compress_backward(dy.contiguous(), h, gh, wc2, ctx.tc, *ctx.needs_input_grad, planes=planes)
         return dh, dgh, (dwc.reshape(ctx.wshape) if dwc is not None else None), dbc
 
 
@@ -453,25 +526,28 @@ class GNNLayerFn(torch.autograd.Function):
                 with _lib.timed("compress_film_fused_fwd", 2.0 * fo * 2 * f * ix.N * p):
                     check(lib().rgnn_tc_conv_film_fused(ptr(wb), ptr(h), ptr(z), ptr(bcf), ptr(y), ptr(gh), ix.G, ix.complete_k, f, fo,
                                                         stream()), "rgnn_tc_conv_film_fused")
-            ctx.tc = True
+            ctx.tc = 1
+            planes = (None, None)
             if gh is None:
                 gh = h.new_empty(0)
         else:
             gh = torch.empty_like(h)
             with torch.cuda.device(h.device):
                 _aggregate(ix, h, z, True, None, _lib.POST_MEAN, None, None, gh, None, False)
-            y, wc2, ctx.tc = _compress_forward(h, gh, wc, bc)
+            y, wc2, ctx.tc, planes = _compress_forward(h, gh, wc, bc)
         ctx.g, ctx.wshape = g, tuple(wc.shape)
-        ctx.save_for_backward(h, pose, w2f, a1, z, gh, wc2)
+        ctx.save_for_backward(h, pose, w2f, a1, z, gh, wc2, *[t for t in planes if t is not None and need_bwd])
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        h, pose, w2f, a1, z, gh, wc2 = ctx.saved_tensors
+        h, pose, w2f, a1, z, gh, wc2 = ctx.saved_tensors[:7]
+        planes = tuple(ctx.saved_tensors[7:9]) if len(ctx.saved_tensors) >= 9 else (None, None)
         ix = ctx.g.index()
         need = ctx.needs_input_grad
         need_edge = any(need[2:6])
-        dh_direct, dgh, dwc, dbc = _compress_backward(dy.contiguous(), h, gh, wc2, ctx.tc, need[0], need[0] or need_edge, need[6], need[7])
+        dh_direct, dgh, dwc, dbc = _compress_backward(dy.contiguous(), h, gh, wc2, ctx.tc, need[0], need[0] or need_edge, need[6], need[7],
+                                                      planes=planes)
         dh = dw1 = db1 = dw2 = db2 = None
         with torch.cuda.device(dy.device):
             if need[0] or need_edge:
