@@ -48,6 +48,9 @@ def parse():
                          "GCN2Conv stack (DGL formula, SURVEY App. B) on channels-last [N, 64, F] features")
     ap.add_argument("--layers", type=int, default=2, choices=[1, 2], help="1 = gcn1 only (-multi_gcn off)")
     ap.add_argument("--no-compress", action="store_true", help="no 1x1 compress conv (-compress_gcn off; single layer only)")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the other_configs block (configs[3] at ResNet-50 width strong- and weak-scaled, one K=64 cell of configs[4])")
+    ap.add_argument("--wire", default="fp32", choices=["fp32", "bf16"], help="gradient all-reduce wire format (fp32 master buckets either way)")
     ap.add_argument("--torch-baseline", action="store_true",
                     help="also time a plain PyTorch-on-GPU restatement (index_select / index_add_ / conv2d) of the same step")
     return ap.parse_args()
@@ -146,33 +149,171 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def config_of(a, world):
+    """The `config` object of the JSON line - identical for both arms (`--impl ours|reference`) of one command line."""
+    return {"workload": workload_name(a), "graphs_per_gpu": a.graphs, "robots": a.robots, "feature_dim": a.feat, "pixels": PIX,
+            "stack": a.stack, "layers": a.layers, "compress": (not a.no_compress) if a.stack == "film" else None,
+            "l2_policy": "inputs (1.3 GB/GPU at the default workload) larger than the 126 MB L2",
+            "parallelism": f"dp{world}: graphs sharded, NCCL all-reduce of GNN-layer grads only"}
+
+
 def cpu_reference_rate(a, reps):
-    """The reference's CPU path (oracle/ref_port.py over oracle/dgl_shim; /root/reference cannot travel) on a bounded
-    sample of the same workload, fp32, all host threads."""
-    from oracle import ref_port
+    """The reference's CPU path on a bounded sample of the same workload, fp32, all host threads.  Preferred: the reference's own
+    classes, byte-compiled into oracle/_ref by build() (kind "reference"); else the op-for-op port oracle/ref_port.py (kind "port").
+    Both run over oracle/dgl_shim (DGL is not installable).  -> (graphs/s, cores, seconds per pass, kind)"""
+    from oracle import ref_port, ref_runner
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     if a.stack == "gcnii":
-        sec = ref_port.time_gcnii(a.feat, a.robots, a.cpu_graphs, layers=a.layers, reps=reps, threads=cores)
-    else:
-        sec = ref_port.time_block(a.feat, a.robots, a.cpu_graphs, not a.no_compress, a.layers == 2, reps=reps, threads=cores)
-    return a.cpu_graphs / sec, cores, sec
+        return a.cpu_graphs / ref_port.time_gcnii(a.feat, a.robots, a.cpu_graphs, layers=a.layers, reps=reps, threads=cores), cores, None, "port"
+    kind = "reference" if ref_runner.available() else "port"
+    mod = ref_runner if kind == "reference" else ref_port
+    sec = mod.time_block(a.feat, a.robots, a.cpu_graphs, not a.no_compress, a.layers == 2, reps=reps, threads=cores)
+    return a.cpu_graphs / sec, cores, sec, kind
+
+
+CPU_WHAT = {"reference": "unmodified reference classes (dgl/model/models.py byte-compiled into oracle/_ref: multi_view_dgl_model members, GCN, "
+                         "edge_encoder, edge_udf, node_udf) over the DGL-semantics shim, GNN slice models.py:181-189",
+            "port": "op-for-op port of the reference block (oracle/ref_port.py) over the DGL-semantics shim"}
 
 
 def run_reference(a, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores.  One "step" = one fwd+bwd
+    pass over the bounded sample; `steps` / `warmup` report the passes actually run (bounded so the arm ends within minutes)."""
     if rank != 0:
         return
     t0 = time.time()
-    rate, cores, sec = cpu_reference_rate(a, reps=max(1, min(a.steps, 5)))
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "graphs/s", "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "sample": f"{a.cpu_graphs} graphs per step (bounded sample of the workload)"},
-            "cpu_baseline": {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port",
-                             "sample": f"fwd+bwd of {a.cpu_graphs} graphs, best of {max(1, min(a.steps, 5))} after 1 warm-up, torch {torch.__version__} CPU"},
+    reps = max(1, min(a.steps, 5))
+    rate, cores, sec, kind = cpu_reference_rate(a, reps=reps)
+    sec = a.cpu_graphs / rate if sec is None else sec
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "graphs/s", "n_gpus": a.gpus, "steps": reps,
+            "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_of(a, a.gpus),
+            "cpu_baseline": {"value": rate, "unit": "graphs/s", "cores": cores, "kind": kind,
+                             "sample": f"{CPU_WHAT[kind]}; fwd+bwd of {a.cpu_graphs} graphs per step (bounded sample of the workload), "
+                                       f"best of {reps} after 1 warm-up, torch {torch.__version__} CPU, {cores} threads"},
             "e2e": {"value": rate, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "wall_s": time.time() - t0}
+            "requested": {"steps": a.steps, "warmup": a.warmup}, "wall_s": time.time() - t0}
     print(json.dumps(line))
+
+
+TRAFFIC_FILE = "traffic_r02.json"
+
+
+def peaks_for_other():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pk = {}
+    return pk.get("hbm_gbs", 6650.0), pk.get("bf16_tflops_sustained", 1400.0)
+
+
+def allreduce_cost(sync, step, barrier, dist, dev, world, n, ms_step_with):
+    """What the gradient all-reduce costs a step: (a) the collective alone, back to back on idle GPUs; (b) EXPOSED time = the step
+    with the reduction minus the same step without it (sync.enabled = False), both timed over n steps, max over ranks."""
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def only_reduce():
+        for bi in range(len(sync.buckets)):
+            sync._launch(bi)
+        sync.finish()
+    for _ in range(2):
+        only_reduce()
+    ar_ms = timed(only_reduce)
+    sync.enabled = False
+    step()
+    ms_without = timed(step)
+    sync.enabled = True
+    ms_with = timed(step)
+    return {"grad_bytes": sync.grad_bytes(), "wire_bytes": sync.wire_bytes(), "buckets": len(sync.buckets),
+            "allreduce_ms_alone": round(ar_ms, 4), "algbw_gbs": round(sync.wire_bytes() / (ar_ms * 1e-3) / 1e9, 1),
+            "ms_per_step_with": round(ms_with, 4), "ms_per_step_without": round(ms_without, 4),
+            "exposed_ms": round(ms_with - ms_without, 4), "exposed_frac": round((ms_with - ms_without) / ms_with, 4)}
+
+
+def other_configs(R, dist, dev, rank, world, wire, peaks):
+    """BASELINE.json configs[3] (ResNet-50 width F=2048, train_camera_warehouse_gcn2_resnet50.sh:4) strong- and weak-scaled, and one
+    cell of configs[4] (K = 64 robots), measured in the same process group right after the headline workload: graphs/s, the
+    dominant kernel's roofline, and (N > 1) the all-reduce cost with its exposed share.  Every entry is a full fwd+bwd(+all-reduce)."""
+    import types
+    hbm_peak, tc_peak = peaks
+    out = []
+    cells = [dict(name="C4 strong: F=2048, K=5, 2 layers + compress, bf16, 8192 graphs in total", F=2048, K=5, G=max(1, 8192 // world), scaling="strong", steps=4),
+             dict(name="C4 weak: F=2048, K=5, 2 layers + compress, bf16, 1024 graphs per GPU", F=2048, K=5, G=1024, scaling="weak", steps=8),
+             dict(name="C5 cell: F=512, K=64 robots, 2 layers + compress, bf16, 128 graphs per GPU", F=512, K=64, G=128, scaling="weak", steps=6)]
+    for c in cells:
+        F, K, G = c["F"], c["K"], c["G"]
+        N, E = G * K, G * K * (K - 1)
+        torch.manual_seed(1)
+        blk = R.GNNBlock(types.SimpleNamespace(feature_dim=F, compress_gcn=True, multi_gcn=True)).to(dev)
+        sync = R.parallel.GradSync(blk, wire_dtype=wire) if world > 1 else None
+        gen = torch.Generator(device=dev).manual_seed(1 + rank)
+        h = torch.relu(torch.randn((N, F, 8, 8), generator=gen, device=dev, dtype=torch.float32)).bfloat16().requires_grad_()
+        dy = torch.randn((N, F, 8, 8), generator=gen, device=dev, dtype=torch.float32).bfloat16()
+        pose = torch.randn((E, 9), generator=gen, device=dev, dtype=torch.float32)
+        g = R.robot_batch(G, K, device=dev)
+        g.index()
+
+        def step():
+            h.grad = None
+            if sync is not None:
+                sync.zero_grad()
+            else:
+                for p in blk.parameters():
+                    p.grad = None
+            blk(g, h, pose).backward(dy)
+            if sync is not None:
+                sync.finish()
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        for _ in range(3):
+            step()
+        barrier()
+        R._lib.PROFILE = {}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(c["steps"]):
+            step()
+        e1.record()
+        barrier()
+        prof = R._lib.profile_summary()
+        R._lib.PROFILE = None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_step = float(ms.item()) / c["steps"]
+        top, d = max(prof.items(), key=lambda kv: kv[1]["ms_total"])
+        mem = top.startswith(MEM_KERNELS)
+        ach = d["work_total"] / (d["ms_total"] * 1e-3) / (1e9 if mem else 1e12)
+        ent = {"name": c["name"], "scaling": c["scaling"], "n_gpus": world, "graphs_per_gpu": G, "robots": K, "feature_dim": F,
+               "value": world * G / (ms_step * 1e-3), "unit": "graphs/s", "ms_per_step": round(ms_step, 4), "steps": c["steps"], "warmup": 3,
+               "roofline": {"kernel": top, "bound": "hbm" if mem else "tensor", "achieved": round(ach, 2), "unit": "GB/s" if mem else "TFLOP/s",
+                            "peak": hbm_peak if mem else tc_peak, "frac": round(ach / (hbm_peak if mem else tc_peak), 4),
+                            "ms_avg_per_launch": round(d["ms_avg"], 4), "share": round(d["ms_total"] / (ms_step * c["steps"]), 4)}}
+        if sync is not None:
+            ok, dev_rel = sync.check_ranks_agree()
+            ent["grad_sync_check"] = "ok" if ok else f"MISMATCH ({dev_rel:.3e})"
+            ent["comm"] = allreduce_cost(sync, step, barrier, dist, dev, world, max(3, c["steps"] // 2), ms_step)
+            sync.remove()
+        out.append(ent)
+        del blk, sync, h, dy, pose, g
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -222,7 +363,8 @@ def main():
     else:
         blk = R.GNNBlock(types.SimpleNamespace(feature_dim=F, compress_gcn=not a.no_compress, multi_gcn=a.layers == 2))
     blk.to(dev)
-    sync = R.parallel.GradSync(blk) if world > 1 else None
+    wire = torch.bfloat16 if a.wire == "bf16" else None
+    sync = R.parallel.GradSync(blk, wire_dtype=wire) if world > 1 else None
 
     # synthetic inputs of the scripts' shape, seeded per rank; resident in HBM for `value`
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -236,8 +378,11 @@ def main():
 
     def step():
         h.grad = None
-        for p in blk.parameters():
-            p.grad = None
+        if sync is not None:
+            sync.zero_grad()          # gradients are views into the persistent all-reduce buckets
+        else:
+            for p in blk.parameters():
+                p.grad = None
         y = blk(g, h, pose)
         y.backward(dy)
         if sync is not None:
@@ -279,6 +424,13 @@ def main():
     clk = clocks.stop() if rank == 0 else None
     value = world * G * a.steps / (ms_total * 1e-3)
 
+    # ---- N > 1: do the ranks agree on the reduced gradients, and what does the all-reduce cost the step? -------------------
+    comm = None
+    if sync is not None:
+        ok, dev_rel = sync.check_ranks_agree()
+        comm = {"grad_sync_check": "ok" if ok else f"MISMATCH (max relative deviation of bucket checksums {dev_rel:.3e})"}
+        comm.update(allreduce_cost(sync, step, barrier, dist, dev, world, max(3, min(a.steps, 10)), ms_total / a.steps))
+
     # ---- e2e: the public call with HOST buffers; H2D of the step's inputs and D2H of its results inside the timed region
     e2e = None
     if not a.no_e2e:
@@ -287,19 +439,16 @@ def main():
         h2d = hh.numel() * hh.element_size() + hdy.numel() * hdy.element_size() + hpose.numel() * 4
         d2h = 2 * out_y.numel() * out_y.element_size()
 
-        pipe = R.HostPipeline(blk, G, K, F, dtype=dtype, device=dev, chunks=a.e2e_chunks, out_feat=f_out)
+        pipe = R.HostPipeline(blk, G, K, F, dtype=dtype, device=dev, chunks=a.e2e_chunks, out_feat=f_out, grad_sync=sync)
         h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
 
         def e2e_step():
-            # single GPU: steps stream back to back through the pipeline (every step still copies its own inputs in and its own
-            # results out inside the timed region); with gradient all-reduce the calling stream joins after every step
-            pipe.step(hh, hpose, hdy, out_y, out_dh, wait=sync is not None)
-            if sync is not None:
-                sync.finish()
+            # steps stream back to back through the pipeline (every step still copies its own inputs in and its own results out
+            # inside the timed region).  N > 1: the gradients of all chunks accumulate in the all-reduce buckets and ONE reduction per
+            # bucket is enqueued on the compute stream behind the last chunk - no per-step join, the next step's copies run under it
+            pipe.step(hh, hpose, hdy, out_y, out_dh, wait=False)
 
         n_e2e = max(3, min(a.steps, 10))
-        if sync is not None:
-            sync.overlap = False       # gradients accumulate over the chunks; one reduction after the last chunk
         e2e_step(); e2e_step()
         pipe.wait()
         barrier()
@@ -341,6 +490,17 @@ def main():
         torch_gpu = {"value": G * nt / (t0.elapsed_time(t1) * 1e-3), "unit": "graphs/s", "ms_per_step": t0.elapsed_time(t1) / nt,
                      "what": f"plain PyTorch {torch.__version__} eager on the same GPU and inputs (index_select / index_add_ / cuBLAS / cuDNN), 1 GPU"}
 
+    # ---- the other BASELINE configs in the same run (every rank takes part; rank 0 reports) ---------------------------------
+    other = None
+    if not a.no_other_configs and a.stack == "film" and (a.feat, a.robots, a.graphs, a.dtype, a.layers) == (F_DIM, K_ROBOTS, 4096, "bf16", 2):
+        del h, dy, pose, g, blk, sync
+        if not a.no_e2e:
+            del pipe, hh, hdy, hpose, out_y, out_dh
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        other = other_configs(R, dist, dev, rank, world, wire, peaks_for_other())
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -369,33 +529,37 @@ def main():
                                         "unit": "GB/s", "frac": 0.0}
     top, topd = by_time[0]
     top_mem = top.startswith(MEM_KERNELS)
-    traffic = None
-    try:    # measured once under ncu --set full for this exact workload (profiles/); only valid for the default workload
-        if (G, K, F, a.dtype) == (4096, 5, 512, "bf16"):
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json"))).get(top)
+    traffic, traffic_source = None, None
+    try:    # measured once under `ncu --set full` for this exact workload and committed under profiles/ (NOT measured in this run)
+        if (G, K, F, a.dtype, a.stack, a.layers) == (4096, 5, 512, "bf16", "film", 2) and not a.no_compress:
+            tj = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))
+            traffic = tj.get(top)
+            traffic_source = f"profiles/{TRAFFIC_FILE}: dram__bytes_read.sum + dram__bytes_write.sum per launch from {tj.get('_source', 'an ncu --set full capture')}"
     except Exception:
         pass
     roofline = {"kernel": top, "bound": "hbm" if top_mem else "tensor", "achieved": kernels[top]["achieved"],
                 "peak": hbm_peak if top_mem else tc_peak, "unit": kernels[top]["unit"], "frac": kernels[top]["frac"],
-                "traffic": traffic, "algorithmic_per_launch": topd["work_total"] / max(1, topd["calls"]),
+                "traffic": traffic, "traffic_source": traffic_source, "algorithmic_per_launch": topd["work_total"] / max(1, topd["calls"]),
                 "peak_source": peak_src, "ms_avg_per_launch": kernels[top]["ms_avg"]}
 
     cpu = None
     if not a.no_cpu_baseline:
-        rate, cores, sec = cpu_reference_rate(a, reps=3)
-        cpu = {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port",
-               "sample": f"{'reference CPU path' if a.stack == 'film' else 'DGL-formula GCN2Conv stack on CPU'} (oracle/ref_port.py over the DGL-semantics shim), fp32, fwd+bwd of {a.cpu_graphs} graphs, "
-                         f"best of 3 after 1 warm-up ({sec * 1e3:.1f} ms)"}
+        rate, cores, sec, kind = cpu_reference_rate(a, reps=3)
+        what = CPU_WHAT[kind] if a.stack == "film" else "DGL-formula GCN2Conv stack on CPU (oracle/dgl_shim)"
+        cpu = {"value": rate, "unit": "graphs/s", "cores": cores, "kind": kind,
+               "sample": f"{what}, fp32, fwd+bwd of {a.cpu_graphs} graphs, best of 3 after 1 warm-up ({a.cpu_graphs / rate * 1e3:.1f} ms)"}
 
     line = {"metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": a.dtype, "data": "synthetic",
-            "config": {"workload": workload_name(a), "graphs_per_gpu": G, "robots": K, "feature_dim": F, "pixels": PIX,
-                       "stack": a.stack, "layers": a.layers, "compress": (not a.no_compress) if a.stack == "film" else None, "l2_policy": "inputs (1.3 GB/GPU) larger than the 126 MB L2",
-                       "parallelism": f"dp{world}: graphs sharded, NCCL all-reduce of GNN-layer grads only",
-                       "numa_node_rank0": numa},
+            "config": config_of(a, world), "numa_node_rank0": numa,
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk}
+    if comm is not None:
+        line["comm"] = comm
+        line["grad_sync_check"] = comm["grad_sync_check"]
+    if other is not None:
+        line["other_configs"] = other
     if torch_gpu is not None:
         line["torch_gpu_baseline"] = torch_gpu
     print(json.dumps(line))

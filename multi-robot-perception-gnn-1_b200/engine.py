@@ -18,7 +18,8 @@ from .graph import robot_batch
 
 
 class HostPipeline:
-    def __init__(self, block, num_graphs, robots, feat, dtype=torch.bfloat16, device="cuda", chunks=8, slots=3, hw=(8, 8), out_feat=None):
+    def __init__(self, block, num_graphs, robots, feat, dtype=torch.bfloat16, device="cuda", chunks=8, slots=3, hw=(8, 8), out_feat=None,
+                 grad_sync=None):
         if num_graphs % chunks:
             raise ValueError("num_graphs must be a multiple of chunks")
         self.block, self.G, self.K, self.F, self.dtype = block, num_graphs, robots, feat, dtype
@@ -27,6 +28,10 @@ class HostPipeline:
         self.gc = num_graphs // chunks
         self.nc, self.ec = self.gc * robots, self.gc * robots * (robots - 1)
         self.hw = hw
+        # data-parallel runs: a parallel.GradSync whose buckets hold the parameter gradients.  The gradients of all chunks accumulate
+        # in the buckets (hooks quiet), and ONE all-reduce per bucket is enqueued on the compute stream behind the last chunk, so
+        # consecutive steps keep streaming (wait=False) - the next step's first chunks copy in while the reduction runs.
+        self.grad_sync = grad_sync
         out_feat = feat if out_feat is None else out_feat        # 2 * feat for a block without the compress conv (cat output)
         self.graph = robot_batch(self.gc, robots, device=self.dev)
         self.graph.index()
@@ -49,8 +54,13 @@ class HostPipeline:
         cur = torch.cuda.current_stream(self.dev)
         for s in (self.s_in, self.s_comp, self.s_out):
             s.wait_stream(cur)
-        for p in self.block.parameters():           # (allocated on s_comp: the memory goes back to that stream's pool)
-            p.grad = None
+        if self.grad_sync is not None:
+            self.grad_sync.overlap = False
+            with torch.cuda.stream(self.s_comp):
+                self.grad_sync.zero_grad()
+        else:
+            for p in self.block.parameters():       # (allocated on s_comp: the memory goes back to that stream's pool)
+                p.grad = None
         ev_comp = [None] * self.chunks
         for i in range(self.chunks):
             sl = i % self.slots
@@ -78,6 +88,9 @@ class HostPipeline:
                 dhd.record_stream(self.s_out)
                 y_out[n0:n1].copy_(yd, non_blocking=True)
                 dh_out[n0:n1].copy_(dhd, non_blocking=True)
+        if self.grad_sync is not None:
+            with torch.cuda.stream(self.s_comp):
+                self.grad_sync.finish()             # stream-ordered: the host does not block, s_comp waits for NCCL
         for i in range(max(0, self.chunks - self.slots), self.chunks):
             self._slot_done[i % self.slots] = ev_comp[i]
         if wait:

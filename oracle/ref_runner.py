@@ -1,0 +1,106 @@
+"""Run the UNMODIFIED reference classes (byte-compiled into oracle/_ref by oracle/build_ref.py) on the CPU - the timed
+`--impl reference` arm and `cpu_baseline` of bench.py (kind "reference"), and a second pin for the oracle (TEST INFRASTRUCTURE).
+
+What is the reference's and what is restated here:
+  * reference, unmodified (from oracle/_ref/model/models.pyc): `multi_view_dgl_model.__init__` (it creates gcn1 / conv1 / gcn2 /
+    conv2 exactly as the scripts do, models.py:158-171), `GCN`, `edge_encoder.forward` (models.py:152-155), `edge_udf`, `node_udf`
+    (models.py:207-211);
+  * restated: the DGL runtime underneath (oracle/dgl_shim - DGL is not installable here), and the two statements of
+    `GCN.forward` around `update_all` (models.py:219-226) so that the layer returns ndata['images'] - the aggregate `node_udf`
+    writes - instead of its input: with the literal return the backward would skip the aggregation entirely and the
+    timed work would not be the layer's;
+  * the torchvision encoder and the decoder are out of scope: their constructors are stubbed while the model object is
+    built, and the timed region is the GNN slice of `multi_view_dgl_model.forward` (models.py:181-189) only.
+"""
+import importlib
+import os
+import sys
+import time
+import types
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIM = os.path.join(HERE, "dgl_shim")
+_REF = os.path.join(HERE, "_ref")
+
+
+def available():
+    return all(os.path.exists(os.path.join(_REF, "model", f)) for f in ("models.pyc", "blocks.pyc"))
+
+
+def load():
+    """-> (dgl shim module, reference `model.models` module)."""
+    if not available():
+        raise RuntimeError("oracle/_ref is not built (run __graft_entry__.build() where /root/reference is mounted)")
+    for p in (_SHIM, _REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    other = sys.modules.get("model")
+    if other is not None and _REF not in [os.path.dirname(p) for p in getattr(other, "__path__", [])]:
+        raise RuntimeError("another package named `model` is already imported (compat/model?); run the reference in its own process")
+    dgl = importlib.import_module("dgl")
+    ref = importlib.import_module("model.models")
+    return dgl, ref
+
+
+def make_model(ref, f, k, compress_gcn, multi_gcn):
+    opt = types.SimpleNamespace(feature_dim=f, compress_gcn=compress_gcn, multi_gcn=multi_gcn, camera_num=k, image_size=256,
+                                task='depth', skip_level=False, backbone='resnet18', pretrained=False)
+    enc, dec = ref.encoder, ref.decoder
+    ref.encoder = lambda o: torch.nn.Identity()
+    ref.decoder = lambda o, d: torch.nn.Identity()
+    try:
+        return ref.multi_view_dgl_model(opt)
+    finally:
+        ref.encoder, ref.decoder = enc, dec
+
+
+def gnn_layer(ref, gcn, g, h):
+    """GCN.forward (models.py:219-226) with the intended return key."""
+    with g.local_scope():
+        g.ndata['image'] = h
+        with g.local_scope():
+            g.edata['pose_gamma'], g.edata['pose_beta'] = gcn.edge_encoder(g.edata['pose'])
+            g.update_all(ref.edge_udf, ref.node_udf)
+            return g.ndata['images']
+
+
+def gnn_slice(ref, model, g, h):
+    """models.py:181-189."""
+    g_h = gnn_layer(ref, model.gcn1, g, h)
+    h = torch.cat((h, g_h), dim=1)
+    if model.opt.compress_gcn:
+        h = model.conv1(h)
+    if model.opt.multi_gcn:
+        g_h = gnn_layer(ref, model.gcn2, g, h)
+        h = torch.cat((h, g_h), dim=1)
+        h = model.conv2(h)
+    return h
+
+
+def time_block(f, k, graphs, compress_gcn, multi_gcn, reps=3, threads=None, seed=1):
+    """fwd+bwd seconds (best of `reps` after one warm-up) of the reference's GNN slice on `graphs` K-robot graphs, fp32."""
+    from . import gnn_oracle as O
+    dgl, ref = load()
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(seed)
+    sb = O.synthetic_batch(graphs, k, f, p=64, seed=seed)
+    n = graphs * k
+    model = make_model(ref, f, k, compress_gcn, multi_gcn)
+    g = dgl.graph((torch.as_tensor(sb["src"]), torch.as_tensor(sb["dst"])), num_nodes=n)
+    g.edata['pose'] = sb["pose"]
+    h = sb["h"].reshape(n, f, 8, 8).clone().requires_grad_()
+    dy = torch.randn((n, f if compress_gcn else 2 * f, 8, 8), generator=torch.Generator().manual_seed(2))
+    best = float("inf")
+    for it in range(reps + 1):
+        model.zero_grad(set_to_none=True)
+        h.grad = None
+        t0 = time.perf_counter()
+        y = gnn_slice(ref, model, g, h)
+        y.backward(dy)
+        dt = time.perf_counter() - t0
+        if it > 0:
+            best = min(best, dt)
+    return best

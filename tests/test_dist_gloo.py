@@ -45,6 +45,33 @@ def _worker(rank, world, port, q):
     loss.backward()
     sync.finish()
     ok2 = all(torch.allclose(p.grad, torch.full_like(p, 2.0)) for p in blk.parameters())
+    # third step the intended way: zero_grad() keeps every .grad a view into its persistent flat bucket (no cat / copy-back),
+    # autograd accumulates in place, and after finish() the ranks hold bit-identical buckets
+    sync.zero_grad()
+    views_ok = all(p.grad.data_ptr() == v.data_ptr() for b, vs in zip(sync.buckets, sync._views) for (_, p), v in zip(b, vs))
+    loss = sum((p * float(rank + 1)).sum() for p in blk.parameters())
+    loss.backward()
+    views_ok = views_ok and all(p.grad.data_ptr() == v.data_ptr() for b, vs in zip(sync.buckets, sync._views) for (_, p), v in zip(b, vs))
+    sync.finish()
+    ok3 = all(torch.allclose(p.grad, torch.full_like(p, 1.5)) for p in blk.parameters())
+    agree, _ = sync.check_ranks_agree()
+    # accumulate over two backward passes with the hooks quiet, reduce once (HostPipeline chunks)
+    sync.zero_grad()
+    sync.overlap = False
+    for _ in range(2):
+        sum((p * float(rank + 1)).sum() for p in blk.parameters()).backward()
+    sync.finish()
+    ok4 = all(torch.allclose(p.grad, torch.full_like(p, 3.0)) for p in blk.parameters())
+    sync.remove()
+    # bf16 wire format: half the bytes on the link, fp32 master buckets
+    for p in blk.parameters():
+        p.grad = None
+    sync16 = R.parallel.GradSync(blk, wire_dtype=torch.bfloat16)
+    sum((p * (0.1 * (rank + 1))).sum() for p in blk.parameters()).backward()
+    sync16.finish()
+    ok5 = all(torch.allclose(p.grad, torch.full_like(p, 0.15), rtol=1e-2) for p in blk.parameters()) and sync16.check_ranks_agree()[0] \
+        and sync16.wire_bytes() * 2 == sync16.grad_bytes()
+    ok2 = ok2 and views_ok and ok3 and agree and ok4 and ok5
     lo, hi = R.parallel.shard_range(11, rank, world)
     q.put((rank, local, out, ok2, (lo, hi)))
     dist.destroy_process_group()

@@ -151,3 +151,32 @@ def test_ref_port_matches_golden(ci):
     assert nerr(y, c["y"]) <= 1e-6
     y.backward(t(c["dy"]))
     assert nerr(h.grad, c["dh"]) <= 1e-6
+
+
+@pytest.mark.parametrize("ci", range(len(load_cases("block_cases.npz"))))
+def test_compiled_reference_matches_golden(ci):
+    """oracle/_ref (the reference's own classes, byte-compiled by oracle/build_ref.py) driven by oracle/ref_runner.py - what
+    `bench.py --impl reference` times - reproduces the golden outputs made from the reference sources."""
+    from oracle import ref_runner
+    if not ref_runner.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    dgl, ref = ref_runner.load()
+    c = load_cases("block_cases.npz")[ci]
+    seed, f, k, gN, comp, multi = [int(v) for v in c["cfg"]]
+    t = lambda a: torch.from_numpy(np.asarray(a))
+    model = ref_runner.make_model(ref, f, k, bool(comp), bool(multi))
+    assert type(model).__name__ == "multi_view_dgl_model" and type(model.gcn1).__module__ == "model.models"
+    sd = {}
+    for j in range(2 if multi else 1):
+        pre = f"gcn{j + 1}.edge_encoder.layers."
+        sd.update({pre + "0.weight": t(c[f"l{j}_w1"]), pre + "0.bias": t(c[f"l{j}_b1"]), pre + "2.weight": t(c[f"l{j}_w2"]), pre + "2.bias": t(c[f"l{j}_b2"])})
+        if comp:
+            sd.update({f"conv{j + 1}.weight": t(c[f"l{j}_wc"]).reshape(f, 2 * f, 1, 1), f"conv{j + 1}.bias": t(c[f"l{j}_bc"])})
+    model.load_state_dict(sd, strict=True)
+    g = dgl.graph((t(c["src"]), t(c["dst"])), num_nodes=gN * k)
+    g.edata['pose'] = t(c["pose"])
+    h = t(c["h"]).clone().requires_grad_()
+    y = ref_runner.gnn_slice(ref, model, g, h)
+    assert nerr(y, c["y"]) <= 1e-6
+    y.backward(t(c["dy"]))
+    assert nerr(h.grad, c["dh"]) <= 1e-6
