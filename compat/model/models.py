@@ -127,7 +127,8 @@ class multi_view_dgl_model(nn.Module):
             h_list = self.encoder(image)
             h = h_list[-1]
             h = h.view(-1, h.size(-3), h.size(-2), h.size(-1))
-            h = rg.gnn_slice(self, g, h.contiguous())                       # models.py:180-189
+            # models.py:180-189; under torch.no_grad() (dgl/eval.py) small batches replay a captured CUDA graph of the slice
+            h = rg.gnn_slice_auto(self, g, h.contiguous())
             if self.opt.task == 'depthseg':
                 # the reference never builds depth_decoder / seg_decoder for this model (models.py:191-193)
                 raise AttributeError("multi_view_dgl_model has no depth_decoder/seg_decoder (reference defect, task=depthseg)")

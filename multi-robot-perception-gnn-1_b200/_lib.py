@@ -124,7 +124,15 @@ def ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_cur_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def stream():
+    """torch's current stream on the current device as a cudaStream_t.  The raw C accessors are ~20x cheaper than
+    torch.cuda.current_stream().cuda_stream, and at the reference's batch (8 graphs) the step is host-bound: 30 such lookups."""
+    if _raw_stream is not None and _cur_device is not None:
+        return ctypes.c_void_p(_raw_stream(_cur_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

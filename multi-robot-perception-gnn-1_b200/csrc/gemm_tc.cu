@@ -554,13 +554,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
 }
 
-// out[i] = alpha * sum_s partial[s][i]   (fixed order: deterministic)
+// out[i] = alpha * sum_s partial[s][i]   (fixed order: deterministic); optionally, in the same launch, a second (small) segment:
+// out2[j] = sum_s part2[s][j], j < n2 (the conv bias gradient's row-sum partials ride on the weight gradient's reduction)
 __global__ void __launch_bounds__(256) k_sum_partials(const float* __restrict__ part, int splits, int64_t n, float* __restrict__ out,
-                                                      int64_t ld_out, int64_t cols, float alpha) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+                                                      int64_t ld_out, int64_t cols, float alpha, const float* __restrict__ part2 = nullptr,
+                                                      int64_t n2 = 0, float* __restrict__ out2 = nullptr) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n + n2; i += (int64_t)gridDim.x * blockDim.x) {
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += part[(int64_t)s * n + i];
-    out[(i / cols) * ld_out + (i % cols)] = alpha * acc;
+    if (i < n) {
+      for (int s = 0; s < splits; ++s) acc += part[(int64_t)s * n + i];
+      out[(i / cols) * ld_out + (i % cols)] = alpha * acc;
+    } else {
+      const int64_t j = i - n;
+      for (int s = 0; s < splits; ++s) acc += part2[(int64_t)s * n2 + j];
+      out2[j] = acc;
+    }
   }
 }
 
@@ -870,14 +878,10 @@ static int wgrad_impl(const void* dy, int64_t M, const void* x0, int64_t c0, con
   int rc = launch<BN>(ta, tb0, tb1, p, st);
   if (rc) return rc;
   const int64_t n = M * Nn;
-  int64_t blocks = (n + 255) / 256;
+  int64_t blocks = (n + (dbias ? M : 0) + 255) / 256;
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-  k_sum_partials<<<(unsigned)blocks, 256, 0, st>>>(partial, (int)splits, n, dW, ldw, Nn, 1.0f);
+  k_sum_partials<<<(unsigned)blocks, 256, 0, st>>>(partial, (int)splits, n, dW, ldw, Nn, 1.0f, dbias ? p.rowsum : nullptr, dbias ? M : 0, dbias);
   RGNN_LAUNCH_CHECK("k_sum_partials");
-  if (dbias) {
-    k_sum_partials<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(p.rowsum, (int)splits, M, dbias, M, M, 1.0f);
-    RGNN_LAUNCH_CHECK("k_sum_partials(bias)");
-  }
   return 0;
 }
 

@@ -205,6 +205,15 @@ inline int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
                     CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   RGNN_REQUIRE(enc, RGNN_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  {
+    // cuTensorMapEncodeTiled is a DRIVER call and wants a current context on the calling thread (CUDA_ERROR_INVALID_CONTEXT
+    // otherwise).  Autograd's backward threads may not have touched the runtime yet: bind the device's primary context once
+    // per (thread, device) with a no-op runtime call.
+    static thread_local int ctx_dev = -1;
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d != ctx_dev) { cudaFree(nullptr); ctx_dev = d; }
+  }
   cuuint64_t d[5]; cuuint64_t s[5]; cuuint32_t b[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];

@@ -12,6 +12,8 @@ The reference has no counterpart (its loop moves a whole DGL batch with data.to(
 everything else on the device); this exists so that end-to-end throughput with host-resident data is bounded by the PCIe
 link, not by serialising copies and kernels.
 """
+import weakref
+
 import torch
 
 from .graph import robot_batch
@@ -148,3 +150,66 @@ class GraphedStep:
         for p, gr in self.param_grads:      # re-attach in case the caller replaced or cleared .grad (optimizer.zero_grad)
             p.grad = gr
         return self.y, self.dh
+
+
+class GraphedForward:
+    """Forward-only GNN slice (dgl/model/models.py:180-189) captured once into a CUDA graph and replayed per batch - the eval path
+    (dgl/eval.py:23 runs batch 1 under torch.no_grad(): 5 robots, ~10 short kernels, pure launch latency when issued one by one).
+    Valid for batches of `num_graphs` complete `robots`-node graphs in the reference's edge order (every batch of the reference's
+    dataset is one; dataloader.py:88-95), so the topology is a constant of the captured graph and only h / pose are copied in.
+    The weight casts are part of the captured graph: a replay always uses the module's current weights.
+    The returned tensor is a static buffer that the next call overwrites."""
+
+    def __init__(self, mod, num_graphs, robots, feat, dtype=torch.float32, device="cuda", hw=(8, 8), warmup=2):
+        from .layers import gnn_slice
+        self.dev = torch.device(device)
+        self.g = robot_batch(num_graphs, robots, device=self.dev)
+        self.g.index()
+        n, e = num_graphs * robots, num_graphs * robots * (robots - 1)
+        self.h = torch.zeros((n, feat) + tuple(hw), dtype=dtype, device=self.dev)
+        self.pose = torch.zeros((e, 9), dtype=torch.float32, device=self.dev)
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(cur)
+        with torch.no_grad():
+            with torch.cuda.stream(side):
+                for _ in range(warmup):      # first calls set kernel attributes: must happen outside capture
+                    gnn_slice(mod, self.g, self.h, self.pose)
+            cur.wait_stream(side)
+            self.cuda_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.cuda_graph):
+                self.y = gnn_slice(mod, self.g, self.h, self.pose)
+
+    def __call__(self, h, pose):
+        with torch.no_grad():
+            self.h.copy_(h)
+            self.pose.copy_(pose)
+        self.cuda_graph.replay()
+        return self.y
+
+
+_GRAPHED = weakref.WeakKeyDictionary()      # module -> {(G, K, F, hw, dtype, device): GraphedForward}; never pickled with the module
+GRAPHED_EVAL_MAX_NODES = 4096               # above this the kernels are long enough that launch latency does not matter
+
+
+def gnn_slice_auto(mod, g, h, pose=None):
+    """gnn_slice, replayed from a captured CUDA graph when that is safe and pays: gradients disabled (eval), a CUDA batch of complete
+    K-robot graphs (2..8 robots), intended return key, small batch.  Anything else runs the eager path."""
+    from .layers import gnn_slice
+    opt = mod.opt
+    k = g.complete_k
+    ok = (not torch.is_grad_enabled() and h.is_cuda and 2 <= k <= 8 and g.num_nodes() == g.batch_size * k and h.dim() == 4
+          and g.num_nodes() <= GRAPHED_EVAL_MAX_NODES and getattr(opt, "compress_gcn", False)
+          and mod.gcn1.return_key == "images" and mod.gcn1.film and h.dtype in (torch.float32, torch.bfloat16)
+          and not torch.cuda.is_current_stream_capturing())
+    if not ok:
+        return gnn_slice(mod, g, h, pose)
+    pose = g.edata['pose'] if pose is None else pose
+    key = (g.batch_size, k, h.shape[1], tuple(h.shape[2:]), h.dtype, h.device)
+    cache = _GRAPHED.setdefault(mod, {})
+    gf = cache.get(key)
+    if gf is None:
+        if len(cache) >= 8:                 # a handful of batch shapes at most (last partial batch of an epoch)
+            cache.clear()
+        gf = cache[key] = GraphedForward(mod, g.batch_size, k, h.shape[1], h.dtype, h.device, tuple(h.shape[2:]))
+    return gf(h, pose)

@@ -202,6 +202,38 @@ def _cast_w(w, transpose=False, both=False, alpha=1.0, ident=0.0):
     return (o, ot) if both else (ot if transpose else o)
 
 
+def _cached_casts(w, wf, split3=False):
+    """bf16 copy AND bf16 transpose (or the split-bf16 planes of both) of a weight, cached on the parameter object `w` until the
+    parameter changes (`_version`: optimizer steps and load_state_dict write in place and bump it).  One cast kernel produces both
+    orientations, so a training step pays one launch per weight instead of one per use (forward + dX), and a loop over fixed
+    weights (eval, the bench) pays none.  `wf` is the fp32 contiguous 2-D view the kernels read.  During CUDA-graph capture the
+    cast is always re-issued into the cached buffers, so a replayed graph re-casts the weights it finds at replay time."""
+    r, c = wf.shape
+    key = "_rgnn_cast3" if split3 else "_rgnn_cast"
+    ent = getattr(w, key, None)
+    ver = w._version
+    fresh = ent is not None and ent[0] == ver and ent[1].device == wf.device and ent[3] == wf.data_ptr() and tuple(ent[1].shape[-2:]) == (r, c)
+    if fresh and not torch.cuda.is_current_stream_capturing():
+        return ent[1], ent[2]
+    if ent is not None and ent[1].device == wf.device and tuple(ent[1].shape[-2:]) == (r, c):
+        o, ot = ent[1], ent[2]
+    elif split3:
+        o = torch.empty((3, r, c), dtype=torch.bfloat16, device=wf.device)
+        ot = torch.empty((3, c, r), dtype=torch.bfloat16, device=wf.device)
+    else:
+        o = torch.empty((r, c), dtype=torch.bfloat16, device=wf.device)
+        ot = torch.empty((c, r), dtype=torch.bfloat16, device=wf.device)
+    if split3:
+        check(lib().rgnn_tc_split3_weights(ptr(wf), r, c, ptr(o), ptr(ot), stream()), "rgnn_tc_split3_weights")
+    else:
+        check(lib().rgnn_tc_cast_weights(ptr(wf), r, c, ptr(o), ptr(ot), stream()), "rgnn_tc_cast_weights")
+    try:
+        setattr(w, key, (ver, o, ot, wf.data_ptr()))
+    except Exception:
+        pass
+    return o, ot
+
+
 def _split3(x, n_valid=None, plane=None):
     """fp32 tensor -> bf16 planes [3, plane] with x = x0 + x1 + x2 (rgnn_tc_split3); elements [n_valid, plane) are zero."""
     n = x.numel() if n_valid is None else n_valid
@@ -254,27 +286,30 @@ def _edge_mlp_forward(pose, w1, b1, w2, b2, out_dtype):
     e, hid, f2 = pose.shape[0], w1.shape[0], w2.shape[0]
     if pose.shape[1] != 9 or w1.shape != (hid, 9) or w2.shape != (f2, hid) or f2 % 2:
         raise ValueError("edge encoder expects pose [E,9], W1 [H,9], W2 [2F,H]")
+    w2_param = w2
     w1, b1, w2, b2 = (t.detach().float().contiguous() for t in (w1, b1, w2, b2))
+    w2t = None                    # the K-major operand of dA1 = dZ . W2, produced by the same cast launch as the forward operand
     a1 = torch.empty((e, hid), dtype=out_dtype, device=pose.device)
     z = torch.empty((e, f2), dtype=out_dtype, device=pose.device)
     with torch.cuda.device(pose.device):
         check(lib().rgnn_edge_mlp1_fwd(dtype_code(a1), ptr(pose), ptr(w1), ptr(b1), ptr(a1), e, hid, stream()), "rgnn_edge_mlp1_fwd")
         if _lib.USE_TC and out_dtype == torch.bfloat16 and hid % 64 == 0 and f2 % 128 == 0 and e > 0:
-            w2b = _cast_w(w2)
+            w2b, w2t = _cached_casts(w2_param, w2)
             with _lib.timed("mlp2_fwd", 2.0 * e * f2 * hid):
                 check(lib().rgnn_tc_gemm_tn(ptr(a1), hid, ptr(w2b), hid, ptr(z), f2, e, f2, hid,
                                             _lib.EPI_BIAS_N | _lib.EPI_SIGMOID, ptr(b2), None, 1.0, 0.0, stream()), "rgnn_tc_gemm_tn")
         elif _lib.USE_TC3 and out_dtype == torch.float32 and hid % 64 == 0 and f2 % 128 == 0 and e > 0:
             # fp32 parity mode on the tensor cores: split-bf16 planes, six plane-pair products, fp32 accumulate and output
             prow = (e + 63) // 64 * 64
-            a1p, w2p = _split3(a1, e * hid, prow * hid), _split3_w(w2)
+            a1p = _split3(a1, e * hid, prow * hid)
+            w2p, w2t = _cached_casts(w2_param, w2, split3=True)
             with _lib.timed("mlp2_fwd", 2.0 * e * f2 * hid):
                 check(lib().rgnn_tc3_gemm_tn(ptr(a1p), hid, prow, ptr(w2p), hid, f2, ptr(z), f2, e, f2, hid,
                                              _lib.EPI_BIAS_N | _lib.EPI_SIGMOID, ptr(b2), 1.0, stream()), "rgnn_tc3_gemm_tn")
         else:
             _gemm(a1, (0, 0, hid, 1), w2, (0, 0, 1, hid), z, (0, f2, 1), e, f2, hid,
                   epi=_lib.EPI_BIAS_N | _lib.EPI_SIGMOID, bias=b2, tag="mlp2_fwd")
-    return pose, w2, a1, z
+    return pose, w2, a1, z, w2t
 
 
 class EdgeMLPFn(torch.autograd.Function):
@@ -282,7 +317,7 @@ class EdgeMLPFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pose, w1, b1, w2, b2, out_dtype):
-        pose, w2, a1, z = _edge_mlp_forward(pose, w1, b1, w2, b2, out_dtype)
+        pose, w2, a1, z, ctx.w2t = _edge_mlp_forward(pose, w1, b1, w2, b2, out_dtype)
         ctx.save_for_backward(pose, w2, a1, z)
         return z
 
@@ -294,12 +329,13 @@ class EdgeMLPFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             dzp = torch.empty_like(z)
             check(lib().rgnn_sigmoid_grad(dtype_code(z), ptr(z), ptr(dz), ptr(dzp), z.numel(), stream()), "rgnn_sigmoid_grad")
-            dw1, db1, dw2, db2 = edge_mlp_param_grads(pose, w2, a1, dzp)
+            dw1, db1, dw2, db2 = edge_mlp_param_grads(pose, w2, a1, dzp, w2t=ctx.w2t)
         return None, dw1, db1, dw2, db2, None
 
 
-def edge_mlp_param_grads(pose, w2, a1, dzp):
-    """Parameter gradients of the edge encoder from dzp = dL/d(pre-sigmoid) [E, 2F] (autograd of models.py:146-151)."""
+def edge_mlp_param_grads(pose, w2, a1, dzp, w2t=None):
+    """Parameter gradients of the edge encoder from dzp = dL/d(pre-sigmoid) [E, 2F] (autograd of models.py:146-151).
+    w2t: the transposed bf16 weight (or its split planes) the forward's cast already produced."""
     e, hid = a1.shape
     f2 = w2.shape[0]
     dev = a1.device
@@ -307,7 +343,8 @@ def edge_mlp_param_grads(pose, w2, a1, dzp):
     da1 = torch.empty_like(a1)
     dw2 = torch.empty((f2, hid), **f32)
     if _lib.USE_TC and a1.dtype == torch.bfloat16 and hid % 128 == 0 and f2 % 128 == 0 and e > 0:
-        w2t = _cast_w(w2, transpose=True)                       # [hid, f2], K-major for dA1 = dZ . W2
+        if w2t is None or w2t.dim() != 2:
+            w2t = _cast_w(w2, transpose=True)                   # [hid, f2], K-major for dA1 = dZ . W2
         with _lib.timed("mlp2_dx", 2.0 * e * f2 * hid):
             check(lib().rgnn_tc_gemm_tn(ptr(dzp), f2, ptr(w2t), f2, ptr(da1), hid, e, hid, f2, _lib.EPI_RELU_MASK, None, ptr(a1),
                                         1.0, 0.0, stream()), "rgnn_tc_gemm_tn")
@@ -319,7 +356,7 @@ def edge_mlp_param_grads(pose, w2, a1, dzp):
     elif _lib.USE_TC3 and a1.dtype == torch.float32 and dzp.dtype == torch.float32 and hid % 128 == 0 and f2 % 128 == 0 and e > 0:
         prow = (e + 63) // 64 * 64                              # rows beyond E are zero planes: they are the K tail of dW2 = dZ^T . A1
         dzp3, a13 = _split3(dzp, e * f2, prow * f2), _split3(a1, e * hid, prow * hid)
-        w2t3 = _split3_w(w2, transpose=True)                    # [3, hid, f2]: K-major for dA1 = dZ . W2
+        w2t3 = w2t if (w2t is not None and w2t.dim() == 3) else _split3_w(w2, transpose=True)    # [3, hid, f2]: K-major for dA1 = dZ . W2
         with _lib.timed("mlp2_dx", 2.0 * e * f2 * hid):
             check(lib().rgnn_tc3_gemm_tn(ptr(dzp3), f2, prow, ptr(w2t3), f2, hid, ptr(da1), hid, e, hid, f2, 0, None, 1.0, stream()),
                   "rgnn_tc3_gemm_tn")
@@ -346,8 +383,9 @@ def edge_mlp(pose, w1, b1, w2, b2, out_dtype=torch.float32):
 
 
 def _compress_forward(h, gh, wc, bc):
-    """-> (y, wc2 fp32 [Fo, 2F], mode, planes): mode 0 = CUDA-core products, 1 = bf16 tcgen05, 3 = fp32 as split-bf16 planes on
-    tcgen05 (planes = (h3, g3), kept for the weight gradient; (None, None) otherwise)."""
+    """-> (y, wc2 fp32 [Fo, 2F], mode, planes, wt): mode 0 = CUDA-core products, 1 = bf16 tcgen05, 3 = fp32 as split-bf16 planes on
+    tcgen05 (planes = (h3, g3), kept for the weight gradient; (None, None) otherwise); wt = the transposed weight operand of dX
+    that the forward's cast launch produced alongside (None in mode 0)."""
     _lib.require_cuda(h, gh, wc, bc)
     n, f = h.shape[0], h.shape[1]
     _, p = _row_shape(h)
@@ -359,15 +397,15 @@ def _compress_forward(h, gh, wc, bc):
     y = torch.empty((n, fo) + tuple(h.shape[2:]), dtype=h.dtype, device=h.device)
     shape_ok = p == 64 and f % 64 == 0 and fo % 128 == 0 and n > 0
     tc = 1 if (_lib.USE_TC and h.dtype == torch.bfloat16 and shape_ok) else (3 if (_lib.USE_TC3 and h.dtype == torch.float32 and shape_ok) else 0)
-    planes = (None, None)
+    planes, wt = (None, None), None
     with torch.cuda.device(h.device):
         if tc == 1:
-            wb = _cast_w(wc2)
+            wb, wt = _cached_casts(wc, wc2)
             with _lib.timed("compress_fwd", 2.0 * fo * 2 * f * n * p):
                 check(lib().rgnn_tc_conv1x1(ptr(wb), ptr(h), f, ptr(gh), f, ptr(y), fo, None, 0, ptr(bcf), n, stream()), "rgnn_tc_conv1x1")
         elif tc == 3:
             planes = (_split3(h), _split3(gh))
-            w3 = _split3_w(wc2)
+            w3, wt = _cached_casts(wc, wc2, split3=True)
             with _lib.timed("compress_fwd", 2.0 * fo * 2 * f * n * p):
                 check(lib().rgnn_tc3_conv1x1(ptr(w3), ptr(planes[0]), f, ptr(planes[1]), f, n, ptr(y), fo, None, 0, ptr(bcf), n, stream()),
                       "rgnn_tc3_conv1x1")
@@ -378,10 +416,10 @@ def _compress_forward(h, gh, wc, bc):
                 sb, sc, bt, nn = (f * p, 0, p, 1), (fo * p, p, 1), n, p
             _gemm(wc2, (0, 0, 2 * f, 1), h, sb, y, sc, fo, nn, f, batch=bt, epi=_lib.EPI_BIAS_M, bias=bcf, tag="compress_fwd")
             _gemm(wc2[:, f:], (0, 0, 2 * f, 1), gh, sb, y, sc, fo, nn, f, batch=bt, epi=_lib.EPI_ADD_AUX, aux=y, beta=1.0, tag="compress_fwd")
-    return y, wc2, tc, planes
+    return y, wc2, tc, planes, wt
 
 
-def _compress_backward(dy, h, gh, wc2, tc, need_dh, need_dgh, need_dw, need_db, planes=(None, None)):
+def _compress_backward(dy, h, gh, wc2, tc, need_dh, need_dgh, need_dw, need_db, planes=(None, None), wt=None):
     """Autograd of the concat + 1x1 conv: dh (direct), dg_h, dWc [Fo, 2F] fp32, dbc [Fo] fp32."""
     n, f = h.shape[0], h.shape[1]
     _, p = _row_shape(h)
@@ -397,7 +435,7 @@ def _compress_backward(dy, h, gh, wc2, tc, need_dh, need_dgh, need_dw, need_db, 
         if (tc3_dx and (need_dh or need_dgh)) or (tc3_dw and need_dw):
             dy3 = _split3(dy)
         if tc3_dx and (need_dh or need_dgh):
-            wt3 = _split3_w(wc2, transpose=True)            # [3, 2F, Fo]
+            wt3 = wt if (wt is not None and wt.dim() == 3) else _split3_w(wc2, transpose=True)            # [3, 2F, Fo]
             dh, dgh = torch.empty_like(h), torch.empty_like(gh)
             with _lib.timed("compress_dx", 2.0 * fo * 2 * f * n * p):
                 check(lib().rgnn_tc3_conv1x1(ptr(wt3), ptr(dy3), fo, None, 0, n, ptr(dh), f, ptr(dgh), f, None, n, stream()), "rgnn_tc3_conv1x1")
@@ -409,7 +447,8 @@ def _compress_backward(dy, h, gh, wc2, tc, need_dh, need_dgh, need_dw, need_db, 
                 check(lib().rgnn_tc3_conv1x1_wgrad(ptr(dy3), fo, ptr(planes[0]), f, ptr(planes[1]), f, n, ptr(dwc), 2 * f, ptr(partial), split, n,
                                                    stream()), "rgnn_tc3_conv1x1_wgrad")
         if tc_dx and (need_dh or need_dgh):
-            wt = _cast_w(wc2, transpose=True)               # [2F, Fo] K-major: dX_v = Wc^T . dY_v
+            if wt is None or wt.dim() != 2:
+                wt = _cast_w(wc2, transpose=True)           # [2F, Fo] K-major: dX_v = Wc^T . dY_v
             dh, dgh = torch.empty_like(h), torch.empty_like(gh)
             with _lib.timed("compress_dx", 2.0 * fo * 2 * f * n * p):
                 check(lib().rgnn_tc_conv1x1(ptr(wt), ptr(dy), fo, None, 0, ptr(dh), f, ptr(dgh), f, None, n, stream()), "rgnn_tc_conv1x1")
@@ -455,7 +494,7 @@ class CompressFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, gh, wc, bc):
         h, gh = h.contiguous(), gh.contiguous()
-        y, wc2, ctx.tc, planes = _compress_forward(h, gh, wc, bc)
+        y, wc2, ctx.tc, planes, ctx.wt = _compress_forward(h, gh, wc, bc)
         ctx.save_for_backward(h, gh, wc2, *[t for t in planes if t is not None])
         ctx.wshape = tuple(wc.shape)
         return y
@@ -464,7 +503,7 @@ class CompressFn(torch.autograd.Function):
     def backward(ctx, dy):
         h, gh, wc2 = ctx.saved_tensors[:3]
         planes = tuple(ctx.saved_tensors[3:5]) if len(ctx.saved_tensors) >= 5 else (None, None)
-        dh, dgh, dwc, dbc = _compress_backward(dy.contiguous(), h, gh, wc2, ctx.tc, *ctx.needs_input_grad, planes=planes)
+        dh, dgh, dwc, dbc = _compress_backward(dy.contiguous(), h, gh, wc2, ctx.tc, *ctx.needs_input_grad, planes=planes, wt=ctx.wt)
         return dh, dgh, (dwc.reshape(ctx.wshape) if dwc is not None else None), dbc
 
 
@@ -506,7 +545,7 @@ class GNNLayerFn(torch.autograd.Function):
             raise ValueError(f"feature rows ({h.shape[0]}) != graph nodes ({ix.N})")
         if pose.shape[0] != ix.E:
             raise ValueError(f"pose rows ({pose.shape[0]}) != graph edges ({ix.E})")
-        pose, w2f, a1, z = _edge_mlp_forward(pose, w1, b1, w2, b2, h.dtype)
+        pose, w2f, a1, z, ctx.w2t = _edge_mlp_forward(pose, w1, b1, w2, b2, h.dtype)
         if z.shape[1] != 2 * h.shape[1]:
             raise ValueError("edge encoder width does not match the feature maps")
         f = h.shape[1]
@@ -522,7 +561,7 @@ class GNNLayerFn(torch.autograd.Function):
             y = torch.empty((ix.N, fo) + tuple(h.shape[2:]), dtype=h.dtype, device=h.device)
             gh = torch.empty_like(h) if need_bwd else None
             with torch.cuda.device(h.device):
-                wb = _cast_w(wc2)
+                wb, ctx.wt = _cached_casts(wc, wc2)
                 with _lib.timed("compress_film_fused_fwd", 2.0 * fo * 2 * f * ix.N * p):
                     check(lib().rgnn_tc_conv_film_fused(ptr(wb), ptr(h), ptr(z), ptr(bcf), ptr(y), ptr(gh), ix.G, ix.complete_k, f, fo,
                                                         stream()), "rgnn_tc_conv_film_fused")
@@ -534,7 +573,7 @@ class GNNLayerFn(torch.autograd.Function):
             gh = torch.empty_like(h)
             with torch.cuda.device(h.device):
                 _aggregate(ix, h, z, True, None, _lib.POST_MEAN, None, None, gh, None, False)
-            y, wc2, ctx.tc, planes = _compress_forward(h, gh, wc, bc)
+            y, wc2, ctx.tc, planes, ctx.wt = _compress_forward(h, gh, wc, bc)
         ctx.g, ctx.wshape = g, tuple(wc.shape)
         ctx.save_for_backward(h, pose, w2f, a1, z, gh, wc2, *[t for t in planes if t is not None and need_bwd])
         return y
@@ -547,13 +586,13 @@ class GNNLayerFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         need_edge = any(need[2:6])
         dh_direct, dgh, dwc, dbc = _compress_backward(dy.contiguous(), h, gh, wc2, ctx.tc, need[0], need[0] or need_edge, need[6], need[7],
-                                                      planes=planes)
+                                                      planes=planes, wt=ctx.wt)
         dh = dw1 = db1 = dw2 = db2 = None
         with torch.cuda.device(dy.device):
             if need[0] or need_edge:
                 dh, dzp = _film_backward(ix, h, dgh, z, dh_direct, True)
                 if need_edge:
-                    dw1, db1, dw2, db2 = edge_mlp_param_grads(pose, w2f, a1, dzp)
+                    dw1, db1, dw2, db2 = edge_mlp_param_grads(pose, w2f, a1, dzp, w2t=ctx.w2t)
         return (dh if need[0] else None, None, dw1, db1, dw2, db2,
                 dwc.reshape(ctx.wshape) if dwc is not None else None, dbc, None)
 

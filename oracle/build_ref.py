@@ -1,12 +1,15 @@
 """Compile the reference's own model code for the CPU-baseline / --impl reference legs of bench.py (TEST INFRASTRUCTURE).
 
 The reference for this path is Python: `dgl/model/models.py` (+ `blocks.py`, its relative import).  The analogue of "compile the
-reference from its sources where they lie, outputs only into oracle/_ref/" is byte-compilation: py_compile reads
-/root/reference/dgl/model/*.py IN PLACE and writes sourceless .pyc files to oracle/_ref/model/ (git-ignored, but shipped to the
-GPU box like our own built .so).  No reference source text enters the repository, and /root/reference is not needed at run time.
+reference from its sources where they lie, outputs only into oracle/_ref/" is byte-compilation: the files under
+/root/reference/dgl/model/ are compiled IN PLACE and the marshalled code objects are written to oracle/_ref/model/*.bin
+(git-ignored, but shipped to the GPU box like our own built .so; plain .pyc files are dropped by the gpurun snapshot, hence the
+own container: one line with the interpreter version, then marshal.dumps(code)).  No reference source text enters the
+repository, and /root/reference is not needed at run time.
 Called by __graft_entry__.build() when /root/reference is present; a no-op elsewhere (the GPU box uses the prebuilt files)."""
 import os
-import py_compile
+import marshal
+import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = "/root/reference/dgl/model"
@@ -15,15 +18,19 @@ FILES = ("models.py", "blocks.py")
 
 
 def build_ref(force=False):
-    """-> list of .pyc paths written (empty when the reference tree is absent)."""
+    """-> list of compiled files written (empty when the reference tree is absent)."""
     if not all(os.path.exists(os.path.join(REF_SRC, f)) for f in FILES):
         return []
     os.makedirs(REF_OUT, exist_ok=True)
     out = []
     for f in FILES:
-        src, dst = os.path.join(REF_SRC, f), os.path.join(REF_OUT, f + "c")
+        src, dst = os.path.join(REF_SRC, f), os.path.join(REF_OUT, f[:-3] + ".bin")
         if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
-            py_compile.compile(src, cfile=dst, doraise=True)
+            with open(src, "rb") as fh:
+                code = compile(fh.read(), src, "exec", dont_inherit=True)
+            with open(dst, "wb") as fh:
+                fh.write((sys.version.split()[0] + "\n").encode())
+                fh.write(marshal.dumps(code))
         out.append(dst)
     return out
 

@@ -78,3 +78,86 @@ def test_cuda_graph_replay_matches_eager(R, dtype, f):
         for n, p in blk.named_parameters():
             # atomics in the bias / edge-MLP layer-1 gradient kernels reorder fp32 sums between runs
             assert nerr(grads[n], p.grad) <= 1e-5, n
+
+
+@pytest.mark.parametrize("dtype,f,tol", [(torch.bfloat16, 512, 2e-2), (torch.float32, 128, 1e-5)])
+def test_weight_cast_cache_follows_the_weights(R, dtype, f, tol):
+    """The bf16 / split-plane weight operands are cached on the parameters until they change: after an in-place update (what an
+    optimizer step or load_state_dict does) forward and backward must use the NEW weights, and a loop over fixed weights must
+    not launch cast kernels at all."""
+    from robot_check import make_block, nerr
+    from oracle import gnn_oracle as O
+    G, K = 4, 5
+    blk, _ = make_block(R, O, f, True, True)
+    blk.cuda()
+    g = R.robot_batch(G, K, device="cuda")
+    g.index()                                                    # (the lazily built CSR index would count as launches of the first pass)
+    sb = O.synthetic_batch(G, K, f, p=64, seed=2)
+    h0 = sb["h"].reshape(G * K, f, 8, 8).cuda().to(dtype)
+    pose, dy = sb["pose"].cuda(), sb["dy"].reshape(G * K, f, 8, 8).cuda().to(dtype)
+
+    def run():
+        h = h0.clone().requires_grad_()
+        for p in blk.parameters():
+            p.grad = None
+        n0 = R._lib.lib().rgnn_launch_count()
+        y = blk(g, h, pose)
+        y.backward(dy)
+        return y.detach().float(), h.grad.float(), R._lib.lib().rgnn_launch_count() - n0
+
+    def oracle():
+        ls = []
+        for j in (1, 2):
+            enc, conv = getattr(blk, f"gcn{j}").edge_encoder.layers, getattr(blk, f"conv{j}")
+            ls.append({k: v.detach().double().cpu() for k, v in dict(w1=enc[0].weight, b1=enc[0].bias, w2=enc[2].weight, b2=enc[2].bias,
+                                                                     wc=conv.weight.reshape(f, 2 * f), bc=conv.bias).items()})
+        ho = h0.double().cpu().requires_grad_()
+        yo = O.gnn_block(ho, pose.double().cpu(), sb["src"], sb["dst"], ls, compress_gcn=True)
+        yo.backward(dy.double().cpu())
+        return yo.detach(), ho.grad
+
+    y1, dh1, l1 = run()
+    y1b, dh1b, l1b = run()
+    assert l1b < l1 and torch.equal(y1, y1b), (l1, l1b)         # second pass: no cast launches, same result
+    yo, dho = oracle()
+    assert nerr(y1, yo) <= tol and nerr(dh1, dho) <= tol
+    with torch.no_grad():                                        # an "optimizer step"
+        for p in blk.parameters():
+            p.mul_(1.5)
+    y2, dh2, l2 = run()
+    assert l2 == l1, (l1, l2)                                    # the casts ran again
+    yo2, dho2 = oracle()
+    assert nerr(y2, yo2) <= tol and nerr(dh2, dho2) <= tol
+    assert nerr(y2, yo) > 3 * tol, nerr(y2, yo)                  # and the result really moved
+
+
+@pytest.mark.parametrize("dtype,f,tol", [(torch.bfloat16, 512, 2e-2), (torch.float32, 64, 1e-5)])
+def test_graphed_forward_only_slice_matches_eager(R, dtype, f, tol):
+    """Eval path (dgl/eval.py: batch 1 under torch.no_grad()): gnn_slice_auto replays a captured CUDA graph; results equal the
+    eager slice bit for bit, for fresh inputs on every replay, and follow weight updates between replays."""
+    from robot_check import make_block
+    from oracle import gnn_oracle as O
+    blk, _ = make_block(R, O, f, True, True)
+    blk.cuda()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for G, K in ((1, 5), (8, 5), (1, 5)):
+        g = R.robot_batch(G, K, device="cuda")
+        h = torch.rand((G * K, f, 8, 8), generator=gen, device="cuda").to(dtype)
+        g.edata["pose"] = torch.randn((G * K * (K - 1), 9), generator=gen, device="cuda")
+        with torch.no_grad():
+            n0 = R._lib.lib().rgnn_launch_count()
+            y = R.gnn_slice_auto(blk, g, h).clone()
+            y2 = R.gnn_slice_auto(blk, g, h).clone()             # pure replay: no launches through the C ABI
+            n1 = R._lib.lib().rgnn_launch_count()
+            ye = R.gnn_slice(blk, g, h)
+        assert torch.equal(y, ye) and torch.equal(y2, ye)
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.mul_(0.5)
+        y3 = R.gnn_slice_auto(blk, g, h).clone()
+        ye3 = R.gnn_slice(blk, g, h)
+    assert torch.equal(y3, ye3) and not torch.equal(y3, ye)
+    # with gradients enabled the auto path is the eager path (autograd graph intact)
+    hh = h.clone().requires_grad_()
+    R.gnn_slice_auto(blk, g, hh).float().sum().backward()
+    assert hh.grad is not None
