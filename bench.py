@@ -313,7 +313,57 @@ def other_configs(R, dist, dev, rank, world, wire, peaks):
         import gc
         gc.collect()
         torch.cuda.empty_cache()
+    out.append(script_shape_latency(R, dev))
     return out
+
+
+def script_shape_latency(R, dev):
+    """The reference's REAL batch (dgl/training.py:28: 8 graphs of 5 robots; dgl/eval.py:23: 1 graph): launch-bound, so what is
+    measured is host + launch latency of one step on one GPU - eager (kernel by kernel through the C ABI) and replayed from CUDA graphs
+    (GraphedTrainSlice: forward + backward graphs behind one autograd node; GraphedForward: the eval slice).  Wall-clock per step over
+    200 steps bracketed by synchronize (CUDA events cannot see host latency)."""
+    import sys
+    import types
+    eng = sys.modules[R.GraphedForward.__module__]
+    F, K = 512, 5
+    torch.manual_seed(1)
+    blk = R.GNNBlock(types.SimpleNamespace(feature_dim=F, compress_gcn=True, multi_gcn=True)).to(dev)
+    res = {"name": "script shape: F=512, K=5, 2 layers + compress, bf16, G=8 (training.py:28) and G=1 (eval.py:23), one GPU", "unit": "ms/step"}
+    n_steps = 200
+    for G, mode in ((8, "train"), (8, "eval"), (1, "eval")):
+        N, E = G * K, G * K * (K - 1)
+        g = R.robot_batch(G, K, device=dev)
+        g.index()
+        h = torch.relu(torch.randn((N, F, 8, 8), device=dev)).bfloat16()
+        dy = torch.randn((N, F, 8, 8), device=dev).bfloat16()
+        g.edata["pose"] = torch.randn((E, 9), device=dev)
+        for graphed in (False, True):
+            old_flag, eng.GRAPHED_TRAIN = eng.GRAPHED_TRAIN, True
+            fn = R.gnn_slice_auto if graphed else R.gnn_slice
+
+            def step():
+                if mode == "eval":
+                    with torch.no_grad():
+                        return fn(blk, g, h)
+                hh = h.detach().requires_grad_()
+                for p in blk.parameters():
+                    p.grad = None
+                fn(blk, g, hh).backward(dy)
+            try:
+                for _ in range(10):
+                    step()
+                torch.cuda.synchronize()
+                n0 = R._lib.lib().rgnn_launch_count()
+                t0 = time.perf_counter()
+                for _ in range(n_steps):
+                    step()
+                torch.cuda.synchronize()
+                ms = (time.perf_counter() - t0) / n_steps * 1e3
+                res[f"G{G}_{mode}_{'graphed' if graphed else 'eager'}"] = {"ms_per_step": round(ms, 4), "graphs_per_s": round(G / (ms * 1e-3)),
+                                                                       "c_abi_launches_per_step": (R._lib.lib().rgnn_launch_count() - n0) / n_steps}
+            finally:
+                eng.GRAPHED_TRAIN = old_flag
+    return res
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -8,10 +8,10 @@ from . import _lib
 from .graph import RobotGraph, graph, batch, robot_batch, function, relative_pose_edges, complete_k_of
 from . import functional
 from . import parallel
-from .engine import HostPipeline, GraphedStep, GraphedForward, gnn_slice_auto
+from .engine import HostPipeline, GraphedStep, GraphedForward, GraphedTrainSlice, gnn_slice_auto
 from .functional import film_mean, film_mean_cat, copy_u_reduce, edge_mlp, compress, linear, axpby
 from .layers import edge_encoder, GCN, GNNBlock, GraphConv, GCN2Conv, gnn_slice
 
 __all__ = ["RobotGraph", "graph", "batch", "robot_batch", "function", "relative_pose_edges", "complete_k_of", "functional", "film_mean", "film_mean_cat",
            "copy_u_reduce", "edge_mlp", "compress", "linear", "axpby", "edge_encoder", "GCN", "GNNBlock",
-           "GraphConv", "GCN2Conv", "HostPipeline", "GraphedStep", "GraphedForward", "gnn_slice_auto", "gnn_slice"]
+           "GraphConv", "GCN2Conv", "HostPipeline", "GraphedStep", "GraphedForward", "GraphedTrainSlice", "gnn_slice_auto", "gnn_slice"]

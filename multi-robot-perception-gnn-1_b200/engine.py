@@ -188,28 +188,74 @@ class GraphedForward:
         return self.y
 
 
+class _SliceModule(torch.nn.Module):
+    """gnn_slice over a fixed topology as a tensor-in / tensor-out module (what torch.cuda.make_graphed_callables captures)."""
+
+    def __init__(self, mod, graph):
+        super().__init__()
+        self.mod, self.g = mod, graph
+
+    def forward(self, h, pose):
+        from .layers import gnn_slice
+        return gnn_slice(self.mod, self.g, h, pose)
+
+
+class GraphedTrainSlice:
+    """The GNN slice as TWO captured CUDA graphs (forward, backward) behind one autograd node, so it sits inside an ordinary
+    training loop (loss.backward(), optimizer.step(); dgl/training.py:192-216) and still costs two graph launches per step instead
+    of ~26 kernel launches - at the reference's batch (8 graphs, training.py:28) the step is launch-bound.  Built with
+    torch.cuda.make_graphed_callables over librobotgnn's capture-safe launch sequences; parameter gradients flow through
+    autograd as usual (accumulated into .grad).  Fixed batch shape and topology (complete K-robot graphs)."""
+
+    def __init__(self, mod, num_graphs, robots, feat, dtype=torch.float32, device="cuda", hw=(8, 8), h_requires_grad=True):
+        self.dev = torch.device(device)
+        self.g = robot_batch(num_graphs, robots, device=self.dev)
+        self.g.index()
+        n, e = num_graphs * robots, num_graphs * robots * (robots - 1)
+        sample_h = torch.zeros((n, feat) + tuple(hw), dtype=dtype, device=self.dev, requires_grad=h_requires_grad)
+        sample_pose = torch.zeros((e, 9), dtype=torch.float32, device=self.dev)
+        self.fn = torch.cuda.make_graphed_callables(_SliceModule(mod, self.g), (sample_h, sample_pose))
+
+    def __call__(self, h, pose):
+        return self.fn(h, pose)
+
+
 _GRAPHED = weakref.WeakKeyDictionary()      # module -> {(G, K, F, hw, dtype, device): GraphedForward}; never pickled with the module
 GRAPHED_EVAL_MAX_NODES = 4096               # above this the kernels are long enough that launch latency does not matter
 
 
+import os as _os
+# gnn_slice_auto may also graph the TRAINING step (forward + backward graphs).  Opt-in (ROBOT_GNN_GRAPHED_TRAIN=1 or set this flag):
+# capture happens inside the first training forward, and stream capture is process-global - a DataLoader pin-memory thread or an
+# older autograd graph that is still alive can invalidate it (torch.cuda.make_graphed_callables' documented constraints).  The
+# eval graph (no backward) has no such constraint and is always on.
+GRAPHED_TRAIN = _os.environ.get("ROBOT_GNN_GRAPHED_TRAIN", "0") == "1"
+
+
 def gnn_slice_auto(mod, g, h, pose=None):
-    """gnn_slice, replayed from a captured CUDA graph when that is safe and pays: gradients disabled (eval), a CUDA batch of complete
-    K-robot graphs (2..8 robots), intended return key, small batch.  Anything else runs the eager path."""
+    """gnn_slice, replayed from captured CUDA graphs when that is safe and pays: a small CUDA batch of complete K-robot graphs
+    (2..8 robots), intended return key.  Gradients disabled (eval): one forward graph (GraphedForward).  Gradients enabled
+    (training): a forward and a backward graph behind one autograd node (GraphedTrainSlice).  Anything else runs the eager path."""
     from .layers import gnn_slice
     opt = mod.opt
     k = g.complete_k
-    ok = (not torch.is_grad_enabled() and h.is_cuda and 2 <= k <= 8 and g.num_nodes() == g.batch_size * k and h.dim() == 4
+    train = torch.is_grad_enabled()
+    ok = (h.is_cuda and 2 <= k <= 8 and g.num_nodes() == g.batch_size * k and h.dim() == 4
           and g.num_nodes() <= GRAPHED_EVAL_MAX_NODES and getattr(opt, "compress_gcn", False)
           and mod.gcn1.return_key == "images" and mod.gcn1.film and h.dtype in (torch.float32, torch.bfloat16)
-          and not torch.cuda.is_current_stream_capturing())
+          and not torch.cuda.is_current_stream_capturing() and (GRAPHED_TRAIN or not train))
     if not ok:
         return gnn_slice(mod, g, h, pose)
     pose = g.edata['pose'] if pose is None else pose
-    key = (g.batch_size, k, h.shape[1], tuple(h.shape[2:]), h.dtype, h.device)
+    key = (train, bool(h.requires_grad), g.batch_size, k, h.shape[1], tuple(h.shape[2:]), h.dtype, h.device)
     cache = _GRAPHED.setdefault(mod, {})
     gf = cache.get(key)
     if gf is None:
         if len(cache) >= 8:                 # a handful of batch shapes at most (last partial batch of an epoch)
             cache.clear()
-        gf = cache[key] = GraphedForward(mod, g.batch_size, k, h.shape[1], h.dtype, h.device, tuple(h.shape[2:]))
+        if train:
+            gf = GraphedTrainSlice(mod, g.batch_size, k, h.shape[1], h.dtype, h.device, tuple(h.shape[2:]), h_requires_grad=h.requires_grad)
+        else:
+            gf = GraphedForward(mod, g.batch_size, k, h.shape[1], h.dtype, h.device, tuple(h.shape[2:]))
+        cache[key] = gf
     return gf(h, pose)

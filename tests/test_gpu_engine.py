@@ -157,7 +157,45 @@ def test_graphed_forward_only_slice_matches_eager(R, dtype, f, tol):
         y3 = R.gnn_slice_auto(blk, g, h).clone()
         ye3 = R.gnn_slice(blk, g, h)
     assert torch.equal(y3, ye3) and not torch.equal(y3, ye)
-    # with gradients enabled the auto path is the eager path (autograd graph intact)
-    hh = h.clone().requires_grad_()
-    R.gnn_slice_auto(blk, g, hh).float().sum().backward()
-    assert hh.grad is not None
+
+
+@pytest.mark.parametrize("dtype,f,tol", [(torch.bfloat16, 512, 2e-2), (torch.float32, 64, 1e-5)])
+def test_graphed_training_slice_inside_an_ordinary_autograd_loop(R, dtype, f, tol):
+    """Training at the reference's batch (8 graphs, dgl/training.py:28): gnn_slice_auto with gradients enabled runs a forward and a
+    backward CUDA graph behind one autograd node; outputs, dh and every parameter gradient equal the eager path, weight updates
+    between steps are picked up, and gradients accumulate into .grad like any autograd node's."""
+    from robot_check import make_block
+    from oracle import gnn_oracle as O
+    import sys
+    eng = sys.modules[R.GraphedForward.__module__]
+    G, K = 8, 5
+    blk, _ = make_block(R, O, f, True, True)
+    blk.cuda()
+    g = R.robot_batch(G, K, device="cuda")
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    opt_ = torch.optim.SGD(blk.parameters(), lr=0.05)
+    old_flag, eng.GRAPHED_TRAIN = eng.GRAPHED_TRAIN, True
+    for it in range(3):
+        h = torch.rand((G * K, f, 8, 8), generator=gen, device="cuda").to(dtype)
+        pose = torch.randn((G * K * (K - 1), 9), generator=gen, device="cuda")
+        dy = torch.randn((G * K, f, 8, 8), generator=gen, device="cuda").to(dtype)
+        g.edata["pose"] = pose
+        he = h.clone().requires_grad_()
+        opt_.zero_grad(set_to_none=True)
+        ye = R.gnn_slice(blk, g, he)
+        ye.backward(dy)
+        ref = {n: p.grad.clone() for n, p in blk.named_parameters()}
+        ye = ye.detach()      # drop the eager autograd graph: its AccumulateGrad nodes belong to the default stream and must not be
+        #                       alive while the backward graph is captured (torch.cuda.make_graphed_callables' documented rule)
+        hg = h.clone().requires_grad_()
+        opt_.zero_grad(set_to_none=True)
+        n0 = R._lib.lib().rgnn_launch_count()
+        yg = R.gnn_slice_auto(blk, g, hg)
+        (yg * 1.0).backward(dy)                                  # an op behind the slice, like the decoder
+        launched = R._lib.lib().rgnn_launch_count() - n0
+        assert it == 0 or launched == 0                          # replays launch nothing through the C ABI
+        assert torch.equal(yg, ye) and torch.equal(hg.grad, he.grad)
+        for n, p in blk.named_parameters():
+            assert nerr(p.grad, ref[n]) <= 1e-5, n               # (atomics in the small gradient kernels reorder fp32 sums)
+        opt_.step()                                              # the next replay must see the new weights
+    eng.GRAPHED_TRAIN = old_flag
