@@ -250,10 +250,16 @@ def other_configs(R, dist, dev, rank, world, wire, peaks):
     out = []
     cells = [dict(name="C4 strong: F=2048, K=5, 2 layers + compress, bf16, 8192 graphs in total", F=2048, K=5, G=max(1, 8192 // world), scaling="strong", steps=4),
              dict(name="C4 weak: F=2048, K=5, 2 layers + compress, bf16, 1024 graphs per GPU", F=2048, K=5, G=1024, scaling="weak", steps=8),
-             dict(name="C5 cell: F=512, K=64 robots, 2 layers + compress, bf16, 128 graphs per GPU", F=512, K=64, G=128, scaling="weak", steps=6)]
+             dict(name="C5 cell: F=512, K=64 robots, 2 layers + compress, bf16, 128 graphs per GPU", F=512, K=64, G=128, scaling="weak", steps=6),
+             dict(name="ragged batch: robots per graph mixed over {3, 4, 5} (dropped cameras, dataloader.py:88-99), F=512, 2 layers + compress, "
+                       "bf16, 4096 graphs per GPU", F=512, K=5, G=4096, scaling="weak", steps=8, ragged=(3, 4, 5))]
     for c in cells:
         F, K, G = c["F"], c["K"], c["G"]
         N, E = G * K, G * K * (K - 1)
+        ks = None
+        if c.get("ragged"):
+            ks = [c["ragged"][i % len(c["ragged"])] for i in range(G)]
+            N, E = sum(ks), sum(k * (k - 1) for k in ks)
         torch.manual_seed(1)
         blk = R.GNNBlock(types.SimpleNamespace(feature_dim=F, compress_gcn=True, multi_gcn=True)).to(dev)
         sync = R.parallel.GradSync(blk, wire_dtype=wire) if world > 1 else None
@@ -261,7 +267,11 @@ def other_configs(R, dist, dev, rank, world, wire, peaks):
         h = torch.relu(torch.randn((N, F, 8, 8), generator=gen, device=dev, dtype=torch.float32)).bfloat16().requires_grad_()
         dy = torch.randn((N, F, 8, 8), generator=gen, device=dev, dtype=torch.float32).bfloat16()
         pose = torch.randn((E, 9), generator=gen, device=dev, dtype=torch.float32)
-        g = R.robot_batch(G, K, device=dev)
+        if ks is None:
+            g = R.robot_batch(G, K, device=dev)
+        else:       # per-sample dgl.graph + dgl.batch as the DataLoader collate does (training.py:57-58), then .to(device)
+            tmpl = {k: R.robot_batch(1, k) for k in set(ks)}
+            g = R.batch([tmpl[k] for k in ks]).to(dev)
         g.index()
 
         def step():
@@ -303,6 +313,9 @@ def other_configs(R, dist, dev, rank, world, wire, peaks):
                "roofline": {"kernel": top, "bound": "hbm" if mem else "tensor", "achieved": round(ach, 2), "unit": "GB/s" if mem else "TFLOP/s",
                             "peak": hbm_peak if mem else tc_peak, "frac": round(ach / (hbm_peak if mem else tc_peak), 4),
                             "ms_avg_per_launch": round(d["ms_avg"], 4), "share": round(d["ms_total"] / (ms_step * c["steps"]), 4)}}
+        ent["hbm_kernels"] = {n: {"ms_avg": round(v["ms_avg"], 4), "GB/s": round(v["work_total"] / (v["ms_total"] * 1e-3) / 1e9, 1),
+                                  "frac": round(v["work_total"] / (v["ms_total"] * 1e-3) / 1e9 / hbm_peak, 4)}
+                              for n, v in prof.items() if n.startswith(MEM_KERNELS) and v["ms_total"] > 0}
         if sync is not None:
             ok, dev_rel = sync.check_ranks_agree()
             ent["grad_sync_check"] = "ok" if ok else f"MISMATCH ({dev_rel:.3e})"

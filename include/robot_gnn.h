@@ -149,6 +149,18 @@ int rgnn_film_backward(int dtype, const void* h, int64_t ldh, const void* dagg, 
                        int64_t num_graphs, int64_t max_graph_nodes, int64_t max_graph_edges, int64_t complete_k,
                        int64_t num_nodes, int64_t num_edges, int64_t feat, int64_t pix, void* stream);
 
+/* ---- A5/A6/A10 on RAGGED batches of complete graphs (samples with different camera counts, dgl/dataloader.py:88-99) ------
+ * The host buckets the batch by robot count; each call covers ONE bucket of `bucket_graphs` complete `robots`-node graphs (2..8,
+ * reference edge order) scattered through the batch: bases = int32 [bucket_graphs, 2] = (first node row, first edge row) of each.
+ * Same arithmetic, layouts and results as rgnn_aggregate (FiLM, mean) / rgnn_film_backward on those graphs, with the topology
+ * compiled in (streaming ring kernels) instead of a CSR walk.  RGNN_E_UNSUPPORTED when pix != 64 or the rows are not 16-byte
+ * addressable (caller: the general kernels). */
+int rgnn_film_bucket_forward(int dtype, const void* x, int64_t ldx, const void* z, void* out, int64_t ldout, void* copy_x_to,
+                             const int32_t* bases, int64_t bucket_graphs, int64_t robots, int64_t feat, int64_t pix, void* stream);
+int rgnn_film_bucket_backward(int dtype, const void* h, int64_t ldh, const void* dagg, int64_t lddagg, const void* z, int fuse_sigmoid_grad,
+                              const void* addend, int64_t ldadd, void* dh, int64_t lddh, void* dz, const int32_t* bases,
+                              int64_t bucket_graphs, int64_t robots, int64_t feat, int64_t pix, void* stream);
+
 /* ---- A4 (+A10): first edge-encoder layer, K = 9 -----------------------------------------
  * a1 = relu(pose W1^T + b1)   (nn.Linear(9,F)+ReLU, dgl/model/models.py:147-148); pose [E,9] fp32
  * (edge.float(), models.py:153); w1 [F,9], b1 [F] fp32 master weights; a1 [E,F] in `dtype`. */

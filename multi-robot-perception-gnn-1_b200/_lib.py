@@ -27,6 +27,8 @@ SIGNATURES = {
     "rgnn_relative_pose": [_i32, _vp, _vp, _i64, _i64, _vp],
     "rgnn_film_edge_grad": [_i32, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     "rgnn_film_backward": [_i32, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp] + [_i64] * 8 + [_vp],
+    "rgnn_film_bucket_forward": [_i32, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp],
+    "rgnn_film_bucket_backward": [_i32, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp],
     "rgnn_edge_mlp1_fwd": [_i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "rgnn_edge_mlp1_bwd": [_i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "rgnn_gemm": [_i32, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i64, _i64, _i64]

@@ -484,11 +484,11 @@ static int launch_bwd(int K, const T* h, int64_t ldh, const T* dagg, int64_t ldd
 // streaming variants (film_ring.cu)
 bool film_fwd_ring_ok(int dtype, int K, const void* x, int64_t ldx, const void* z, int64_t F, int64_t P);
 int film_fwd_ring(int dtype, int K, const void* x, int64_t ldx, const void* z, void* out, int64_t ldout, void* copy_to, int64_t G,
-                  int64_t F, cudaStream_t st);
+                  int64_t F, cudaStream_t st, const int2* gb);
 
 int film_fwd_complete(int dtype, int K, const void* x, int64_t ldx, const void* z, void* out, int64_t ldout, void* copy_to,
                       int64_t G, int64_t F, int64_t P, cudaStream_t st) {
-  if (film_fwd_ring_ok(dtype, K, x, ldx, z, F, P)) return film_fwd_ring(dtype, K, x, ldx, z, out, ldout, copy_to, G, F, st);
+  if (film_fwd_ring_ok(dtype, K, x, ldx, z, F, P)) return film_fwd_ring(dtype, K, x, ldx, z, out, ldout, copy_to, G, F, st, nullptr);
   if (dtype == RGNN_F32) {
     auto X = static_cast<const float*>(x); auto Z = static_cast<const float*>(z);
     return z ? launch_fwd<float, true>(K, X, ldx, Z, static_cast<float*>(out), ldout, static_cast<float*>(copy_to), G, (int)F, (int)P, st)
@@ -500,12 +500,12 @@ int film_fwd_complete(int dtype, int K, const void* x, int64_t ldx, const void* 
 }
 
 int film_bwd_ring(int dtype, int K, const void* h, int64_t ldh, const void* dagg, int64_t ldd, const void* z, const void* addend,
-                  int64_t ldadd, void* dh, int64_t lddh, void* dz, int64_t G, int64_t F, int64_t P, int fuse_sig, cudaStream_t st);
+                  int64_t ldadd, void* dh, int64_t lddh, void* dz, int64_t G, int64_t F, int64_t P, int fuse_sig, cudaStream_t st, const int2* gb);
 
 int film_bwd_complete(int dtype, int K, const void* h, int64_t ldh, const void* dagg, int64_t ldd, const void* z, const void* addend,
                       int64_t ldadd, void* dh, int64_t lddh, void* dz, int64_t G, int64_t F, int64_t P, int fuse_sig, cudaStream_t st) {
   {
-    const int rc = film_bwd_ring(dtype, K, h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sig, st);
+    const int rc = film_bwd_ring(dtype, K, h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sig, st, nullptr);
     if (rc != RGNN_E_UNSUPPORTED) return rc;
   }
   if (dtype == RGNN_F32)

@@ -36,7 +36,9 @@ template <> __device__ __forceinline__ float2 lds_pair<__nv_bfloat16>(const unsi
 template <typename T, int K, bool HAS_Z, int NST>
 __global__ void __launch_bounds__(RING_TPB + 32) k_film_fwd_ring(const T* __restrict__ x, int64_t ldx, const T* __restrict__ z,
                                                                  T* __restrict__ out, int64_t ldout, T* __restrict__ copy_to,
-                                                                 int64_t G, int F) {
+                                                                 int64_t G, int F, const int2* __restrict__ gb) {
+  // gb (optional): per-graph (first node row, first edge row) of the graphs this launch covers - a bucket of equal-K graphs
+  // inside a ragged batch; null = graph g owns rows [g K, (g+1) K) and edges [g NE, (g+1) NE)
   using S = RingShape<T, K>;
   constexpr int VEC = S::VEC, NE = S::NE, NP = VEC / 2;
   constexpr bool EXACT = sizeof(T) == 4;       // fp32: the reference's rounding order; bf16: fused multiply-add
@@ -60,13 +62,14 @@ __global__ void __launch_bounds__(RING_TPB + 32) k_film_fwd_ring(const T* __rest
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
       const int64_t g = it / ipg;
       const int cb = (int)(it - g * ipg);
+      const int64_t nb = gb ? (int64_t)gb[g].x : g * K, eb = gb ? (int64_t)gb[g].y : g * NE;
       tma::mbar_wait(empty + s, ph ^ 1);                   // first lap: passes immediately (phase bit starts at 0)
       unsigned char* st = ring + (size_t)s * STAGE;
       if (lane == 0) tma::mbar_expect_tx(full + s, STAGE);
       __syncwarp();
       for (int i = lane; i < K + (HAS_Z ? NE : 0); i += 32) {
-        if (i < K) tma::bulk_g2s(st + i * S::PIECE, x + (g * K + i) * ldx + (int64_t)cb * S::CH * RING_P, S::PIECE, full + s);
-        else tma::bulk_g2s(st + K * S::PIECE + (i - K) * S::ZPIECE, z + (g * NE + (i - K)) * 2 * (int64_t)F + 2 * cb * S::CH, S::ZPIECE, full + s);
+        if (i < K) tma::bulk_g2s(st + i * S::PIECE, x + (nb + i) * ldx + (int64_t)cb * S::CH * RING_P, S::PIECE, full + s);
+        else tma::bulk_g2s(st + K * S::PIECE + (i - K) * S::ZPIECE, z + (eb + (i - K)) * 2 * (int64_t)F + 2 * cb * S::CH, S::ZPIECE, full + s);
       }
       if (++s == NST) { s = 0; ph ^= 1; }
     }
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(RING_TPB + 32) k_film_fwd_ring(const T* __rest
     const int64_t g = it / ipg;
     const int cb = (int)(it - g * ipg);
     const int64_t off = (int64_t)cb * S::CH * RING_P + tid * VEC;
-    const int64_t n0 = g * K;
+    const int64_t n0 = gb ? (int64_t)gb[g].x : g * K;
     const unsigned char* st = ring + (size_t)s * STAGE;
     tma::mbar_wait(full + s, ph);
     float2 xv[K][NP];
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(RING_TPB + 32) k_film_fwd_ring(const T* __rest
 template <int K> constexpr int ring_fwd_stages() { return K <= 3 ? 8 : (K <= 5 ? 4 : 3); }
 
 template <typename T, int K, bool HAS_Z>
-static int launch_fwd_ring_k(const T* x, int64_t ldx, const T* z, T* out, int64_t ldout, T* copy_to, int64_t G, int F, cudaStream_t st) {
+static int launch_fwd_ring_k(const T* x, int64_t ldx, const T* z, T* out, int64_t ldout, T* copy_to, int64_t G, int F, cudaStream_t st, const int2* gb) {
   using S = RingShape<T, K>;
   constexpr int NST = ring_fwd_stages<K>();
   constexpr size_t smem = 128 + (size_t)NST * (K * S::PIECE + (HAS_Z ? S::NE * S::ZPIECE : 0));
@@ -165,14 +168,14 @@ static int launch_fwd_ring_k(const T* x, int64_t ldx, const T* z, T* out, int64_
   int64_t blocks = (int64_t)per_sm * num_sms();
   if (blocks > items) blocks = items;
   if (blocks < 1) return 0;
-  kern<<<(unsigned)blocks, RING_TPB + 32, smem, st>>>(x, ldx, z, out, ldout, copy_to, G, F);
+  kern<<<(unsigned)blocks, RING_TPB + 32, smem, st>>>(x, ldx, z, out, ldout, copy_to, G, F, gb);
   RGNN_LAUNCH_CHECK("k_film_fwd_ring");
   return 0;
 }
 
 template <typename T, bool HAS_Z>
-static int launch_fwd_ring(int K, const T* x, int64_t ldx, const T* z, T* out, int64_t ldout, T* copy_to, int64_t G, int F, cudaStream_t st) {
-#define RGNN_CASE(KK) case KK: return launch_fwd_ring_k<T, KK, HAS_Z>(x, ldx, z, out, ldout, copy_to, G, F, st);
+static int launch_fwd_ring(int K, const T* x, int64_t ldx, const T* z, T* out, int64_t ldout, T* copy_to, int64_t G, int F, cudaStream_t st, const int2* gb) {
+#define RGNN_CASE(KK) case KK: return launch_fwd_ring_k<T, KK, HAS_Z>(x, ldx, z, out, ldout, copy_to, G, F, st, gb);
   switch (K) { RGNN_CASE(2) RGNN_CASE(3) RGNN_CASE(4) RGNN_CASE(5) RGNN_CASE(6) RGNN_CASE(7) RGNN_CASE(8) default: return RGNN_E_UNSUPPORTED; }
 #undef RGNN_CASE
 }
@@ -324,7 +327,7 @@ template <typename T, int K, int TPB> struct RingBwd {
 template <typename T, int K, int TPB, int NST>
 __global__ void __launch_bounds__(2 * TPB + 32, 1) k_film_bwd_ring(const T* __restrict__ h, int64_t ldh, const T* __restrict__ dagg, int64_t ldd,
                                                                    const T* __restrict__ z, const T* addend, int64_t ldadd,
-                                                                   T* dh, int64_t lddh, T* __restrict__ dz, int64_t G, int F, int fuse_sig) {
+                                                                   T* dh, int64_t lddh, T* __restrict__ dz, int64_t G, int F, int fuse_sig, const int2* __restrict__ gb) {
   using S = RingBwd<T, K, TPB>;
   constexpr int VEC = S::VEC, NE = S::NE, NP = VEC / 2, LPC = S::LPC, NVP = S::NVP;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -351,6 +354,7 @@ __global__ void __launch_bounds__(2 * TPB + 32, 1) k_film_bwd_ring(const T* __re
     const int ncopy = (has_add ? 3 : 2) * K + NE;
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
       const int64_t g = it / ipg;
+      const int64_t nb = gb ? (int64_t)gb[g].x : g * K, eb = gb ? (int64_t)gb[g].y : g * NE;
       const int cb = (int)(it - g * ipg);
       const int64_t coff = (int64_t)cb * S::CH * RING_P;
       tma::mbar_wait(empty + s, ph ^ 1);
@@ -358,10 +362,10 @@ __global__ void __launch_bounds__(2 * TPB + 32, 1) k_film_bwd_ring(const T* __re
       if (lane == 0) tma::mbar_expect_tx(full + s, stage_bytes);
       __syncwarp();
       for (int i = lane; i < ncopy; i += 32) {
-        if (i < K) tma::bulk_g2s(st + i * S::PIECE, h + (g * K + i) * ldh + coff, S::PIECE, full + s);
-        else if (i < 2 * K) tma::bulk_g2s(st + OFF_D + (i - K) * S::PIECE, dagg + (g * K + (i - K)) * ldd + coff, S::PIECE, full + s);
-        else if (i < 2 * K + NE) tma::bulk_g2s(st + OFF_Z + (i - 2 * K) * S::ZPIECE, z + (g * NE + (i - 2 * K)) * 2 * (int64_t)F + 2 * cb * S::CH, S::ZPIECE, full + s);
-        else tma::bulk_g2s(st + OFF_A + (i - 2 * K - NE) * S::PIECE, addend + (g * K + (i - 2 * K - NE)) * ldadd + coff, S::PIECE, full + s);
+        if (i < K) tma::bulk_g2s(st + i * S::PIECE, h + (nb + i) * ldh + coff, S::PIECE, full + s);
+        else if (i < 2 * K) tma::bulk_g2s(st + OFF_D + (i - K) * S::PIECE, dagg + (nb + (i - K)) * ldd + coff, S::PIECE, full + s);
+        else if (i < 2 * K + NE) tma::bulk_g2s(st + OFF_Z + (i - 2 * K) * S::ZPIECE, z + (eb + (i - 2 * K)) * 2 * (int64_t)F + 2 * cb * S::CH, S::ZPIECE, full + s);
+        else tma::bulk_g2s(st + OFF_A + (i - 2 * K - NE) * S::PIECE, addend + (nb + (i - 2 * K - NE)) * ldadd + coff, S::PIECE, full + s);
       }
       if (++s == NST) { s = 0; ph ^= 1; }
     }
@@ -378,6 +382,7 @@ __global__ void __launch_bounds__(2 * TPB + 32, 1) k_film_bwd_ring(const T* __re
   if (!grp_b) {                                            // ---- group A: dh
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
       const int64_t g = it / ipg;
+      const int64_t nb = gb ? (int64_t)gb[g].x : g * K, eb = gb ? (int64_t)gb[g].y : g * NE;
       const int cb = (int)(it - g * ipg);
       const int64_t off = (int64_t)cb * S::CH * RING_P + t * VEC;
       const unsigned char* st = ring + (size_t)s * stage_bytes;
@@ -432,7 +437,7 @@ __global__ void __launch_bounds__(2 * TPB + 32, 1) k_film_bwd_ring(const T* __re
         float o[VEC];
 #pragma unroll
         for (int q = 0; q < NP; ++q) { o[2 * q] = acc[q].x; o[2 * q + 1] = acc[q].y; }
-        Vec16<T>::store(dh + (g * K + u) * lddh + off, o);
+        Vec16<T>::store(dh + (nb + u) * lddh + off, o);
       }
       __syncwarp();
       if (lane == 0) tma::mbar_arrive(empty + s);
@@ -453,6 +458,7 @@ __global__ void __launch_bounds__(2 * TPB + 32, 1) k_film_bwd_ring(const T* __re
   }
   for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
     const int64_t g = it / ipg;
+      const int64_t nb = gb ? (int64_t)gb[g].x : g * K, eb = gb ? (int64_t)gb[g].y : g * NE;
     const int cb = (int)(it - g * ipg);
     const unsigned char* st = ring + (size_t)s * stage_bytes;
     tma::mbar_wait(full + s, ph);
@@ -479,7 +485,7 @@ __global__ void __launch_bounds__(2 * TPB + 32, 1) k_film_bwd_ring(const T* __re
     tma::mbar_wait(sdfull + s, ph);
     const float* sdc = sdx + (s * S::CH + cl) * K;
     const unsigned char* zs = st + OFF_Z + cl * 2 * (int)sizeof(T);
-    T* dzc = dz + g * NE * 2 * (int64_t)F + 2 * (cb * S::CH + cl);
+    T* dzc = dz + eb * 2 * (int64_t)F + 2 * (cb * S::CH + cl);
 #pragma unroll
     for (int i = 0; i < NVP / LPC; ++i) {
       if (my_e[i] >= 0) {
@@ -499,7 +505,7 @@ __global__ void __launch_bounds__(2 * TPB + 32, 1) k_film_bwd_ring(const T* __re
 
 template <typename T, int K>
 static int launch_bwd_ring_k(const T* h, int64_t ldh, const T* dagg, int64_t ldd, const T* z, const T* addend, int64_t ldadd, T* dh, int64_t lddh,
-                             T* dz, int64_t G, int F, int fuse_sig, cudaStream_t st) {
+                             T* dz, int64_t G, int F, int fuse_sig, cudaStream_t st, const int2* gb) {
   constexpr int TPB = K <= 5 ? 256 : 128;
   using S = RingBwd<T, K, TPB>;
   constexpr int NST = (200 * 1024) / S::stage(3) >= 4 ? 4 : ((200 * 1024) / S::stage(3) >= 3 ? 3 : 2);
@@ -516,15 +522,15 @@ static int launch_bwd_ring_k(const T* h, int64_t ldh, const T* dagg, int64_t ldd
   int64_t blocks = num_sms();
   if (blocks > items) blocks = items;
   if (blocks < 1) return 0;
-  kern<<<(unsigned)blocks, 2 * TPB + 32, smem, st>>>(h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, fuse_sig);
+  kern<<<(unsigned)blocks, 2 * TPB + 32, smem, st>>>(h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, fuse_sig, gb);
   RGNN_LAUNCH_CHECK("k_film_bwd_ring");
   return 0;
 }
 
 template <typename T>
 static int launch_bwd_ring(int K, const T* h, int64_t ldh, const T* dagg, int64_t ldd, const T* z, const T* addend, int64_t ldadd, T* dh,
-                           int64_t lddh, T* dz, int64_t G, int F, int fuse_sig, cudaStream_t st) {
-#define RGNN_CASE(KK) case KK: return launch_bwd_ring_k<T, KK>(h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, fuse_sig, st);
+                           int64_t lddh, T* dz, int64_t G, int F, int fuse_sig, cudaStream_t st, const int2* gb) {
+#define RGNN_CASE(KK) case KK: return launch_bwd_ring_k<T, KK>(h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, fuse_sig, st, gb);
   switch (K) { RGNN_CASE(2) RGNN_CASE(3) RGNN_CASE(4) RGNN_CASE(5) RGNN_CASE(6) RGNN_CASE(7) RGNN_CASE(8) default: return RGNN_E_UNSUPPORTED; }
 #undef RGNN_CASE
 }
@@ -544,33 +550,67 @@ bool film_fwd_ring_ok(int dtype, int K, const void* x, int64_t ldx, const void* 
 }
 
 int film_fwd_ring(int dtype, int K, const void* x, int64_t ldx, const void* z, void* out, int64_t ldout, void* copy_to, int64_t G,
-                  int64_t F, cudaStream_t st) {
+                  int64_t F, cudaStream_t st, const int2* gb) {
   if (dtype == RGNN_F32) {
     auto X = static_cast<const float*>(x); auto Z = static_cast<const float*>(z);
-    return z ? launch_fwd_ring<float, true>(K, X, ldx, Z, static_cast<float*>(out), ldout, static_cast<float*>(copy_to), G, (int)F, st)
-             : launch_fwd_ring<float, false>(K, X, ldx, Z, static_cast<float*>(out), ldout, static_cast<float*>(copy_to), G, (int)F, st);
+    return z ? launch_fwd_ring<float, true>(K, X, ldx, Z, static_cast<float*>(out), ldout, static_cast<float*>(copy_to), G, (int)F, st, gb)
+             : launch_fwd_ring<float, false>(K, X, ldx, Z, static_cast<float*>(out), ldout, static_cast<float*>(copy_to), G, (int)F, st, gb);
   }
   auto X = static_cast<const __nv_bfloat16*>(x); auto Z = static_cast<const __nv_bfloat16*>(z);
-  return z ? launch_fwd_ring<__nv_bfloat16, true>(K, X, ldx, Z, static_cast<__nv_bfloat16*>(out), ldout, static_cast<__nv_bfloat16*>(copy_to), G, (int)F, st)
-           : launch_fwd_ring<__nv_bfloat16, false>(K, X, ldx, Z, static_cast<__nv_bfloat16*>(out), ldout, static_cast<__nv_bfloat16*>(copy_to), G, (int)F, st);
+  return z ? launch_fwd_ring<__nv_bfloat16, true>(K, X, ldx, Z, static_cast<__nv_bfloat16*>(out), ldout, static_cast<__nv_bfloat16*>(copy_to), G, (int)F, st, gb)
+           : launch_fwd_ring<__nv_bfloat16, false>(K, X, ldx, Z, static_cast<__nv_bfloat16*>(out), ldout, static_cast<__nv_bfloat16*>(copy_to), G, (int)F, st, gb);
 }
 
 // Backward; returns RGNN_E_UNSUPPORTED when the shape / alignment is not covered (caller falls back to film_complete.cu).
 int film_bwd_ring(int dtype, int K, const void* h, int64_t ldh, const void* dagg, int64_t ldd, const void* z, const void* addend,
-                  int64_t ldadd, void* dh, int64_t lddh, void* dz, int64_t G, int64_t F, int64_t P, int fuse_sig, cudaStream_t st) {
+                  int64_t ldadd, void* dh, int64_t lddh, void* dz, int64_t G, int64_t F, int64_t P, int fuse_sig, cudaStream_t st, const int2* gb) {
   const int es = dtype == RGNN_F32 ? 4 : 2;
   if (!ring_enabled() || K < 2 || K > 8 || P != RING_P || !aligned16(h) || !aligned16(dagg) || !aligned16(z) || (addend && !aligned16(addend)) ||
       (ldh * es) % 16 || (ldd * es) % 16 || (addend && (ldadd * es) % 16))
     return RGNN_E_UNSUPPORTED;
   if (dtype == RGNN_F32)
     return launch_bwd_ring<float>(K, static_cast<const float*>(h), ldh, static_cast<const float*>(dagg), ldd, static_cast<const float*>(z),
-                                  static_cast<const float*>(addend), ldadd, static_cast<float*>(dh), lddh, static_cast<float*>(dz), G, (int)F, fuse_sig, st);
+                                  static_cast<const float*>(addend), ldadd, static_cast<float*>(dh), lddh, static_cast<float*>(dz), G, (int)F, fuse_sig, st, gb);
   return launch_bwd_ring<__nv_bfloat16>(K, static_cast<const __nv_bfloat16*>(h), ldh, static_cast<const __nv_bfloat16*>(dagg), ldd,
                                         static_cast<const __nv_bfloat16*>(z), static_cast<const __nv_bfloat16*>(addend), ldadd,
-                                        static_cast<__nv_bfloat16*>(dh), lddh, static_cast<__nv_bfloat16*>(dz), G, (int)F, fuse_sig, st);
+                                        static_cast<__nv_bfloat16*>(dh), lddh, static_cast<__nv_bfloat16*>(dz), G, (int)F, fuse_sig, st, gb);
 }
 
 }  // namespace rgnn
+
+// ---- ragged batches of complete graphs (a dropped camera in some samples; dgl/dataloader.py:88-99 builds each sample's graph from
+// the cameras present): the batch is bucketed by robot count on the host and each bucket runs the compiled-topology ring kernel
+// over ITS graphs, addressed through `bases` = int32 pairs (first node row, first edge row) - instead of sending the whole batch
+// to the CSR-walking staged kernels (0.29 of HBM peak).
+extern "C" int rgnn_film_bucket_forward(int dtype, const void* x, int64_t ldx, const void* z, void* out, int64_t ldout, void* copy_x_to,
+                                        const int32_t* bases, int64_t bucket_graphs, int64_t robots, int64_t feat, int64_t pix, void* stream) {
+  using namespace rgnn;
+  RGNN_REQUIRE(dtype == RGNN_F32 || dtype == RGNN_BF16, RGNN_E_ARG, "rgnn_film_bucket_forward: bad dtype %d", dtype);
+  RGNN_REQUIRE(bucket_graphs >= 0 && feat > 0 && pix > 0, RGNN_E_ARG, "rgnn_film_bucket_forward: bad sizes");
+  if (bucket_graphs == 0) return 0;
+  RGNN_REQUIRE(x && out && bases, RGNN_E_ARG, "rgnn_film_bucket_forward: null pointer");
+  RGNN_REQUIRE((reinterpret_cast<uintptr_t>(bases) & 7u) == 0, RGNN_E_ALIGN, "rgnn_film_bucket_forward: bases must be 8-byte aligned");
+  const int es = dtype == RGNN_F32 ? 4 : 2;
+  if (!film_fwd_ring_ok(dtype, (int)robots, x, ldx, z, feat, pix) || !aligned16(out) || (ldout * es) % 16 || (copy_x_to && !aligned16(copy_x_to)))
+    return RGNN_E_UNSUPPORTED;
+  return film_fwd_ring(dtype, (int)robots, x, ldx, z, out, ldout, copy_x_to, bucket_graphs, feat, as_stream(stream),
+                       reinterpret_cast<const int2*>(bases));
+}
+
+extern "C" int rgnn_film_bucket_backward(int dtype, const void* h, int64_t ldh, const void* dagg, int64_t lddagg, const void* z, int fuse_sigmoid_grad,
+                                         const void* addend, int64_t ldadd, void* dh, int64_t lddh, void* dz, const int32_t* bases,
+                                         int64_t bucket_graphs, int64_t robots, int64_t feat, int64_t pix, void* stream) {
+  using namespace rgnn;
+  RGNN_REQUIRE(dtype == RGNN_F32 || dtype == RGNN_BF16, RGNN_E_ARG, "rgnn_film_bucket_backward: bad dtype %d", dtype);
+  RGNN_REQUIRE(bucket_graphs >= 0 && feat > 0 && pix > 0, RGNN_E_ARG, "rgnn_film_bucket_backward: bad sizes");
+  if (bucket_graphs == 0) return 0;
+  RGNN_REQUIRE(h && dagg && z && dh && dz && bases, RGNN_E_ARG, "rgnn_film_bucket_backward: null pointer");
+  RGNN_REQUIRE((reinterpret_cast<uintptr_t>(bases) & 7u) == 0, RGNN_E_ALIGN, "rgnn_film_bucket_backward: bases must be 8-byte aligned");
+  const int es = dtype == RGNN_F32 ? 4 : 2;
+  if (!aligned16(dh) || (lddh * es) % 16 || !aligned16(dz)) return RGNN_E_UNSUPPORTED;
+  return film_bwd_ring(dtype, (int)robots, h, ldh, dagg, lddagg, z, addend, ldadd, dh, lddh, dz, bucket_graphs, feat, pix, fuse_sigmoid_grad,
+                       as_stream(stream), reinterpret_cast<const int2*>(bases));
+}
 
 extern "C" int rgnn_complete_mean_mix(int dtype, const void* x, int64_t ldx, const void* addend, int64_t ldadd, void* out, int64_t ldout,
                                       int64_t num_graphs, int64_t robots, int64_t row, float sa, float sb, void* stream) {

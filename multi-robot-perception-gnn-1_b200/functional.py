@@ -56,6 +56,22 @@ def _aggregate(ix, x, z, use_beta, nbr_scale, post, dst_scale, addend, out, copy
             if (f * p) % 64 == 0:
                 f, p = f * p // 64, 64
     row = f * p
+    buckets = getattr(ix, "buckets", None)
+    if (buckets and z is not None and not transposed and post == _lib.POST_MEAN and nbr_scale is None and dst_scale is None
+            and addend is None and use_beta):
+        # ragged batch of complete graphs: one compiled-topology launch per robot count instead of the CSR-walking kernels
+        nbytes = x.element_size() * (ix.N * row * (2 + (copy_to is not None)) + ix.E * 2 * f)
+        done = True
+        with _lib.timed("aggregate_fwd", nbytes):
+            for k, cnt, bases in buckets:
+                rc = lib().rgnn_film_bucket_forward(dtype_code(x), ptr(x), row if ldx is None else ldx, ptr(z), ptr(out),
+                                                    row if ldout is None else ldout, ptr(copy_to), ptr(bases), cnt, k, f, p, stream())
+                if rc == -4:          # shape not covered (same answer for every bucket: nothing has been launched yet)
+                    done = False
+                    break
+                check(rc, "rgnn_film_bucket_forward")
+        if done:
+            return out
     if transposed:
         ptr32, nbr, eid = ix.out_ptr32, ix.out_dst32, ix.out_eid32
     else:
@@ -517,6 +533,19 @@ def _film_backward(ix, h, dagg, z, addend, fuse_sig, ldd=None, ldadd=None, dh=No
         dh = addend if addend is not None else torch.empty_like(h)
     dz = torch.empty_like(z)
     nbytes = h.element_size() * (ix.N * f * p * (3 + (addend is not None)) + 2 * ix.E * 2 * f)
+    buckets = getattr(ix, "buckets", None)
+    if buckets:
+        done = True
+        with _lib.timed("film_backward", nbytes):
+            for k, cnt, bases in buckets:
+                rc = lib().rgnn_film_bucket_backward(dtype_code(h), ptr(h), f * p, ptr(dagg), ldd, ptr(z), int(fuse_sig), ptr(addend), ldadd,
+                                                     ptr(dh), f * p, ptr(dz), ptr(bases), cnt, k, f, p, stream())
+                if rc == -4:
+                    done = False
+                    break
+                check(rc, "rgnn_film_bucket_backward")
+        if done:
+            return dh, dz
     with _lib.timed("film_backward", nbytes):
         rc = lib().rgnn_film_backward(dtype_code(h), ptr(h), f * p, ptr(dagg), ldd, ptr(z), int(fuse_sig), ptr(addend), ldadd,
                                       ptr(dh), f * p, ptr(dz), ptr(ix.inv_in_deg), ptr(ix.ptr32), ptr(ix.idx32), ptr(ix.noff32),

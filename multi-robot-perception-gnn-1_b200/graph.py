@@ -34,6 +34,17 @@ class RobotGraph:
         # K if every graph is the reference's complete K-robot topology in its edge order (dataloader.py:88-95), else 0.
         # Established on the host where the edge lists are host data (graph(), robot_batch()); a claim on device data
         # is verified on the device by rgnn_check_complete and reported by validate().
+        # complete_k may also be a per-graph list (batch() of graphs with different robot counts - a sample that lost a camera):
+        # complete_ks keeps it, and a RAGGED batch whose graphs are all complete is bucketed by K for the compiled-topology kernels.
+        if isinstance(complete_k, (list, tuple)):
+            ks = [int(k) for k in complete_k]
+            if len(ks) != len(self._bnn):
+                raise ValueError("per-graph complete_k list does not match the number of graphs")
+            self.complete_ks = [k if (k >= 2 and k == n and e == k * (k - 1)) else 0 for k, n, e in zip(ks, self._bnn, self._bne)]
+            complete_k = self.complete_ks[0] if self.complete_ks and all(k == self.complete_ks[0] for k in self.complete_ks) else 0
+        else:
+            ck = int(complete_k) if complete_k else 0
+            self.complete_ks = [ck if (ck >= 2 and n == ck and e == ck * (ck - 1)) else 0 for n, e in zip(self._bnn, self._bne)]
         self.complete_k = int(complete_k) if complete_k and all(n == complete_k for n in self._bnn) else 0
         self._global = None   # (src, dst, node_offsets, edge_offsets) on self.device
         self._index = None
@@ -126,8 +137,31 @@ class RobotGraph:
             ix.out_dst32, ix.out_eid32 = ix.idx32[2 * e: 3 * e], ix.idx32[3 * e: 4 * e]
             ix.src32, ix.dst32 = ix.idx32[4 * e: 5 * e], ix.idx32[5 * e: 6 * e]
             ix.inv_in_deg, ix.rsqrt_in, ix.rsqrt_out = ix.norm[0:n], ix.norm[n: 2 * n], ix.norm[2 * n: 3 * n]
+            ix.buckets = self._k_buckets(dev) if not ix.complete_k else None
             self._index = ix
         return self._index
+
+    def _k_buckets(self, dev):
+        """Ragged batch of complete graphs -> [(K, graphs in the bucket, int32 [gb, 2] device tensor of (first node, first edge))],
+        or None when some graph is not a (host-verified) complete 2..8-robot graph.  Host prefix sums + ONE small H2D copy at
+        index-build time; the FiLM kernels then run once per bucket with the topology compiled in."""
+        ks = self.complete_ks
+        if not ks or any(k < 2 or k > 8 for k in ks) or self._n >= 2 ** 31 or self._e >= 2 ** 31:
+            return None
+        nb = eb = 0
+        per = {}
+        for k, n, e in zip(ks, self._bnn, self._bne):
+            per.setdefault(k, []).extend((nb, eb))
+            nb += n
+            eb += e
+        flat = torch.tensor([v for k in sorted(per) for v in per[k]], dtype=torch.int32)
+        flat = flat.to(dev, non_blocking=False)
+        out, off = [], 0
+        for k in sorted(per):
+            cnt = len(per[k]) // 2
+            out.append((k, cnt, flat[off: off + 2 * cnt]))
+            off += 2 * cnt
+        return out
 
     def validate(self):
         """Host-synchronising check that no edge leaves its graph (DGL raises at construction time)."""
@@ -151,7 +185,7 @@ class RobotGraph:
         if device == self.device:
             return self
         g = RobotGraph(self._lsrc.to(device, non_blocking=non_blocking), self._ldst.to(device, non_blocking=non_blocking),
-                       self._bnn, self._bne, self.complete_k)
+                       self._bnn, self._bne, list(self.complete_ks))
         g.ndata = {k: v.to(device, non_blocking=non_blocking) for k, v in self.ndata.items()}
         g.edata = {k: v.to(device, non_blocking=non_blocking) for k, v in self.edata.items()}
         return g
@@ -255,7 +289,7 @@ def batch(graphs):
             raise ValueError("all graphs must carry the same ndata/edata keys")
     bg = RobotGraph(torch.cat([g._lsrc for g in graphs]), torch.cat([g._ldst for g in graphs]),
                     [n for g in graphs for n in g._bnn], [e for g in graphs for e in g._bne],
-                    graphs[0].complete_k if all(g.complete_k == graphs[0].complete_k for g in graphs) else 0)
+                    [k for g in graphs for k in g.complete_ks])
     for k in graphs[0].ndata:
         bg.ndata[k] = torch.cat([g.ndata[k] for g in graphs], 0)
     for k in graphs[0].edata:

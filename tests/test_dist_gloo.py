@@ -32,10 +32,18 @@ def _worker(rank, world, port, q):
     sync = R.parallel.GradSync(blk)
     assert len(sync.buckets) == 2 and sync.buckets[0][0][0].startswith(("gcn2", "conv2"))   # layer 2 reduces first
     # rank-dependent synthetic gradients, produced through autograd so the hooks fire in backward order
-    gen = torch.Generator().manual_seed(100 + rank)
-    loss = sum((p * torch.randn(p.shape, generator=gen)).sum() for p in blk.parameters())
-    loss.backward()
+    # (the collective runs IN PLACE on the gradient buckets as soon as a bucket is complete, so the rank-local gradients are taken
+    #  from a pass with the collective switched off)
+    def local_loss():
+        gen = torch.Generator().manual_seed(100 + rank)
+        return sum((p * torch.randn(p.shape, generator=gen)).sum() for p in blk.parameters())
+    sync.enabled = False
+    local_loss().backward()
+    sync.finish()
     local = {n: p.grad.clone().numpy() for n, p in blk.named_parameters()}
+    sync.enabled = True
+    sync.zero_grad()
+    local_loss().backward()
     sync.finish()
     out = {n: p.grad.clone().numpy() for n, p in blk.named_parameters()}
     # second step must work too (state reset)
