@@ -209,6 +209,17 @@ int rgnn_tc_conv1x1(const void* W, const void* x0, int64_t c0, const void* x1, i
 int rgnn_tc_conv_film_fused(const void* W, const void* h, const void* z, const float* bias, void* y, void* g_out,
                             int64_t graphs, int64_t robots, int64_t F, int64_t Fo, void* stream);
 
+/* north_star (c)/(d), backward: the FiLM-mean backward FUSED INTO THE EPILOGUE of the compress conv's dX GEMM - the gradient of the
+ * concat, dcat = [dh_direct ; dg_h], stays in TMEM and never reaches HBM (autograd of models.py:181-184, 207-211):
+ *   dcat_v = Wc^T dY_v;  dh[u] = dcat[u,:F] + 1/(K-1) sum_{a != u} gamma_{u->a} dcat[a,F:];  dgamma_{u->a} = 1/(K-1) sum_p h[u,:,p] dcat[a,F:,p];
+ *   dbeta_{u->a} = 1/(K-1) sum_p dcat[a,F:,p];  dz = (dgamma, dbeta) [* sigmoid' when fuse_sigmoid_grad].
+ * W_perm: bf16 [2F, Fo] = Wc^T with rows permuted per 64-channel tile t, j < 8: rows 128t+16j+(0..7) = direct channels 64t+8j+(0..7), rows
+ * 128t+16j+8+(0..7) = the aggregated rows F+64t+8j+(0..7) (a channel's two accumulator rows share a warp).  dy [G K, Fo, 64], h [G K, F, 64],
+ * z / dz [G K(K-1), 2F] interleaved (gamma,beta), dh [G K, F, 64], all bf16; G complete `robots`-node graphs (2..6), reference edge order.
+ * HBM traffic: dY + h in, dh out (3 tensor passes) instead of 7 for rgnn_tc_conv1x1 (dX) + rgnn_film_backward. */
+int rgnn_tc_conv_dx_film_bwd(const void* W_perm, const void* dy, const void* h, const void* z, int fuse_sigmoid_grad,
+                             void* dh, void* dz, int64_t graphs, int64_t robots, int64_t F, int64_t Fo, void* stream);
+
 /* weight gradient of the above: dW[m,k] = sum_v sum_p dy[v,m,p] x[v,k,p], x = x0 | x1; dW fp32 (row stride ldw);
  * dbias (nullable) fp32 [M] = sum_v sum_p dy[v,m,p], computed by the otherwise idle epilogue warps from the dy tiles the
  * mainloop stages anyway (no second pass over dy); partial fp32 [splits, M, c0+c1 (+1 if dbias)] scratch; the robots are

@@ -37,6 +37,7 @@ SIGNATURES = {
     "rgnn_tc_cast_weights_affine": [_vp, _i64, _i64, _f32, _f32, _vp, _vp, _vp],
     "rgnn_tc_conv1x1": [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp],
     "rgnn_tc_conv_film_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp],
+    "rgnn_tc_conv_dx_film_bwd": [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _vp],
     "rgnn_tc_conv1x1_wgrad": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _vp],
     "rgnn_tc_gemm_tn": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _f32, _f32, _vp],
     "rgnn_tc_gemm_nn": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _i64, _vp],
@@ -58,6 +59,8 @@ _lib = None
 USE_FUSED = False  # FiLM aggregation fused into the compress GEMM's prologue (rgnn_tc_conv_film_fused; complete graphs of 2..8 robots,
                    # bf16, P = 64).  Correct and tested, but measured SLOWER than aggregation kernel + GEMM at F = 512 (2.13 vs 1.71 ms
                    # with the aggregate stored for the backward, 1.74 vs 1.71 ms in eval), so it is opt-in.
+USE_FUSED_BWD = os.environ.get("RGNN_FUSED_BWD", "1") != "0"   # FiLM backward in the epilogue of the compress conv's dX GEMM (rgnn_tc_conv_dx_film_bwd): dcat never reaches HBM.
+                       # bf16, P = 64, complete graphs of 2..6 robots; anything else runs dX GEMM + FiLM backward kernel.
 USE_TC3 = True     # fp32 (parity mode) transforms as split-bf16 products on the tcgen05 path when the shape allows (rgnn_tc3_*); False:
                    # the CUDA-core FFMA GEMMs (rgnn_gemm)
 USE_TC = True      # bf16 transforms on the tcgen05 path when the shape allows (tests flip it to compare with rgnn_gemm)
@@ -90,8 +93,8 @@ PROFILE = None      # None = off; else dict: name -> list of (start_event, end_e
 class timed:
     """with timed("name", work): <C-ABI call>   - records CUDA events on the current stream when PROFILE is on."""
 
-    def __init__(self, name, work=0.0):
-        self.name, self.work = name, work
+    def __init__(self, name, work=0.0, nbytes=0.0):
+        self.name, self.work, self.nbytes = name, work, nbytes      # nbytes: algorithmic HBM bytes of a kernel whose `work` is flops
 
     def __enter__(self):
         if PROFILE is not None:
@@ -103,7 +106,7 @@ class timed:
         if PROFILE is not None:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
-            PROFILE.setdefault(self.name, []).append((self.s, e, self.work))
+            PROFILE.setdefault(self.name, []).append((self.s, e, self.work, self.nbytes))
         return False
 
 
@@ -111,8 +114,9 @@ def profile_summary():
     """name -> dict(calls, ms_total, ms_avg, work_total) after a torch.cuda.synchronize()."""
     out = {}
     for name, evs in (PROFILE or {}).items():
-        ms = [s.elapsed_time(e) for s, e, _ in evs]
-        out[name] = dict(calls=len(ms), ms_total=sum(ms), ms_avg=sum(ms) / max(1, len(ms)), work_total=sum(w for _, _, w in evs))
+        ms = [ev[0].elapsed_time(ev[1]) for ev in evs]
+        out[name] = dict(calls=len(ms), ms_total=sum(ms), ms_avg=sum(ms) / max(1, len(ms)), work_total=sum(ev[2] for ev in evs),
+                         bytes_total=sum(ev[3] for ev in evs))
     return out
 
 

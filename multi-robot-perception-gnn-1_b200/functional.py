@@ -250,6 +250,34 @@ def _cached_casts(w, wf, split3=False):
     return o, ot
 
 
+_PERM = {}
+
+
+def _dx_film_perm(f, device):
+    """Row order of the permuted Wc^T operand of rgnn_tc_conv_dx_film_bwd (include/robot_gnn.h): per 64-channel tile and group of 8
+    channels, the 8 direct rows then the 8 aggregated rows."""
+    key = (f, str(device))
+    if key not in _PERM:
+        c = torch.arange(f).view(f // 64, 8, 1, 8)                     # [tile, group, 1, lane]
+        _PERM[key] = torch.cat((c, c + f), dim=2).reshape(-1).to(device)   # [tile, group, {direct, agg}, lane]
+    return _PERM[key]
+
+
+def _cached_wt_perm(w, wt, f):
+    """The permuted transposed weight for the fused dX + FiLM-backward kernel, cached on the parameter like its casts."""
+    ent = getattr(w, "_rgnn_castp", None)
+    ver = w._version
+    if ent is not None and ent[0] == ver and ent[2] == wt.data_ptr() and not torch.cuda.is_current_stream_capturing():
+        return ent[1]
+    wp = ent[1] if (ent is not None and ent[1].shape == wt.shape and ent[1].device == wt.device) else torch.empty_like(wt)
+    torch.index_select(wt, 0, _dx_film_perm(f, wt.device), out=wp)     # (a row gather of a 1 MB weight copy: host-side plumbing)
+    try:
+        w._rgnn_castp = (ver, wp, wt.data_ptr())
+    except Exception:
+        pass
+    return wp
+
+
 def _split3(x, n_valid=None, plane=None):
     """fp32 tensor -> bf16 planes [3, plane] with x = x0 + x1 + x2 (rgnn_tc_split3); elements [n_valid, plane) are zero."""
     n = x.numel() if n_valid is None else n_valid
@@ -603,6 +631,10 @@ class GNNLayerFn(torch.autograd.Function):
             with torch.cuda.device(h.device):
                 _aggregate(ix, h, z, True, None, _lib.POST_MEAN, None, None, gh, None, False)
             y, wc2, ctx.tc, planes, ctx.wt = _compress_forward(h, gh, wc, bc)
+        # backward plan: FiLM backward inside the dX GEMM's epilogue (dcat never written) when the shape allows
+        ctx.fused_bwd = bool(_lib.USE_FUSED_BWD and ctx.tc == 1 and need_bwd and 2 <= ix.complete_k <= 6 and p == 64 and f % 64 == 0
+                             and fo % 64 == 0 and ctx.wt is not None and ctx.wt.dim() == 2 and ix.N == ix.G * ix.complete_k)
+        ctx.wtp = _cached_wt_perm(wc, ctx.wt, f) if ctx.fused_bwd else None
         ctx.g, ctx.wshape = g, tuple(wc.shape)
         ctx.save_for_backward(h, pose, w2f, a1, z, gh, wc2, *[t for t in planes if t is not None and need_bwd])
         return y
@@ -614,12 +646,24 @@ class GNNLayerFn(torch.autograd.Function):
         ix = ctx.g.index()
         need = ctx.needs_input_grad
         need_edge = any(need[2:6])
-        dh_direct, dgh, dwc, dbc = _compress_backward(dy.contiguous(), h, gh, wc2, ctx.tc, need[0], need[0] or need_edge, need[6], need[7],
-                                                      planes=planes, wt=ctx.wt)
-        dh = dw1 = db1 = dw2 = db2 = None
+        dy = dy.contiguous()
+        dh = dw1 = db1 = dw2 = db2 = dzp = None
+        if getattr(ctx, "fused_bwd", False) and (need[0] or need_edge):
+            f, fo = h.shape[1], wc2.shape[0]
+            dh, dzp = torch.empty_like(h), torch.empty_like(z)
+            nbytes = 2.0 * (ix.N * 64 * (2 * f + fo) + 2 * ix.E * 2 * f)
+            with torch.cuda.device(dy.device), _lib.timed("dx_film_bwd", 2.0 * fo * 2 * f * ix.N * 64, nbytes):
+                check(lib().rgnn_tc_conv_dx_film_bwd(ptr(ctx.wtp), ptr(dy), ptr(h), ptr(z), 1, ptr(dh), ptr(dzp), ix.G, ix.complete_k, f, fo,
+                                                     stream()), "rgnn_tc_conv_dx_film_bwd")
+            _, _, dwc, dbc = _compress_backward(dy, h, gh, wc2, ctx.tc, False, False, need[6], need[7], planes=planes, wt=ctx.wt)
+        else:
+            dh_direct, dgh, dwc, dbc = _compress_backward(dy, h, gh, wc2, ctx.tc, need[0], need[0] or need_edge, need[6], need[7],
+                                                          planes=planes, wt=ctx.wt)
+            if need[0] or need_edge:
+                with torch.cuda.device(dy.device):
+                    dh, dzp = _film_backward(ix, h, dgh, z, dh_direct, True)
         with torch.cuda.device(dy.device):
             if need[0] or need_edge:
-                dh, dzp = _film_backward(ix, h, dgh, z, dh_direct, True)
                 if need_edge:
                     dw1, db1, dw2, db2 = edge_mlp_param_grads(pose, w2f, a1, dzp, w2t=ctx.w2t)
         return (dh if need[0] else None, None, dw1, db1, dw2, db2,

@@ -226,3 +226,39 @@ def test_block_with_fused_prologue_matches_unfused(R, train):
             R._lib.USE_FUSED = False
     for a, b in zip(*res):
         assert nerr(b, a) <= 1e-2
+
+
+@pytest.mark.parametrize("g_,k,f", [(5, 5, 512), (3, 2, 64), (4, 3, 128), (7, 4, 256), (2, 6, 192), (150, 5, 128)])
+def test_fused_dx_film_backward(R, g_, k, f):
+    """north_star (c)/(d): the FiLM backward in the epilogue of the dX GEMM (rgnn_tc_conv_dx_film_bwd, default for bf16 complete graphs
+    of 2..6 robots) against the unfused dX GEMM + FiLM backward kernel pair and against the fp64 oracle - dh and every gradient."""
+    from robot_check import check_block, make_block
+    from oracle import gnn_oracle as O
+    L = R._lib
+    assert L.USE_FUSED_BWD
+    errs = check_block(R, O, g_, k, f, torch.bfloat16, 2e-2)
+    assert max(errs.values()) <= 4e-2, errs
+    sb = O.synthetic_batch(g_, k, f, p=64, seed=4)
+    n = g_ * k
+    dy = torch.randn((n, f, 8, 8), generator=torch.Generator().manual_seed(7)).cuda().bfloat16()
+    res = []
+    for fused in (True, False):
+        L.USE_FUSED_BWD = fused
+        try:
+            blk, _ = make_block(R, O, f, True, True)
+            blk.cuda()
+            g = R.robot_batch(g_, k, device="cuda")
+            h = sb["h"].reshape(n, f, 8, 8).cuda().bfloat16().requires_grad_()
+            n0 = L.lib().rgnn_launch_count()
+            y = blk(g, h, sb["pose"].cuda())
+            y.backward(dy)
+            torch.cuda.synchronize()
+            res.append((y.detach().float(), h.grad.float(), {nm: p.grad.clone() for nm, p in blk.named_parameters()}, L.lib().rgnn_launch_count() - n0))
+        finally:
+            L.USE_FUSED_BWD = True
+    (y1, dh1, g1, l1), (y0, dh0, g0, l0) = res
+    assert torch.equal(y1, y0)                       # same forward
+    assert l1 == (l0 - 2 if f % 128 == 0 else l0)    # one launch per layer less (the tcgen05 conv needs Fo % 128 == 0)
+    assert nerr(dh1, dh0) <= 2e-2                    # dcat is rounded to bf16 only in the unfused path
+    for nm in g1:
+        assert nerr(g1[nm], g0[nm]) <= 2e-2, nm
