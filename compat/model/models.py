@@ -128,7 +128,7 @@ class multi_view_dgl_model(nn.Module):
             h = h_list[-1]
             h = h.view(-1, h.size(-3), h.size(-2), h.size(-1))
             # models.py:180-189; under torch.no_grad() (dgl/eval.py) small batches replay a captured CUDA graph of the slice
-            h = rg.gnn_slice_auto(self, g, h.contiguous())
+            h = rg.gnn_slice_auto(self, g, h, compute_dtype=getattr(self, 'gnn_dtype', None))   # channels-last / other-dtype maps pass the seams
             if self.opt.task == 'depthseg':
                 # the reference never builds depth_decoder / seg_decoder for this model (models.py:191-193)
                 raise AttributeError("multi_view_dgl_model has no depth_decoder/seg_decoder (reference defect, task=depthseg)")

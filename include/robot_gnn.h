@@ -276,6 +276,12 @@ int rgnn_tc3_gemm_nn(const void* A3, int64_t lda, int64_t plane_a, const void* B
 /* out = a > 0 ? da : 0 elementwise over n values (ReLU backward, models.py:148; the bf16 path fuses it into the dA1 GEMM epilogue) */
 int rgnn_relu_grad(int dtype, const void* a, const void* da, void* out, int64_t n, void* stream);
 
+/* ---- encoder -> GNN and GNN -> decoder seams (models.py:177-180 hand-over, :190-205 / blocks.py:13-25 decoder) ----
+ * out[v, c, r] = (out_dtype) x[v, r, c]: per-robot transpose [rows, cols] -> [cols, rows] with the dtype conversion fused, one pass.
+ * channels-last backbone output [N, H*W, F] -> the NCHW [N, F, H*W] the robot-graph kernels consume: rows = H*W, cols = F;
+ * NCHW block output -> channels-last for the decoder's first conv: rows = F, cols = H*W. */
+int rgnn_layout_cast(int in_dtype, const void* x, int out_dtype, void* out, int64_t nodes, int64_t rows, int64_t cols, void* stream);
+
 /* dzpre = dz * z * (1 - z)  elementwise over n values (sigmoid backward, models.py:150) */
 int rgnn_sigmoid_grad(int dtype, const void* z, const void* dz, void* dzpre, int64_t n, void* stream);
 

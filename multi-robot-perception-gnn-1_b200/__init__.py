@@ -9,9 +9,9 @@ from .graph import RobotGraph, graph, batch, robot_batch, function, relative_pos
 from . import functional
 from . import parallel
 from .engine import HostPipeline, GraphedStep, GraphedForward, GraphedTrainSlice, gnn_slice_auto
-from .functional import film_mean, film_mean_cat, copy_u_reduce, edge_mlp, compress, linear, axpby
+from .functional import film_mean, film_mean_cat, copy_u_reduce, edge_mlp, compress, linear, axpby, to_gnn_layout, from_gnn_layout
 from .layers import edge_encoder, GCN, GNNBlock, GraphConv, GCN2Conv, gnn_slice
 
 __all__ = ["RobotGraph", "graph", "batch", "robot_batch", "function", "relative_pose_edges", "complete_k_of", "functional", "film_mean", "film_mean_cat",
-           "copy_u_reduce", "edge_mlp", "compress", "linear", "axpby", "edge_encoder", "GCN", "GNNBlock",
+           "copy_u_reduce", "edge_mlp", "compress", "linear", "axpby", "to_gnn_layout", "from_gnn_layout", "edge_encoder", "GCN", "GNNBlock",
            "GraphConv", "GCN2Conv", "HostPipeline", "GraphedStep", "GraphedForward", "GraphedTrainSlice", "gnn_slice_auto", "gnn_slice"]

@@ -47,6 +47,7 @@ SIGNATURES = {
     "rgnn_tc3_conv1x1_wgrad": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _i64, _vp],
     "rgnn_tc3_gemm_tn": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _f32, _vp],
     "rgnn_tc3_gemm_nn": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _i64, _vp],
+    "rgnn_layout_cast": [_i32, _vp, _i32, _vp, _i64, _i64, _i64, _vp],
     "rgnn_relu_grad": [_i32, _vp, _vp, _vp, _i64, _vp],
     "rgnn_sigmoid_grad": [_i32, _vp, _vp, _vp, _i64, _vp],
     "rgnn_axpby": [_i32, _f32, _vp, _f32, _vp, _vp, _i64, _vp],

@@ -62,3 +62,64 @@ extern "C" int rgnn_relative_pose(int pose_is_f64, const void* poses, float* edg
   RGNN_LAUNCH_CHECK("k_relative_pose");
   return 0;
 }
+
+
+// ---- section 8(f) row 2: the seams either side of the GNN slice --------------------------------------------------------------
+// A backbone run in channels-last (NHWC: what cuDNN's tensor-core convolutions want) hands over [N, H*W, F] rows; the robot-graph
+// kernels consume NCHW [N, F, H*W] (a robot's [64 ch x 64 px] slab is one MN-major tensor-core operand block); the decoder's first
+// conv (TransBlock 5x5, dgl/model/blocks.py:16) again prefers channels-last.  One pass per seam: tiled transpose with the dtype
+// conversion fused (fp32 <-> bf16), instead of torch's .contiguous() followed by .to(dtype) (two passes each way).
+namespace rgnn {
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) k_layout_cast(const TI* __restrict__ x, TO* __restrict__ out, int64_t nodes, int R, int C) {
+  // per node: in [R, C] (C contiguous) -> out [C, R] (R contiguous); 64 x 64 tiles through shared memory, coalesced on both sides
+  __shared__ float t[64][65];
+  const int tiles_r = (R + 63) / 64, tiles_c = (C + 63) / 64;
+  const int64_t total = nodes * tiles_r * tiles_c;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;       // 64 x 4
+  for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    const int64_t v = w / (tiles_r * tiles_c);
+    const int rem = (int)(w - v * tiles_r * tiles_c);
+    const int r0 = (rem / tiles_c) * 64, c0 = (rem % tiles_c) * 64;
+    const TI* xi = x + v * (int64_t)R * C;
+    TO* oo = out + v * (int64_t)R * C;
+#pragma unroll 4
+    for (int j = ty; j < 64; j += 4) {
+      const int r = r0 + j, c = c0 + tx;
+      t[j][tx] = (r < R && c < C) ? to_f32<TI>(xi[(int64_t)r * C + c]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = ty; j < 64; j += 4) {
+      const int c = c0 + j, r = r0 + tx;
+      if (r < R && c < C) oo[(int64_t)c * R + r] = from_f32<TO>(t[tx][j]);
+    }
+    __syncthreads();
+  }
+}
+}  // namespace rgnn
+
+// out[v, c, r] = (out_dtype) x[v, r, c]: per-node transpose [rows, cols] -> [cols, rows] with dtype conversion.
+// channels-last -> NCHW: rows = H*W, cols = F;  NCHW -> channels-last: rows = F, cols = H*W.
+extern "C" int rgnn_layout_cast(int in_dtype, const void* x, int out_dtype, void* out, int64_t nodes, int64_t rows, int64_t cols, void* stream) {
+  using namespace rgnn;
+  RGNN_REQUIRE((in_dtype == RGNN_F32 || in_dtype == RGNN_BF16) && (out_dtype == RGNN_F32 || out_dtype == RGNN_BF16), RGNN_E_ARG,
+               "rgnn_layout_cast: bad dtype");
+  RGNN_REQUIRE(nodes >= 0 && rows > 0 && cols > 0 && rows < (1 << 30) && cols < (1 << 30), RGNN_E_ARG, "rgnn_layout_cast: bad sizes");
+  if (nodes == 0) return 0;
+  RGNN_REQUIRE(x && out, RGNN_E_ARG, "rgnn_layout_cast: null pointer");
+  const int64_t tiles = nodes * ((rows + 63) / 64) * ((cols + 63) / 64);
+  int64_t blocks = tiles < 16 * num_sms() ? tiles : 16 * num_sms();
+  cudaStream_t st = as_stream(stream);
+  const int R = (int)rows, C = (int)cols;
+  if (in_dtype == RGNN_F32 && out_dtype == RGNN_F32)
+    k_layout_cast<float, float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(out), nodes, R, C);
+  else if (in_dtype == RGNN_F32)
+    k_layout_cast<float, __nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), nodes, R, C);
+  else if (out_dtype == RGNN_F32)
+    k_layout_cast<__nv_bfloat16, float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<float*>(out), nodes, R, C);
+  else
+    k_layout_cast<__nv_bfloat16, __nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), nodes, R, C);
+  RGNN_LAUNCH_CHECK("k_layout_cast");
+  return 0;
+}

@@ -232,7 +232,7 @@ import os as _os
 GRAPHED_TRAIN = _os.environ.get("ROBOT_GNN_GRAPHED_TRAIN", "0") == "1"
 
 
-def gnn_slice_auto(mod, g, h, pose=None):
+def gnn_slice_auto(mod, g, h, pose=None, compute_dtype=None):
     """gnn_slice, replayed from captured CUDA graphs when that is safe and pays: a small CUDA batch of complete K-robot graphs
     (2..8 robots), intended return key.  Gradients disabled (eval): one forward graph (GraphedForward).  Gradients enabled
     (training): a forward and a backward graph behind one autograd node (GraphedTrainSlice).  Anything else runs the eager path."""
@@ -240,12 +240,13 @@ def gnn_slice_auto(mod, g, h, pose=None):
     opt = mod.opt
     k = g.complete_k
     train = torch.is_grad_enabled()
-    ok = (h.is_cuda and 2 <= k <= 8 and g.num_nodes() == g.batch_size * k and h.dim() == 4
+    ok = (h.is_cuda and 2 <= k <= 8 and g.num_nodes() == g.batch_size * k and h.dim() == 4 and h.is_contiguous()
+          and (compute_dtype is None or compute_dtype == h.dtype)
           and g.num_nodes() <= GRAPHED_EVAL_MAX_NODES and getattr(opt, "compress_gcn", False)
           and mod.gcn1.return_key == "images" and mod.gcn1.film and h.dtype in (torch.float32, torch.bfloat16)
           and not torch.cuda.is_current_stream_capturing() and (GRAPHED_TRAIN or not train))
     if not ok:
-        return gnn_slice(mod, g, h, pose)
+        return gnn_slice(mod, g, h, pose, compute_dtype=compute_dtype)
     pose = g.edata['pose'] if pose is None else pose
     key = (train, bool(h.requires_grad), g.batch_size, k, h.shape[1], tuple(h.shape[2:]), h.dtype, h.device)
     cache = _GRAPHED.setdefault(mod, {})

@@ -892,3 +892,73 @@ class BiasAddFn(torch.autograd.Function):
 
 def bias_add(x, bias):
     return BiasAddFn.apply(x, bias)
+
+
+# ---- seams either side of the GNN slice ---------------------------------------------------------------------------
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def _is_channels_last(x):
+    return x.dim() == 4 and x.shape[1] > 1 and x.shape[2] * x.shape[3] > 1 and x.is_contiguous(memory_format=torch.channels_last) \
+        and not x.is_contiguous()
+
+
+class LayoutCastFn(torch.autograd.Function):
+    """One-pass memory-format + dtype change of a [N, F, H, W] feature map (rgnn_layout_cast): channels-last <-> NCHW, fp32 <-> bf16.
+    to_nchw=True : input physically [N, H*W, F] (channels-last)  -> contiguous NCHW tensor of `dtype`   (encoder -> GNN seam)
+    to_nchw=False: input contiguous NCHW                          -> channels-last tensor of `dtype`    (GNN -> decoder seam)
+    The backward is the mirror-image call, so a channels-last bf16/fp32 backbone or decoder never sees a torch transpose copy."""
+
+    @staticmethod
+    def forward(ctx, x, dtype, to_nchw):
+        _lib.require_cuda(x)
+        if x.dtype not in _DT or dtype not in _DT:
+            raise TypeError("feature maps are float32 or bfloat16")
+        n, f, hh, ww = x.shape
+        ctx.in_dtype, ctx.to_nchw = x.dtype, to_nchw
+        if to_nchw:
+            if not x.is_contiguous(memory_format=torch.channels_last):
+                raise ValueError("to_nchw expects a channels-last tensor")
+            out = torch.empty((n, f, hh, ww), dtype=dtype, device=x.device)
+            rows, cols = hh * ww, f
+        else:
+            x = x.contiguous()
+            out = torch.empty((n, f, hh, ww), dtype=dtype, device=x.device, memory_format=torch.channels_last)
+            rows, cols = f, hh * ww
+        with torch.cuda.device(x.device), _lib.timed("seam", x.numel() * (x.element_size() + out.element_size())):
+            check(lib().rgnn_layout_cast(_DT[x.dtype], ptr(x), _DT[dtype], ptr(out), n, rows, cols, stream()), "rgnn_layout_cast")
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        n, f, hh, ww = d.shape
+        if ctx.to_nchw:       # forward produced NCHW from channels-last: the gradient goes back as channels-last in the input's dtype
+            d = d.contiguous()
+            out = torch.empty((n, f, hh, ww), dtype=ctx.in_dtype, device=d.device, memory_format=torch.channels_last)
+            rows, cols = f, hh * ww
+        else:
+            if not d.is_contiguous(memory_format=torch.channels_last):
+                d = d.contiguous(memory_format=torch.channels_last)
+            out = torch.empty((n, f, hh, ww), dtype=ctx.in_dtype, device=d.device)
+            rows, cols = hh * ww, f
+        with torch.cuda.device(d.device):
+            check(lib().rgnn_layout_cast(_DT[d.dtype], ptr(d), _DT[ctx.in_dtype], ptr(out), n, rows, cols, stream()), "rgnn_layout_cast")
+        return out, None, None
+
+
+def to_gnn_layout(h, dtype=None):
+    """Encoder -> GNN seam: whatever the backbone emits (NCHW or channels-last, fp32 or bf16) -> the contiguous NCHW tensor of `dtype`
+    the robot-graph kernels consume; a channels-last input is transposed and cast in one pass."""
+    dtype = h.dtype if dtype is None else dtype
+    if _is_channels_last(h):
+        return LayoutCastFn.apply(h, dtype, True)
+    h = h.contiguous()
+    return h if h.dtype == dtype else h.to(dtype)
+
+
+def from_gnn_layout(y, dtype=None, channels_last=False):
+    """GNN -> decoder seam: the block's NCHW output -> the layout / dtype the decoder's first conv wants, in one pass."""
+    dtype = y.dtype if dtype is None else dtype
+    if channels_last:
+        return LayoutCastFn.apply(y, dtype, False)
+    return y if y.dtype == dtype else y.to(dtype)

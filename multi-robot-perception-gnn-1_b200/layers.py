@@ -93,11 +93,25 @@ def _gnn_layer(g, h, pose, gcn, conv):
     return Fn.compress(h, gcn(g, h, pose), conv.weight, conv.bias)
 
 
-def gnn_slice(mod, g, h, pose=None):
+def gnn_slice(mod, g, h, pose=None, compute_dtype=None, keep_format=True):
     """dgl/model/models.py:180-189 on any module that owns gcn1[/conv1][/gcn2/conv2] and .opt (GNNBlock, or a
-    multi_view_dgl_model that keeps the reference's flat parameter names)."""
+    multi_view_dgl_model that keeps the reference's flat parameter names).
+
+    Seams: `h` may arrive channels-last (a backbone run in torch.channels_last) and / or in another dtype than
+    `compute_dtype` (e.g. an fp32 encoder feeding the bf16 throughput mode); it is brought into the kernels' NCHW layout in ONE pass
+    (transpose + cast fused), and with keep_format the result goes back to the caller's memory format and dtype the same way, so the
+    decoder's first conv (blocks.py:16) gets the layout it was handed before."""
     opt = mod.opt
     pose = g.edata['pose'] if pose is None else pose
+    cl_in, dt_in = Fn._is_channels_last(h), h.dtype
+    if cl_in or (compute_dtype is not None and compute_dtype != dt_in):
+        y = _gnn_slice_nchw(mod, g, Fn.to_gnn_layout(h, compute_dtype or dt_in), pose)
+        return Fn.from_gnn_layout(y, dt_in, cl_in) if keep_format else y
+    return _gnn_slice_nchw(mod, g, h, pose)
+
+
+def _gnn_slice_nchw(mod, g, h, pose):
+    opt = mod.opt
     if opt.compress_gcn:
         h = _gnn_layer(g, h, pose, mod.gcn1, mod.conv1)
     elif mod.gcn1.return_key == "image":
