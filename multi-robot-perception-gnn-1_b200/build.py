@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "librobotgnn.so")
-SOURCES = ["api.cu", "csr.cu", "aggregate.cu", "film_complete.cu", "film_ring.cu", "film_dense.cu", "pose.cu", "edge_mlp.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_fused.cu", "gemm_dxfilm.cu"]
+SOURCES = ["api.cu", "csr.cu", "aggregate.cu", "film_complete.cu", "film_ring.cu", "film_dense.cu", "film_mma.cu", "pose.cu", "edge_mlp.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_fused.cu", "gemm_dxfilm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(CSRC, "film_common.cuh"), os.path.join(HERE, "..", "include", "robot_gnn.h")]
 

@@ -349,9 +349,19 @@ static int bwd_dense_t(int K, const T* h, int64_t ldh, const T* dagg, int64_t ld
   return 0;
 }
 
+// tensor-core variants for bf16, K in {16, 32, 48, 64} (film_mma.cu); RGNN_E_UNSUPPORTED otherwise
+int film_fwd_mma(int dtype, int K, const void* x, int64_t ldx, const void* z, void* out, int64_t ldout, void* copy_to, int64_t G, int64_t F,
+                 int64_t P, cudaStream_t st);
+int film_bwd_mma(int dtype, int K, const void* h, int64_t ldh, const void* dagg, int64_t ldd, const void* z, const void* addend, int64_t ldadd,
+                 void* dh, int64_t lddh, void* dz, int64_t G, int64_t F, int64_t P, int fuse_sig, cudaStream_t st);
+
 // Entry points (aggregate.cu dispatches here for complete graphs with K > 8; P/VEC must be 8 (bf16, P=64) or 16 (fp32, P=64)).
 int film_fwd_dense(int dtype, int K, const void* x, int64_t ldx, const void* z, void* out, int64_t ldout, void* copy_to,
                    int64_t G, int64_t F, int64_t P, cudaStream_t st) {
+  {
+    const int rc = film_fwd_mma(dtype, K, x, ldx, z, out, ldout, copy_to, G, F, P, st);
+    if (rc != RGNN_E_UNSUPPORTED) return rc;
+  }
   const int es = dtype == RGNN_F32 ? 4 : 2, vec = 16 / es;
   if (P % vec != 0 || (P * es) % 16 != 0 || !al16(x) || !al16(out) || (copy_to && !al16(copy_to)) || ldx % vec || ldout % vec) return RGNN_E_UNSUPPORTED;
   if (dtype == RGNN_F32 && P / vec == 16)
@@ -365,6 +375,10 @@ int film_fwd_dense(int dtype, int K, const void* x, int64_t ldx, const void* z, 
 
 int film_bwd_dense(int dtype, int K, const void* h, int64_t ldh, const void* dagg, int64_t ldd, const void* z, const void* addend,
                    int64_t ldadd, void* dh, int64_t lddh, void* dz, int64_t G, int64_t F, int64_t P, int fuse_sig, cudaStream_t st) {
+  {
+    const int rc = film_bwd_mma(dtype, K, h, ldh, dagg, ldd, z, addend, ldadd, dh, lddh, dz, G, F, P, fuse_sig, st);
+    if (rc != RGNN_E_UNSUPPORTED) return rc;
+  }
   const int es = dtype == RGNN_F32 ? 4 : 2, vec = 16 / es;
   if (P % vec != 0) return RGNN_E_UNSUPPORTED;
   if (dtype == RGNN_F32 && P / vec == 16)
