@@ -105,3 +105,41 @@ def test_missing_library_is_loud(R, monkeypatch):
     monkeypatch.setattr(R._lib, "LIB_PATH", "/nonexistent/librobotgnn.so")
     with pytest.raises(RuntimeError, match="librobotgnn.so not found"):
         R._lib.lib()
+
+
+def test_per_graph_complete_k_survives_batching_and_drives_the_k_buckets():
+    """A ragged batch (samples with different camera counts, dataloader.py:88-99): batch() keeps every graph's host-verified
+    complete-K claim, the uniform claim is dropped, and the bucket table groups graphs by K with their node / edge bases."""
+    import robot_gnn_b200 as R
+    import torch
+    ks = [5, 3, 5, 4, 3]
+    gs = [R.robot_batch(1, k) for k in ks]
+    b = R.batch(gs)
+    assert b.complete_k == 0 and b.complete_ks == ks
+    assert R.batch([R.robot_batch(1, 4), R.robot_batch(2, 4)]).complete_k == 4
+    # a graph whose edge list is not the reference enumeration poisons only itself
+    odd = R.graph((torch.tensor([0, 1, 2]), torch.tensor([1, 2, 0])), num_nodes=3)
+    assert odd.complete_k == 0 and R.batch([gs[0], odd]).complete_ks == [5, 0]
+    buckets = b._k_buckets(torch.device("cpu"))
+    assert [k for k, _, _ in buckets] == [3, 4, 5] and [n for _, n, _ in buckets] == [2, 1, 2]
+    nb = [0, 5, 8, 13, 17]
+    eb = [0, 20, 26, 46, 58]
+    want = {3: [nb[1], eb[1], nb[4], eb[4]], 4: [nb[3], eb[3]], 5: [nb[0], eb[0], nb[2], eb[2]]}
+    for k, n, t in buckets:
+        assert t.dtype == torch.int32 and t.tolist() == want[k]
+    assert R.batch([gs[0], odd])._k_buckets(torch.device("cpu")) is None
+    assert R.complete_k_of(b._lsrc[:20], b._ldst[:20], [5]) == 5 and R.complete_k_of(b._lsrc, b._ldst, ks) == 0
+
+
+def test_fused_backward_weight_row_permutation():
+    """rgnn_tc_conv_dx_film_bwd wants Wc^T with, per 64-channel tile and group of 8 channels, the 8 direct rows followed by the 8
+    aggregated rows of the same channels (include/robot_gnn.h)."""
+    import robot_gnn_b200 as R
+    import torch
+    f = 192
+    perm = R.functional._dx_film_perm(f, torch.device("cpu"))
+    assert sorted(perm.tolist()) == list(range(2 * f))
+    for t in range(f // 64):
+        for j in range(8):
+            rows = perm[128 * t + 16 * j: 128 * t + 16 * j + 16].tolist()
+            assert rows[:8] == [64 * t + 8 * j + i for i in range(8)] and rows[8:] == [f + 64 * t + 8 * j + i for i in range(8)]
