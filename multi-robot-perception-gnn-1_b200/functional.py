@@ -633,7 +633,7 @@ class GNNLayerFn(torch.autograd.Function):
             y, wc2, ctx.tc, planes, ctx.wt = _compress_forward(h, gh, wc, bc)
         # backward plan: FiLM backward inside the dX GEMM's epilogue (dcat never written) when the shape allows
         ctx.fused_bwd = bool(_lib.USE_FUSED_BWD and ctx.tc == 1 and need_bwd and 2 <= ix.complete_k <= 6 and p == 64 and f % 64 == 0
-                             and fo % 64 == 0 and ctx.wt is not None and ctx.wt.dim() == 2 and ix.N == ix.G * ix.complete_k)
+                             and fo % 64 == 0 and max(f, fo) <= _lib.FUSED_BWD_MAX_F and ctx.wt is not None and ctx.wt.dim() == 2 and ix.N == ix.G * ix.complete_k)
         ctx.wtp = _cached_wt_perm(wc, ctx.wt, f) if ctx.fused_bwd else None
         ctx.g, ctx.wshape = g, tuple(wc.shape)
         ctx.save_for_backward(h, pose, w2f, a1, z, gh, wc2, *[t for t in planes if t is not None and need_bwd])

@@ -235,7 +235,7 @@ def test_fused_dx_film_backward(R, g_, k, f):
     from robot_check import check_block, make_block
     from oracle import gnn_oracle as O
     L = R._lib
-    assert L.USE_FUSED_BWD
+    assert L.USE_FUSED_BWD and f <= L.FUSED_BWD_MAX_F
     errs = check_block(R, O, g_, k, f, torch.bfloat16, 2e-2)
     assert max(errs.values()) <= 4e-2, errs
     sb = O.synthetic_batch(g_, k, f, p=64, seed=4)
@@ -262,3 +262,22 @@ def test_fused_dx_film_backward(R, g_, k, f):
     assert nerr(dh1, dh0) <= 2e-2                    # dcat is rounded to bf16 only in the unfused path
     for nm in g1:
         assert nerr(g1[nm], g0[nm]) <= 2e-2, nm
+
+
+def test_fused_dx_film_backward_wide_layer_when_forced(R):
+    """Above FUSED_BWD_MAX_F the unfused pair is the default (it is faster there); the fused kernel itself is still correct at
+    ResNet-50 width (Fo = 2048: 32 k-blocks per half-tile) when forced."""
+    from robot_check import check_block
+    from oracle import gnn_oracle as O
+    L = R._lib
+    old, L.FUSED_BWD_MAX_F = L.FUSED_BWD_MAX_F, 1 << 20
+    try:
+        n0 = L.lib().rgnn_launch_count()
+        errs = check_block(R, O, 2, 5, 2048, torch.bfloat16, 2e-2, multi=False)
+        n_forced = L.lib().rgnn_launch_count() - n0
+    finally:
+        L.FUSED_BWD_MAX_F = old
+    assert max(errs.values()) <= 4e-2, errs
+    n0 = L.lib().rgnn_launch_count()
+    check_block(R, O, 2, 5, 2048, torch.bfloat16, 2e-2, multi=False)
+    assert L.lib().rgnn_launch_count() - n0 == n_forced + 1
