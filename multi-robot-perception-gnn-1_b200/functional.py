@@ -94,13 +94,16 @@ class AggregateFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, z, g, post, nbr_scale, dst_scale):
+    def forward(ctx, x, z, g, post, nbr_scale, dst_scale, use_beta=True):
         ix = g.index()
         _lib.require_cuda(x, z)
         x = x.contiguous()
+        ctx.use_beta = bool(use_beta)
         if z is not None:
-            if post != "mean" or nbr_scale is not None:
+            if use_beta and (post != "mean" or nbr_scale is not None):
                 raise ValueError("FiLM modulation is defined for the mean reduce without degree scales")
+            if not use_beta and z.requires_grad:
+                raise NotImplementedError("gradients with respect to edge weights are not implemented")
             z = z.contiguous()
             if z.dtype != x.dtype:
                 raise TypeError("z and x must share a dtype")
@@ -110,7 +113,7 @@ class AggregateFn(torch.autograd.Function):
             raise ValueError(f"feature rows ({x.shape[0]}) != graph nodes ({ix.N})")
         out = torch.empty_like(x)
         with torch.cuda.device(x.device):
-            _aggregate(ix, x, z, True, nbr_scale, _POST[post], dst_scale, None, out, None, False)
+            _aggregate(ix, x, z, ctx.use_beta, nbr_scale, _POST[post], dst_scale, None, out, None, False)
         ctx.g, ctx.post = g, post
         ctx.save_for_backward(x, z, nbr_scale, dst_scale)
         return out
@@ -122,21 +125,21 @@ class AggregateFn(torch.autograd.Function):
         dout = dout.contiguous()
         dx = dz = None
         with torch.cuda.device(dout.device):
-            if z is not None and ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:
+            if z is not None and ctx.use_beta and ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:
                 dx, dz = _film_backward(ix, x, dout, z, None, False)
-                return dx, dz, None, None, None, None
+                return dx, dz, None, None, None, None, None
             if ctx.needs_input_grad[0]:
                 back_nbr = {"mean": ix.inv_in_deg, "scale": dst_scale}.get(ctx.post)
                 dx = torch.empty_like(x)
                 _aggregate(ix, dout, z, False, back_nbr, _lib.POST_SCALE if nbr_scale is not None else _lib.POST_NONE,
                            nbr_scale, None, dx, None, True)
-            if z is not None and ctx.needs_input_grad[1]:
+            if z is not None and ctx.use_beta and ctx.needs_input_grad[1]:
                 f, p = _row_shape(x)
                 dz = torch.empty_like(z)
                 with _lib.timed("film_edge_grad", x.element_size() * (2.0 * ix.E * f * p + 4.0 * ix.E * f)):
                     check(lib().rgnn_film_edge_grad(dtype_code(x), ptr(x), f * p, ptr(dout), f * p, ptr(z), 0, ptr(ix.inv_in_deg),
                                                     ptr(ix.src32), ptr(ix.dst32), ptr(dz), ix.E, f, p, stream()), "rgnn_film_edge_grad")
-        return dx, dz, None, None, None, None
+        return dx, dz, None, None, None, None, None
 
 
 class FilmMeanCatFn(torch.autograd.Function):
@@ -192,10 +195,22 @@ def film_mean(g, h, z):
     return AggregateFn.apply(h, z, g, "mean", None, None)
 
 
-def copy_u_reduce(g, x, op="sum", nbr_scale=None, dst_scale=None):
-    """update_all(fn.copy_u, fn.sum|fn.mean) with optional per-source / per-destination scales."""
+def copy_u_reduce(g, x, op="sum", nbr_scale=None, dst_scale=None, edge_weight=None):
+    """update_all(fn.copy_u, fn.sum|fn.mean) with optional per-source / per-destination scales; with edge_weight [E] the message is
+    fn.u_mul_e (DGL GraphConv / GCN2Conv `edge_weight`): the scalar rides in the gamma slot of the per-edge modulation rows."""
     post = "scale" if (op == "sum" and dst_scale is not None) else op
-    return AggregateFn.apply(x, None, g, post, nbr_scale, dst_scale)
+    if edge_weight is None:
+        return AggregateFn.apply(x, None, g, post, nbr_scale, dst_scale)
+    ix = g.index()
+    ew = edge_weight.reshape(-1)
+    if ew.shape[0] != ix.E:
+        raise ValueError(f"edge_weight must have one value per edge ({ix.E}), got {tuple(edge_weight.shape)}")
+    if ew.requires_grad:
+        raise NotImplementedError("gradients with respect to edge_weight are not implemented (the reference never passes one)")
+    f = x.shape[1] if x.dim() > 1 else 1
+    z = torch.zeros((ix.E, 2 * f), dtype=x.dtype, device=x.device)      # (gamma, beta) rows: gamma = w_e for every channel, beta unused
+    z[:, 0::2] = ew.to(x.dtype).unsqueeze(1)
+    return AggregateFn.apply(x, z, g, post, nbr_scale, dst_scale, False)
 
 
 def _gemm(a, sa, b, sb, c, sc, m, n, k, batch=1, red=1, split=1, partial=None, epi=0, bias=None, aux=None, alpha=1.0, beta=0.0,

@@ -155,8 +155,6 @@ class GraphConv(nn.Module):
         self._allow_zero_in_degree = set_value
 
     def forward(self, graph, feat, weight=None, edge_weight=None):
-        if edge_weight is not None:
-            raise NotImplementedError("edge_weight is not used by the robot-graph path")
         ix = graph.index()
         if not self._allow_zero_in_degree and _has_zero_in_degree(ix):
             raise RuntimeError('There are 0-in-degree nodes in the graph, output for those nodes will be invalid. '
@@ -177,11 +175,11 @@ class GraphConv(nn.Module):
         bias_in_gemm = None
         if weight is not None and self._in_feats > self._out_feats:      # multiply first, then aggregate
             feat = Fn.linear(feat, weight)
-            rst = Fn.copy_u_reduce(graph, feat, "sum", ns, ds)
+            rst = Fn.copy_u_reduce(graph, feat, "sum", ns, ds, edge_weight)
             if self.bias is not None:
                 rst = Fn.bias_add(rst, self.bias)
         else:
-            rst = Fn.copy_u_reduce(graph, feat, "sum", ns, ds)
+            rst = Fn.copy_u_reduce(graph, feat, "sum", ns, ds, edge_weight)
             if weight is not None:
                 rst = Fn.linear(rst, weight, self.bias)
             elif self.bias is not None:
@@ -253,17 +251,15 @@ class GCN2Conv(nn.Module):
         self._allow_zero_in_degree = set_value
 
     def forward(self, graph, feat, feat_0, edge_weight=None):
-        if edge_weight is not None:
-            raise NotImplementedError("edge_weight is not used by the robot-graph path")
         ix = graph.index()
         if not self._allow_zero_in_degree and _has_zero_in_degree(ix):
             raise RuntimeError('There are 0-in-degree nodes in the graph, output for those nodes will be invalid.')
-        if self._project_initial_features and 2 <= ix.complete_k <= 8 and ix.N == ix.G * ix.complete_k:
+        if edge_weight is None and self._project_initial_features and 2 <= ix.complete_k <= 8 and ix.N == ix.G * ix.complete_k:
             # complete K-robot graph: D^-1/2 A D^-1/2 X is the mean over the other robots; the alpha mix rides on the same pass
             r = Fn.mean_mix(graph, feat, feat_0, 1 - self.alpha, self.alpha)
             rst = Fn.linear(r, self.weight1, self.bias, alpha=self.beta, ident=1 - self.beta)
             return rst if self._activation is None else self._activation(rst)
-        agg = Fn.copy_u_reduce(graph, feat, "sum", ix.rsqrt_in, ix.rsqrt_in)       # D^-1/2 A D^-1/2 X (in-degree both sides)
+        agg = Fn.copy_u_reduce(graph, feat, "sum", ix.rsqrt_in, ix.rsqrt_in, edge_weight)   # D^-1/2 A D^-1/2 X (in-degree both sides)
         if self._project_initial_features:
             r = Fn.axpby(agg, feat_0, 1 - self.alpha, self.alpha)
             rst = Fn.linear(r, self.weight1, self.bias, alpha=self.beta, ident=1 - self.beta)

@@ -163,8 +163,9 @@ def gnn_block(h, pose, src, dst, layers, compress_gcn=True, return_key="images",
 # A11  north-star operators not executed by the reference (DGL formulas)
 # --------------------------------------------------------------------------------------
 
-def graphconv(feat, src, dst, weight, bias, norm="both"):
-    """dgl.nn.pytorch.GraphConv.forward (imported at dgl/model/models.py:7, never called)."""
+def graphconv(feat, src, dst, weight, bias, norm="both", edge_weight=None):
+    """dgl.nn.pytorch.GraphConv.forward (imported at dgl/model/models.py:7, never called).  edge_weight [E]: the message is
+    fn.u_mul_e(h, w) instead of fn.copy_u (DGL GraphConv, `edge_weight` argument)."""
     n = feat.shape[0]
     src = torch.as_tensor(src, dtype=torch.int64)
     dst = torch.as_tensor(dst, dtype=torch.int64)
@@ -176,7 +177,10 @@ def graphconv(feat, src, dst, weight, bias, norm="both"):
     mult_first = weight is not None and in_feats > out_feats
     if mult_first:
         feat = feat @ weight
-    rst = torch.zeros_like(feat).index_add(0, dst, feat.index_select(0, src))
+    msg = feat.index_select(0, src)
+    if edge_weight is not None:
+        msg = msg * torch.as_tensor(edge_weight, dtype=feat.dtype).reshape((-1,) + (1,) * (feat.dim() - 1))
+    rst = torch.zeros_like(feat).index_add(0, dst, msg)
     if weight is not None and not mult_first:
         rst = rst @ weight
     if norm in ("right", "both"):
@@ -187,15 +191,18 @@ def graphconv(feat, src, dst, weight, bias, norm="both"):
     return rst
 
 
-def gcn2conv(feat, feat_0, src, dst, weight1, bias, layer, alpha=0.1, lambda_=1.0, weight2=None):
-    """dgl.nn.pytorch.GCN2Conv.forward (named by BASELINE.json north_star only)."""
+def gcn2conv(feat, feat_0, src, dst, weight1, bias, layer, alpha=0.1, lambda_=1.0, weight2=None, edge_weight=None):
+    """dgl.nn.pytorch.GCN2Conv.forward (named by BASELINE.json north_star only).  edge_weight [E] as in GraphConv."""
     n = feat.shape[0]
     src = torch.as_tensor(src, dtype=torch.int64)
     dst = torch.as_tensor(dst, dtype=torch.int64)
     beta = math.log(lambda_ / layer + 1)
     norm = torch.bincount(dst, minlength=n).to(feat.dtype).clamp(min=1).pow(-0.5).unsqueeze(1)
     f = feat * norm
-    f = torch.zeros_like(f).index_add(0, dst, f.index_select(0, src)) * norm
+    msg = f.index_select(0, src)
+    if edge_weight is not None:
+        msg = msg * torch.as_tensor(edge_weight, dtype=feat.dtype).reshape((-1,) + (1,) * (feat.dim() - 1))
+    f = torch.zeros_like(f).index_add(0, dst, msg) * norm
     f = f * (1 - alpha)
     f0 = feat_0 * alpha
     if weight2 is None:

@@ -293,9 +293,10 @@ def test_copy_u_mean_variant(R):
 
 
 # ------------------------------------------------------------------------------------------ A11
+@pytest.mark.parametrize("ew", [False, True])
 @pytest.mark.parametrize("norm", ["both", "left", "right", "none"])
 @pytest.mark.parametrize("din,dout", [(48, 32), (32, 48)])
-def test_graphconv_vs_dgl_formula(R, norm, din, dout):
+def test_graphconv_vs_dgl_formula(R, norm, din, dout, ew):
     from oracle import gnn_oracle as O
     gen = torch.Generator().manual_seed(4)
     g_, k = 5, 4
@@ -306,7 +307,8 @@ def test_graphconv_vs_dgl_formula(R, norm, din, dout):
     b = torch.randn((dout,), generator=gen)
     dy = torch.randn((n, 6, dout), generator=gen)
     xo, wo, bo = x.double().requires_grad_(), w.double().requires_grad_(), b.double().requires_grad_()
-    ref = O.graphconv(xo, sb["src"], sb["dst"], wo, bo, norm)
+    ewt = torch.rand(len(sb["src"]), generator=gen) + 0.25 if ew else None      # DGL's `edge_weight` argument (u_mul_e messages)
+    ref = O.graphconv(xo, sb["src"], sb["dst"], wo, bo, norm, edge_weight=None if ewt is None else ewt.double())
     ref.backward(dy.double())
     conv = R.GraphConv(din, dout, norm=norm)
     assert sorted(conv.state_dict().keys()) == ["bias", "weight"]
@@ -314,7 +316,7 @@ def test_graphconv_vs_dgl_formula(R, norm, din, dout):
     conv.cuda()
     g = R.robot_batch(g_, k, device="cuda")
     xc = x.cuda().requires_grad_()
-    y = conv(g, xc)
+    y = conv(g, xc, edge_weight=None if ewt is None else ewt.cuda())
     y.backward(dy.cuda())
     assert nerr(y, ref) <= FP32_TOL
     assert nerr(xc.grad, xo.grad) <= FP32_TOL
@@ -322,8 +324,9 @@ def test_graphconv_vs_dgl_formula(R, norm, din, dout):
     assert nerr(conv.bias.grad, bo.grad) <= 2 * FP32_TOL
 
 
+@pytest.mark.parametrize("ew", [False, True])
 @pytest.mark.parametrize("project", [True, False])
-def test_gcn2conv_vs_dgl_formula(R, project):
+def test_gcn2conv_vs_dgl_formula(R, project, ew):
     from oracle import gnn_oracle as O
     gen = torch.Generator().manual_seed(6)
     g_, k, d = 6, 5, 64
@@ -334,7 +337,9 @@ def test_gcn2conv_vs_dgl_formula(R, project):
     b = torch.randn((d,), generator=gen)
     dy = torch.randn((n, d), generator=gen)
     t = [v.double().requires_grad_() for v in (x, x0, w1, w2, b)]
-    ref = O.gcn2conv(t[0], t[1], sb["src"], sb["dst"], t[2], t[4], layer=2, alpha=0.1, lambda_=1.0, weight2=None if project else t[3])
+    ewt = torch.rand(len(sb["src"]), generator=gen) + 0.25 if ew else None
+    ref = O.gcn2conv(t[0], t[1], sb["src"], sb["dst"], t[2], t[4], layer=2, alpha=0.1, lambda_=1.0, weight2=None if project else t[3],
+                     edge_weight=None if ewt is None else ewt.double())
     ref.backward(dy.double())
     conv = R.GCN2Conv(d, layer=2, alpha=0.1, lambda_=1, project_initial_features=project)
     sd = {"weight1": w1, "bias": b}
@@ -345,7 +350,7 @@ def test_gcn2conv_vs_dgl_formula(R, project):
     conv.cuda()
     g = R.robot_batch(g_, k, device="cuda")
     xc, x0c = x.cuda().requires_grad_(), x0.cuda().requires_grad_()
-    y = conv(g, xc, x0c)
+    y = conv(g, xc, x0c, edge_weight=None if ewt is None else ewt.cuda())
     y.backward(dy.cuda())
     assert nerr(y, ref) <= FP32_TOL
     assert nerr(xc.grad, t[0].grad) <= FP32_TOL and nerr(x0c.grad, t[1].grad) <= FP32_TOL
