@@ -34,22 +34,28 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     a = ap.parse_args()
     import types
+    import torch.distributed as dist
     import robot_gnn_b200 as R
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
+    world, rank = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0))
+    if world > 1:       # --graphs is the per-GPU batch (weak scaling); one NCCL all-reduce of the GNN-layer gradients per step
+        dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(1)
     blk = R.GNNBlock(types.SimpleNamespace(feature_dim=a.feat, compress_gcn=True, multi_gcn=True))
     blk.to(dev)
+    sync = R.parallel.GradSync(blk) if world > 1 else None
     for k in a.robots:
         for g in a.graphs:
             need = cell_bytes(g, k, a.feat) / 1e9
             rec = {"robots": k, "graphs": g, "feat": a.feat, "est_gb": round(need, 1)}
             if need > a.mem_gb:
                 rec["capped"] = True
-                print(json.dumps(rec), flush=True)
+                if rank == 0:
+                    print(json.dumps(rec), flush=True)
                 continue
             n, e = g * k, g * k * (k - 1)
-            gen = torch.Generator(device=dev).manual_seed(1)
+            gen = torch.Generator(device=dev).manual_seed(1 + rank)
             h = torch.rand((n, a.feat, 8, 8), generator=gen, device=dev).bfloat16().requires_grad_()
             dy = torch.randn((n, a.feat, 8, 8), generator=gen, device=dev).bfloat16()
             pose = torch.randn((e, 9), generator=gen, device=dev)
@@ -57,25 +63,45 @@ def main():
 
             def step():
                 h.grad = None
-                for p in blk.parameters():
-                    p.grad = None
+                if sync is not None:
+                    sync.zero_grad()
+                else:
+                    for p in blk.parameters():
+                        p.grad = None
                 blk(gr, h, pose).backward(dy)
+                if sync is not None:
+                    sync.finish()
+
+            def barrier():
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
             for _ in range(3):
                 step()
-            torch.cuda.synchronize()
+            barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(a.steps):
                 step()
             e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / a.steps
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
             flops = 2 * 3 * (4 * e * a.feat ** 2 + 4 * n * 64 * a.feat ** 2)
-            rec.update(ms_per_step=round(ms, 3), graphs_per_s=round(g / ms * 1e3, 1), tflops=round(flops / ms / 1e9, 1),
-                       path="register-tiled complete-graph kernels (K<=8)" if k <= 8 else "dense shared-memory complete-graph kernels (K>8)")
-            print(json.dumps(rec), flush=True)
+            rec.update(n_gpus=world, graphs_per_gpu=g, ms_per_step=round(ms, 3), graphs_per_s=round(world * g / ms * 1e3, 1),
+                       tflops_per_gpu=round(flops / ms / 1e9, 1),
+                       path="streaming ring kernels + fused dX/FiLM backward (K<=6..8)" if k <= 8 else
+                            ("mma.sync per-channel K x K products (K % 16 == 0)" if k % 16 == 0 else "dense CUDA-core complete-graph kernels"))
+            if sync is not None:
+                rec["grad_sync_check"] = "ok" if sync.check_ranks_agree()[0] else "MISMATCH"
+            if rank == 0:
+                print(json.dumps(rec), flush=True)
             del h, dy, pose, gr
             torch.cuda.empty_cache()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
