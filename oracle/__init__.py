@@ -18,4 +18,11 @@ third-party dependency absent from /root/reference (version unpinned by the
 reference; API implies DGL 0.5.x/0.6.x) - its batching / degree-bucketing
 semantics are restated from its published behaviour, so for the graph-runtime
 part parity is "pinned to the restated DGL semantics", not to a DGL binary.
+
+``oracle/_ref/`` (git-ignored; written by ``oracle/build_ref.py`` from ``__graft_entry__.build()`` where /root/reference
+is mounted) holds the reference's own ``dgl/model/{models,blocks}.py`` and ``dgl/{training,dataloader,dataloader_utils,
+utils}.py`` as marshalled code objects - compiled in place, no reference source text in the repository.
+``oracle/ref_runner.py`` executes them: the unmodified model classes are the timed ``--impl reference`` arm /
+``cpu_baseline`` of bench.py and a second pin for the goldens; the unmodified ``train_dgl`` / ``test_dgl`` loops are run
+over the compat packages by tests/test_compat.py.
 """

@@ -69,6 +69,37 @@ def load():
     return dgl, pkg.models
 
 
+def scripts_available():
+    return all(os.path.exists(os.path.join(_REF, "scripts", f + ".bin")) for f in ("training", "dataloader", "dataloader_utils", "utils"))
+
+
+def load_script_module(name, argv=None):
+    """Execute one of the reference's top-level script modules (dgl/training.py and the modules it imports) from its compiled code
+    object under its own name, so `import <name>` inside the others resolves to it.  The caller decides which `dgl` / `model`
+    packages are importable (the compat ones, to run the scripts over the B200 path).  argv: sys.argv while the module body runs
+    (training.py parses its options at import time, training.py:21-52)."""
+    path = os.path.join(_REF, "scripts", name + ".bin")
+    with open(path, "rb") as fh:
+        ver = fh.readline().decode().strip()
+        if ver != sys.version.split()[0]:
+            raise RuntimeError(f"{path} was compiled by Python {ver}, this is {sys.version.split()[0]}: rebuild oracle/_ref")
+        code = marshal.loads(fh.read())
+    mod = types.ModuleType(name)
+    mod.__file__ = path
+    sys.modules[name] = mod
+    old_argv = sys.argv
+    if argv is not None:
+        sys.argv = list(argv)
+    try:
+        exec(code, mod.__dict__)
+    except Exception:
+        sys.modules.pop(name, None)
+        raise
+    finally:
+        sys.argv = old_argv
+    return mod
+
+
 def make_model(ref, f, k, compress_gcn, multi_gcn):
     opt = types.SimpleNamespace(feature_dim=f, compress_gcn=compress_gcn, multi_gcn=multi_gcn, camera_num=k, image_size=256,
                                 task='depth', skip_level=False, backbone='resnet18', pretrained=False)

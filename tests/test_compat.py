@@ -235,3 +235,66 @@ def test_whole_model_forward_matches_the_reference_model(compat, literal):
     assert y.shape == y_ref.shape
     err = float((y.cpu() - y_ref).abs().max() / y_ref.abs().max())
     assert err <= 2e-4, err          # cuDNN vs CPU convolutions in the encoder / decoder; the GNN slice itself is within 1e-5
+
+
+@pytest.mark.gpu
+def test_unmodified_training_script_loops_run_over_compat(compat, monkeypatch):
+    """SURVEY 8(f) row 1, "scripts run unchanged": the reference's own `train_dgl` / `test_dgl` / loss functions (dgl/training.py:60-254,
+    byte-compiled into oracle/_ref/scripts, not a re-typed miniature) drive the compat `dgl` + `model.models` packages on the GPU over a
+    synthetic in-memory dataset: `dgl.batch` collate (training.py:57-58), `data.to('cuda:0')`, `model(data)`, smooth-L1 + edge-aware
+    loss, `loss.backward()`, Adam.  Modules the scripts import but this environment lacks (matplotlib, imagenet_c: plotting / image
+    corruption, unused by the loops) are stubbed."""
+    from oracle import ref_runner
+    if not ref_runner.scripts_available():
+        pytest.skip("oracle/_ref/scripts not built")
+    dgl_c, models_c = compat
+    import types as _t
+    for name in ("matplotlib", "matplotlib.pyplot", "imagenet_c"):
+        m = _t.ModuleType(name)
+        if name == "imagenet_c":
+            for fn in ("gaussian_noise", "shot_noise", "impulse_noise", "motion_blur", "snow", "jpeg_compression"):
+                setattr(m, fn, lambda *a, **k: None)
+        monkeypatch.setitem(sys.modules, name, m)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    for name in ("utils", "dataloader_utils", "dataloader", "training"):
+        monkeypatch.delitem(sys.modules, name, raising=False)
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", os.environ.get("CUDA_VISIBLE_DEVICES", "0"))
+    argv = ["training.py", "-model", "multi_view_dgl", "-task", "depth", "-backbone", "resnet18", "-compress_gcn", "-multi_gcn",
+            "-image_size", "64", "-batch_size", "2", "-dataset", "airsim-mrmps-data", "-lambda_edge", "0.5"]
+    try:
+        for name in ("utils", "dataloader_utils", "dataloader"):
+            ref_runner.load_script_module(name)
+        training = ref_runner.load_script_module("training", argv)
+        opt = training.opt
+        assert opt.camera_num == 5 and opt.compress_gcn and opt.multi_gcn and training.batch is dgl_c.batch
+        opt.feature_dim, opt.output_dim, opt.pretrained = 512, 1, False         # training.py:302-307 / :279-283 set these in its __main__
+        torch.manual_seed(0)
+        K, S = 5, 64
+        src = torch.arange(K).repeat_interleave(K)
+        dst = torch.arange(K).repeat(K)
+        keep = src != dst
+
+        def sample(i):
+            gen = torch.Generator().manual_seed(100 + i)
+            g = dgl_c.graph((src[keep], dst[keep]), num_nodes=K)                # dataloader.py:88-99
+            img = torch.rand((K, 3, S, S), generator=gen)
+            g.ndata['image'] = img
+            g.ndata['depth'] = img.mean(1, keepdim=True) * 5 + 0.5               # a learnable target
+            g.ndata['seg'] = torch.zeros((K, 1, S, S), dtype=torch.long)
+            g.edata['pose'] = torch.randn((K * (K - 1), 9), generator=gen)
+            return g
+        data = [sample(i) for i in range(8)]
+        loader = torch.utils.data.DataLoader(data, batch_size=opt.batch_size, shuffle=False, collate_fn=training._collate_fn)   # training.py:313-314
+        model = models_c.multi_view_dgl_model(opt).cuda()
+        optimizer = torch.optim.Adam(model.parameters(), opt.lrt)
+        losses = []
+        for epoch in range(3):
+            out = training.train_dgl(model, loader, optimizer, epoch, None, opt, lambda_edge=opt.lambda_edge, task=opt.task)     # training.py:335
+            losses.append(float(out[0]))
+        val = training.test_dgl(model, loader, None, opt, task=opt.task)                                                          # training.py:341
+        assert all(l == l and l < 1e6 for l in losses) and float(val[0]) == float(val[0])
+        assert losses[-1] < losses[0]                                            # it trains
+        assert all(p.grad is not None for n, p in model.named_parameters() if n.startswith(("gcn1", "gcn2", "conv1", "conv2")))
+    finally:
+        for name in ("utils", "dataloader_utils", "dataloader", "training"):
+            sys.modules.pop(name, None)
