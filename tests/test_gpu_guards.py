@@ -160,3 +160,102 @@ def test_csr_guards(R):
         a.check(k)
     ptr32.check("ptr32"); idx32.check("idx32"); norm.check("norm")
     assert int(status.item()) == 0
+
+
+# ------------------------------------------------------------------------------------------ round-2 kernels
+@pytest.mark.parametrize("g_,k,f,fo", [(3, 5, 64, 64), (7, 5, 192, 128), (2, 2, 128, 64), (5, 6, 64, 192), (149, 3, 64, 64)])
+@pytest.mark.parametrize("res", ["1", "0"])
+def test_fused_dx_film_backward_guards(R, g_, k, f, fo, res, monkeypatch):
+    """rgnn_tc_conv_dx_film_bwd (both variants): dh / dz are written completely and nothing else, incl. graph counts that are not a
+    multiple of the SM count and widths with an odd number of channel tiles (cluster variant falls back to single CTAs)."""
+    import subprocess, sys, os, textwrap
+    # the variant switch is read once per process: run the check in a child process per setting
+    code = textwrap.dedent(f"""
+        import sys, os, torch
+        sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r}); sys.path.insert(0, {os.path.dirname(os.path.abspath(__file__))!r})
+        import robot_gnn_b200 as R
+        from test_gpu_guards import Guarded, bf
+        L = R._lib
+        g_, k, f, fo = {g_}, {k}, {f}, {fo}
+        n, e = g_ * k, g_ * k * (k - 1)
+        h, dy = bf(n, f, 64, seed=1), bf(n, fo, 64, seed=2)
+        z = torch.sigmoid(bf(e, 2 * f, seed=3).float()).bfloat16()
+        wt = bf(2 * f, fo, seed=4, scale=0.05)
+        wtp = wt.index_select(0, R.functional._dx_film_perm(f, wt.device))
+        dh, dz = Guarded((n, f, 64), torch.bfloat16, 777.0), Guarded((e, 2 * f), torch.bfloat16, 777.0)
+        L.check(L.lib().rgnn_tc_conv_dx_film_bwd(L.ptr(wtp), L.ptr(dy), L.ptr(h), L.ptr(z), 1, L.ptr(dh.view), L.ptr(dz.view), g_, k, f, fo, L.stream()), "dxf")
+        dh.check("dx_film_bwd dh"); dz.check("dx_film_bwd dz")
+        # values against the unfused formulas in fp32
+        dcat = torch.einsum("ko,vop->vkp", wt.float(), dy.float())
+        dd, da = dcat[:, :f], dcat[:, f:]
+        src = torch.arange(k).repeat_interleave(k); dst = torch.arange(k).repeat(k); keep = src != dst
+        src, dst = src[keep].cuda(), dst[keep].cuda()
+        gam = z.float()[:, 0::2].view(g_, k * (k - 1), f); bet = z.float()[:, 1::2].view(g_, k * (k - 1), f)
+        dav, hv = da.view(g_, k, f, 64), h.float().view(g_, k, f, 64)
+        w = 1.0 / (k - 1)
+        msg = gam[..., None] * dav[:, dst] * w
+        ref_dh = dd.view(g_, k, f, 64).clone().index_add_(1, src, msg)
+        dgam = (hv[:, src] * dav[:, dst]).sum(-1) * w * gam * (1 - gam)
+        dbet = dav[:, dst].sum(-1) * w * bet * (1 - bet)
+        assert float((dh.view.float().view(g_, k, f, 64) - ref_dh).abs().max()) <= 2e-2 * float(ref_dh.abs().max())
+        got = dz.view.float().view(g_, k * (k - 1), f, 2)
+        assert float((got[..., 0] - dgam).abs().max()) <= 2e-2 * float(dgam.abs().max())
+        assert float((got[..., 1] - dbet).abs().max()) <= 2e-2 * float(dbet.abs().max())
+        print("ok")
+    """)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, RGNN_DXF_RES=res), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("g_,k,f", [(3, 16, 8), (2, 32, 24), (1, 64, 16), (5, 48, 8)])
+def test_film_mma_guards(R, g_, k, f):
+    """K = 16..64 robots (mma.sync kernels): forward output, dh and dz written completely and nothing else."""
+    L = R._lib
+    n, e = g_ * k, g_ * k * (k - 1)
+    g = R.robot_batch(g_, k, device="cuda")
+    ix = g.index()
+    h, dagg, add = bf(n, f, 64, seed=1), bf(n, f, 64, seed=2), bf(n, f, 64, seed=3)
+    z = torch.sigmoid(bf(e, 2 * f, seed=4).float()).bfloat16()
+    out = Guarded((n, f, 64), torch.bfloat16, 777.0)
+    R.functional._aggregate(ix, h, z, True, None, L.POST_MEAN, None, None, out.view, None, False)
+    out.check("film_mma fwd")
+    dh, dz = Guarded((n, f, 64), torch.bfloat16, 777.0), Guarded((e, 2 * f), torch.bfloat16, 777.0)
+    L.check(L.lib().rgnn_film_backward(L.BF16, L.ptr(h), f * 64, L.ptr(dagg), f * 64, L.ptr(z), 1, L.ptr(add), f * 64, L.ptr(dh.view), f * 64,
+                                       L.ptr(dz.view), L.ptr(ix.inv_in_deg), L.ptr(ix.ptr32), L.ptr(ix.idx32), L.ptr(ix.noff32), ix.G, ix.max_nodes,
+                                       ix.max_edges, ix.complete_k, ix.N, ix.E, f, 64, L.stream()), "film_backward")
+    dh.check("film_mma dh")
+    dz.check("film_mma dz")
+
+
+@pytest.mark.parametrize("n,rows,cols", [(3, 49, 48), (1, 64, 130), (7, 9, 5)])
+def test_layout_cast_and_split3_guards(R, n, rows, cols):
+    L = R._lib
+    x = torch.randn((n, rows, cols), device="cuda")
+    for dt, code in ((torch.bfloat16, L.BF16), (torch.float32, L.F32)):
+        o = Guarded((n, cols, rows), dt, 777.0)
+        L.check(L.lib().rgnn_layout_cast(L.F32, L.ptr(x), code, L.ptr(o.view), n, rows, cols, L.stream()), "layout_cast")
+        o.check("layout_cast")
+        assert torch.equal(o.view, x.transpose(1, 2).to(dt))
+    m = 4 * ((n * rows * cols) // 4)
+    plane = (m + 7) // 8 * 8 + 64
+    p = Guarded((3, plane), torch.bfloat16, 777.0)
+    xf = x.reshape(-1)[:m].contiguous()
+    L.check(L.lib().rgnn_tc_split3(L.ptr(xf), m, plane, L.ptr(p.view), L.stream()), "split3")
+    p.check("split3")
+
+
+@pytest.mark.parametrize("m,n,k", [(77, 128, 64), (300, 256, 128)])
+def test_tc3_gemm_guards(R, m, n, k):
+    """fp32 outputs of the split-plane GEMMs leave through the 32-column TMA-store slabs: rows beyond M must be clipped."""
+    L = R._lib
+    a, b = torch.randn((m, k), device="cuda"), torch.randn((n, k), device="cuda") * 0.1
+    prow = (m + 63) // 64 * 64
+    a3 = torch.empty((3, prow * k), dtype=torch.bfloat16, device="cuda")
+    L.check(L.lib().rgnn_tc_split3(L.ptr(a), m * k, prow * k, L.ptr(a3), L.stream()), "split3")
+    b3 = torch.empty((3, n, k), dtype=torch.bfloat16, device="cuda")
+    L.check(L.lib().rgnn_tc_split3_weights(L.ptr(b), n, k, L.ptr(b3), None, L.stream()), "split3w")
+    c = Guarded((m, n), torch.float32, 9e9)
+    L.check(L.lib().rgnn_tc3_gemm_tn(L.ptr(a3), k, prow, L.ptr(b3), k, n, L.ptr(c.view), n, m, n, k, 0, None, 1.0, L.stream()), "tn3")
+    c.check("tc3_gemm_tn")
+    ref = a.double() @ b.double().t()
+    assert float((c.view.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
