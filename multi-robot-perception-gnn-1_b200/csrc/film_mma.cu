@@ -38,34 +38,63 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 }
 
 // Gamma_c[a][u] (bf16, zero diagonal) for the CTA's 8 channels from the edge-major z; optionally the beta row sums bs[c][a].
-template <bool WITH_BETA>
-__device__ __forceinline__ void build_gamma(unsigned char* gs, float* bs, const __nv_bfloat16* __restrict__ zc0, int64_t zrow, int K) {
-  const int GP = gp_of(K);
+// thread = (destination a, segment of sources u); the edge rows (32 B per edge for the 8 channels) are fetched FOUR AT A TIME before
+// any of them is scattered (a loop with one row in flight is latency-bound: 16 L2 round trips per CTA at K = 64), and the 8 beta
+// sums stay in registers and reach shared memory with ONE atomic per (thread, channel).
+template <bool WITH_BETA, int K>
+__device__ __forceinline__ void build_gamma(unsigned char* gs, float* bs, const __nv_bfloat16* __restrict__ zc0, int64_t zrow) {
+  constexpr int GP = gp_of(K), NSEG = 256 / K, PER = (K + NSEG - 1) / NSEG;
   for (int i = threadIdx.x; i < CT * K; i += blockDim.x) {
     const int c = i / K, a = i - c * K;
     *reinterpret_cast<__nv_bfloat16*>(gs + (size_t)c * K * GP + a * GP + a * 2) = __float2bfloat16_rn(0.f);
     if (WITH_BETA) bs[i] = 0.f;
   }
   __syncthreads();
-  // thread = (destination a, segment of sources u): the 8 beta sums of its edges stay in registers and reach shared memory with
-  // ONE atomic per (thread, channel) instead of one per edge
-  const int nseg = blockDim.x / K, a = threadIdx.x % K, seg = threadIdx.x / K;
-  if (seg < nseg) {
-    const int per = (K + nseg - 1) / nseg;
-    float bsum[CT];
-#pragma unroll
-    for (int c = 0; c < CT; ++c) bsum[c] = 0.f;
-    const int u_hi = min(K, (seg + 1) * per);
-    for (int u = seg * per; u < u_hi; ++u) {
-      if (u == a) continue;
-      const int64_t e = edge_id(K, u, a);
-      const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(zc0 + e * zrow));
-      const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(zc0 + e * zrow + 8));
+  if constexpr (PER < 4) {           // few edges per thread (K = 16): one edge per thread and iteration, atomics per edge
+    constexpr int NE = K * (K - 1);
+    for (int e = threadIdx.x; e < NE; e += blockDim.x) {
+      const int u = e / (K - 1), r = e - u * (K - 1), a = r < u ? r : r + 1;
+      const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(zc0 + (int64_t)e * zrow));
+      const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(zc0 + (int64_t)e * zrow + 8));
       const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
       for (int c = 0; c < CT; ++c) {
         *reinterpret_cast<uint16_t*>(gs + (size_t)c * K * GP + a * GP + u * 2) = (uint16_t)(w[c] & 0xffffu);
-        if (WITH_BETA) bsum[c] += __uint_as_float(w[c] & 0xffff0000u);
+        if (WITH_BETA) atomicAdd(bs + c * K + a, __uint_as_float(w[c] & 0xffff0000u));
+      }
+    }
+    return;
+  }
+  const int a = threadIdx.x % K, seg = threadIdx.x / K;
+  if (seg < NSEG) {
+    float bsum[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) bsum[c] = 0.f;
+    const int u0 = seg * PER;
+#pragma unroll
+    for (int b = 0; b < PER; b += 4) {
+      uint4 v[4][2];
+      bool ok[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int u = u0 + b + j;
+        ok[j] = (b + j < PER) && u < K && u != a;
+        if (ok[j]) {
+          const int64_t e = edge_id(K, u, a);
+          v[j][0] = __ldg(reinterpret_cast<const uint4*>(zc0 + e * zrow));
+          v[j][1] = __ldg(reinterpret_cast<const uint4*>(zc0 + e * zrow + 8));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!ok[j]) continue;
+        const int u = u0 + b + j;
+        const uint32_t w[8] = {v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w, v[j][1].x, v[j][1].y, v[j][1].z, v[j][1].w};
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          *reinterpret_cast<uint16_t*>(gs + (size_t)c * K * GP + a * GP + u * 2) = (uint16_t)(w[c] & 0xffffu);
+          if (WITH_BETA) bsum[c] += __uint_as_float(w[c] & 0xffff0000u);
+        }
       }
     }
     if (WITH_BETA) {
@@ -100,7 +129,7 @@ __global__ void __launch_bounds__(256) k_film_fwd_mma(const __nv_bfloat16* __res
   }
   __syncthreads();
   if (threadIdx.x < 32) stage_rows(bar, xs, x, ldx, n0, c0, K);
-  build_gamma<true>(gs, bs, z + e0 * 2 * (int64_t)F + 2 * c0, 2 * (int64_t)F, K);
+  build_gamma<true, K>(gs, bs, z + e0 * 2 * (int64_t)F + 2 * c0, 2 * (int64_t)F);
   __syncthreads();
   tma::mbar_wait(bar, 0);
 
@@ -170,7 +199,7 @@ __global__ void __launch_bounds__(256) k_film_bwd_mma(const __nv_bfloat16* __res
   __syncthreads();
   if (threadIdx.x < 32) { stage_rows(bar, xs, h, ldh, n0, c0, K); stage_rows(bar, ds, dagg, ldd, n0, c0, K); }
   const __nv_bfloat16* zc0 = z + e0 * 2 * (int64_t)F + 2 * c0;
-  build_gamma<false>(gs, nullptr, zc0, 2 * (int64_t)F, K);
+  build_gamma<false, K>(gs, nullptr, zc0, 2 * (int64_t)F);
   __syncthreads();
   tma::mbar_wait(bar, 0);
 
@@ -292,30 +321,78 @@ __global__ void __launch_bounds__(256) k_film_bwd_mma(const __nv_bfloat16* __res
   {
     __nv_bfloat16* dz0 = dz + e0 * 2 * (int64_t)F + 2 * c0;
     const int64_t zrow = 2 * (int64_t)F;
-    const int ne = K * (K - 1);
-    for (int e = threadIdx.x; e < ne; e += blockDim.x) {
-      const int u = e / (K - 1), r = e - u * (K - 1), a = r < u ? r : r + 1;
-      uint32_t bw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (fuse_sig) {
-        const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(zc0 + (int64_t)e * zrow));
-        const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(zc0 + (int64_t)e * zrow + 8));
-        bw[0] = v0.x; bw[1] = v0.y; bw[2] = v0.z; bw[3] = v0.w; bw[4] = v1.x; bw[5] = v1.y; bw[6] = v1.z; bw[7] = v1.w;
-      }
-      uint32_t ow[8];
-#pragma unroll
-      for (int cc = 0; cc < CT; ++cc) {
-        const uint32_t dgb = *reinterpret_cast<const uint16_t*>(gs + (size_t)cc * K * GP + a * GP + u * 2);
-        float dbt = dbs[cc * K + a] * w;
+    constexpr int NSEG = 256 / K, PER = (K + NSEG - 1) / NSEG;
+    if constexpr (PER < 4) {
+      constexpr int NE = K * (K - 1);
+      for (int e = threadIdx.x; e < NE; e += blockDim.x) {
+        const int u = e / (K - 1), r = e - u * (K - 1), a = r < u ? r : r + 1;
+        uint32_t bw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (fuse_sig) {
-          const float bet = __uint_as_float(bw[cc] & 0xffff0000u);
-          dbt *= bet * (1.f - bet);
+          const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(zc0 + (int64_t)e * zrow));
+          const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(zc0 + (int64_t)e * zrow + 8));
+          bw[0] = v0.x; bw[1] = v0.y; bw[2] = v0.z; bw[3] = v0.w; bw[4] = v1.x; bw[5] = v1.y; bw[6] = v1.z; bw[7] = v1.w;
         }
-        __nv_bfloat16 db16 = __float2bfloat16_rn(dbt);
-        ow[cc] = dgb | ((uint32_t)(*reinterpret_cast<uint16_t*>(&db16)) << 16);
+        uint32_t ow[8];
+#pragma unroll
+        for (int cc = 0; cc < CT; ++cc) {
+          const uint32_t dgb = *reinterpret_cast<const uint16_t*>(gs + (size_t)cc * K * GP + a * GP + u * 2);
+          float dbt = dbs[cc * K + a] * w;
+          if (fuse_sig) {
+            const float bet = __uint_as_float(bw[cc] & 0xffff0000u);
+            dbt *= bet * (1.f - bet);
+          }
+          __nv_bfloat16 db16 = __float2bfloat16_rn(dbt);
+          ow[cc] = dgb | ((uint32_t)(*reinterpret_cast<uint16_t*>(&db16)) << 16);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(dz0 + (int64_t)e * zrow);
+        dst[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        dst[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
       }
-      uint4* dst = reinterpret_cast<uint4*>(dz0 + (int64_t)e * zrow);
-      dst[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-      dst[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+      return;
+    }
+    const int a = threadIdx.x % K, seg = threadIdx.x / K;
+    if (seg < NSEG) {
+      const int u0 = seg * PER;
+      float dbw[CT];
+#pragma unroll
+      for (int cc = 0; cc < CT; ++cc) dbw[cc] = dbs[cc * K + a] * w;
+#pragma unroll
+      for (int b = 0; b < PER; b += 4) {          // four edge rows in flight, as in build_gamma
+        uint4 v[4][2];
+        bool ok[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int u = u0 + b + j;
+          ok[j] = (b + j < PER) && u < K && u != a;
+          if (ok[j] && fuse_sig) {
+            const int64_t e = edge_id(K, u, a);
+            v[j][0] = __ldg(reinterpret_cast<const uint4*>(zc0 + e * zrow));
+            v[j][1] = __ldg(reinterpret_cast<const uint4*>(zc0 + e * zrow + 8));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!ok[j]) continue;
+          const int u = u0 + b + j;
+          const int64_t e = edge_id(K, u, a);
+          const uint32_t bw[8] = {v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w, v[j][1].x, v[j][1].y, v[j][1].z, v[j][1].w};
+          uint32_t ow[8];
+#pragma unroll
+          for (int cc = 0; cc < CT; ++cc) {
+            const uint32_t dgb = *reinterpret_cast<const uint16_t*>(gs + (size_t)cc * K * GP + a * GP + u * 2);
+            float dbt = dbw[cc];
+            if (fuse_sig) {
+              const float bet = __uint_as_float(bw[cc] & 0xffff0000u);
+              dbt *= bet * (1.f - bet);
+            }
+            __nv_bfloat16 db16 = __float2bfloat16_rn(dbt);
+            ow[cc] = dgb | ((uint32_t)(*reinterpret_cast<uint16_t*>(&db16)) << 16);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(dz0 + e * zrow);
+          dst[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          dst[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+        }
+      }
     }
   }
 }
