@@ -586,6 +586,10 @@ def main():
         kernels[name] = {"calls": d["calls"], "ms_avg": round(d["ms_avg"], 4), "share": round(d["ms_total"] / ms_total, 4),
                          "achieved": round(ach, 2), "unit": "GB/s" if is_mem else "TFLOP/s",
                          "frac": round(ach / (hbm_peak if is_mem else tc_peak), 4)}
+        if d.get("bytes_total", 0) > 0 and d["ms_total"] > 0:      # a fused kernel: its own algorithmic HBM bytes beside its GEMM's flops
+            gbs = d["bytes_total"] / (d["ms_total"] * 1e-3) / 1e9
+            kernels[name].update({"algorithmic_bytes_per_launch": d["bytes_total"] / max(1, d["calls"]), "hbm_GBps": round(gbs, 1),
+                                  "hbm_frac": round(gbs / hbm_peak, 4)})
     if not by_time:      # CUDA-graph replay: no per-call events exist
         by_time = [("cuda_graph_replay", dict(work_total=0.0, calls=1))]
         kernels["cuda_graph_replay"] = {"calls": a.steps, "ms_avg": round(ms_total / a.steps, 4), "share": 1.0, "achieved": 0.0,
@@ -604,6 +608,10 @@ def main():
                 "peak": hbm_peak if top_mem else tc_peak, "unit": kernels[top]["unit"], "frac": kernels[top]["frac"],
                 "traffic": traffic, "traffic_source": traffic_source, "algorithmic_per_launch": topd["work_total"] / max(1, topd["calls"]),
                 "peak_source": peak_src, "ms_avg_per_launch": kernels[top]["ms_avg"]}
+    if "hbm_frac" in kernels[top]:
+        roofline["note"] = ("fused dX GEMM + FiLM backward: bounded by neither roofline but by what one SM can take in through shared memory "
+                            "(DESIGN.md 4.1); `achieved` counts its GEMM's flops, hbm_* its own algorithmic bytes (3 tensor passes + z/dz)")
+        roofline["hbm_GBps"], roofline["hbm_frac"] = kernels[top]["hbm_GBps"], kernels[top]["hbm_frac"]
 
     cpu = None
     if not a.no_cpu_baseline:

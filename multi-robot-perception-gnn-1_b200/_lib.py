@@ -37,7 +37,7 @@ SIGNATURES = {
     "rgnn_tc_cast_weights_affine": [_vp, _i64, _i64, _f32, _f32, _vp, _vp, _vp],
     "rgnn_tc_conv1x1": [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp],
     "rgnn_tc_conv_film_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp],
-    "rgnn_tc_conv_dx_film_bwd": [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _vp],
+    "rgnn_tc_conv_dx_film_bwd": [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp],
     "rgnn_tc_conv1x1_wgrad": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _vp],
     "rgnn_tc_gemm_tn": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _f32, _f32, _vp],
     "rgnn_tc_gemm_nn": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _i64, _vp],

@@ -37,6 +37,7 @@ struct Params {
   int F, Fo, kblocks;   // kblocks = Fo / 64
   __nv_bfloat16* dh;    // [G K, F, 64]
   __nv_bfloat16* dz;    // [G K (K-1), 2 F]
+  float* db2;           // optional fp32 [2 F]: column sums of dz (the bias gradient of the edge encoder's last Linear) are ADDED here
   int fuse_sig;
   int debug;            // RGNN_DXF_DEBUG (experiments): 1 = epilogue only drains TMEM, 2 = no per-edge dots, 4 = no dh part, 8 = MMA issuer skips the MMAs
 };
@@ -62,6 +63,34 @@ template <int KR> struct Cfg {
   static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 512;
 };
 
+// mbarrier wait for the single-lane producer / issuer loops: back off between polls.  These warps share their SM sub-partitions
+// with the FiLM epilogue warps, which are issue-bound (ncu: 28 % of all executed instructions were try_wait / branch pairs of
+// spinning warps); a sleeping poller leaves the issue slots to the arithmetic.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(64);
+  }
+}
+
+// 16 lanes x 256 bits, twice (16 columns): registers {row t/4: col 2(t%4), +1; row t/4 + 8: same cols} per 8-column block - the
+// mma.sync accumulator fragment layout
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -367,14 +396,12 @@ template <int KR> struct CfgR {
   static constexpr uint32_t STAGE = A_BYTES + B_BYTES;
   static constexpr uint32_t H_BYTES = KR * CT * 64;           // K x 4 KB
   static constexpr uint32_t Z_BYTES = ((NE * CT * 4 + 1023) / 1024) * 1024;
-  static constexpr uint32_t X_BYTES = ((4 * 16 * (NE + KR) * 4 + 1023) / 1024) * 1024;
-  static constexpr int NST_FIT = (227 * 1024 - 1024 - 512 - 2 * (int)H_BYTES - 2 * (int)Z_BYTES - (int)X_BYTES) / (int)STAGE;
+  static constexpr int NST_FIT = (227 * 1024 - 1024 - 512 - 2 * (int)H_BYTES - 2 * (int)Z_BYTES) / (int)STAGE;
   static constexpr int NST = NST_FIT > 6 ? 6 : NST_FIT;
   static_assert(NST >= 2 && NBUF >= 2, "shared memory / tensor memory budget");
   static constexpr uint32_t H_OFF = NST * STAGE;              // two h half-tile buffers
   static constexpr uint32_t Z_OFF = H_OFF + 2 * H_BYTES;
-  static constexpr uint32_t X_OFF = Z_OFF + 2 * Z_BYTES;     // two gamma/beta buffers (tile i+1's rows arrive under tile i's epilogue)
-  static constexpr uint32_t BAR_OFF = X_OFF + X_BYTES;
+  static constexpr uint32_t BAR_OFF = Z_OFF + 2 * Z_BYTES;   // two gamma/beta buffers (tile i+1's rows arrive under tile i's epilogue)
   static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 512;
 };
 
@@ -412,6 +439,9 @@ k_dx_film_bwd_res(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // per-CTA column sums of dz (one cell per (channel, gamma|beta); a cell is only ever touched by the thread that owns that channel)
+  float* dbacc = reinterpret_cast<float*>(smem + C::BAR_OFF + 512);
+  if (p.db2) for (int i = threadIdx.x; i < 2 * p.F; i += NTHR) dbacc[i] = 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -430,9 +460,9 @@ k_dx_film_bwd_res(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const int64_t g = w / p.tiles;
         for (int ph = 0; ph < 2; ++ph) {
           // the half-tile's h rows (and, with the first half, the tile's gamma/beta rows): double-buffered, asked for up front
-          mbar_wait(bar_xempty + 8 * xb, xphase ^ 1);
+          mbar_wait_backoff(bar_xempty + 8 * xb, xphase ^ 1);
           if (ph == 0) {
-            mbar_wait(bar_zempty + 8 * zb, zphase ^ 1);
+            mbar_wait_backoff(bar_zempty + 8 * zb, zphase ^ 1);
             mbar_expect_tx(bar_zfull + 8 * zb, NE * CT * 4);
             tma_2d(base + C::Z_OFF + zb * C::Z_BYTES, &tmZ, bar_zfull + 8 * zb, 2 * t * CT, (int)(g * NE));
             if (++zb == 2) { zb = 0; zphase ^= 1; }
@@ -441,11 +471,12 @@ k_dx_film_bwd_res(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           tma_3d(base + C::H_OFF + xb * C::H_BYTES, &tmH, bar_xfull + 8 * xb, ph * 32, t * CT, (int)(g * KR));
           if (++xb == 2) { xb = 0; xphase ^= 1; }
           for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            mbar_wait_backoff(bar_empty + 8 * stage, phase ^ 1);
             const uint32_t fb = bar_full + 8 * stage;
             const uint32_t s0 = base + stage * C::STAGE;
-            mbar_expect_tx(fb, C::STAGE);
-            tma_2d(s0, &tmW, fb, kb * BK, t * BM);                                                       // permuted Wc^T rows of the channel tile
+            const bool skip_a = (p.debug & 16) != 0;                                                      // knock-out: what an A operand kept on chip would save
+            mbar_expect_tx(fb, skip_a ? C::B_BYTES : C::STAGE);
+            if (!skip_a) tma_2d(s0, &tmW, fb, kb * BK, t * BM);                                          // permuted Wc^T rows of the channel tile
             tma_3d(s0 + C::A_BYTES, &tmDY, fb, ph * 32, kb * BK, (int)(g * KR));                         // dY[g's robots, 64 o, 32 px]
             if (++stage == NST) { stage = 0; phase ^= 1; }
           }
@@ -461,11 +492,11 @@ k_dx_film_bwd_res(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       int tb = 0; uint32_t tphase = 0;
       for (int64_t w = blockIdx.x; w < work_total; w += gridDim.x) {
         for (int ph = 0; ph < 2; ++ph) {
-          mbar_wait(bar_tempty + 8 * tb, tphase ^ 1);
+          mbar_wait_backoff(bar_tempty + 8 * tb, tphase ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t tacc = tmem_base + tb * C::NCOL;
           for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(bar_full + 8 * stage, phase);
+            mbar_wait_backoff(bar_full + 8 * stage, phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = base + stage * C::STAGE, sb = sa + C::A_BYTES;
 #pragma unroll
@@ -484,12 +515,18 @@ k_dx_film_bwd_res(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     }
   } else if (warp >= 4) {
     // ================================ epilogue: FiLM backward ================================
+    // The accumulator is read with the 16-lane x 256-bit TMEM load shape: thread t of a warp receives, for accumulator rows t/4 and
+    // t/4 + 8 of a 16-lane group, columns 2 (t % 4) + {0, 1} of every 8-column block.  With the host's row permutation (8 direct rows
+    // then the 8 aggregated rows of the same channels) a thread therefore holds BOTH rows of its channel for two pixels: no lane idles
+    // in either half of the math, and the direct and aggregated values meet without a shuffle.  The two warps of a TMEM lane quadrant
+    // split its channels (16 lanes = 8 channels each) and each covers all 32 pixels; the per-edge sums are completed by a butterfly
+    // over the four threads of a channel once per tile.
     const int q = warp & 3;                                     // TMEM lane quadrant
-    const int hw = (warp - 4) >> 2;                             // which 16 of the half-tile's 32 pixels this warp owns
-    const bool is_agg = ((lane >> 3) & 1) != 0;
-    const int ci = 8 * (2 * q + (lane >> 4)) + (lane & 7);      // channel inside the tile (see the row permutation, host side)
+    const int lg = (warp - 4) >> 2;                             // which 16 of its lanes: 8 of the quadrant's 16 channels
+    const int pq = lane & 3;                                    // pixel pair inside an 8-pixel block
+    const int ci = 8 * (2 * q + lg) + (lane >> 2);              // channel inside the tile (see the row permutation, host side)
+    const int hsw = (ci >> 1) & 3;                              // SWIZZLE_64B: 16-byte chunk index ^ ((row >> 1) & 3)
     const float wmean = 1.0f / (KR - 1);
-    float* xs = reinterpret_cast<float*>(smem + C::X_OFF) + (q * 16 + (lane >> 4) * 8 + (lane & 7)) * (NE + KR);
     int tb = 0; uint32_t tphase = 0;
     int xb = 0, zb = 0; uint32_t xphase = 0, zphase = 0;
     for (int64_t w = blockIdx.x; w < work_total; w += gridDim.x) {
@@ -498,12 +535,12 @@ k_dx_film_bwd_res(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       const int c = t * CT + ci;
       float gw[NE];
       float2 dg[NE];
-      float db[KR];
+      float2 db[KR];
 #pragma unroll
       for (int e = 0; e < NE; ++e) dg[e] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int a = 0; a < KR; ++a) db[a] = 0.f;
-      __nv_bfloat16* dh_row = p.dh + ((g * KR) * (int64_t)p.F + c) * 64;
+      for (int a = 0; a < KR; ++a) db[a] = make_float2(0.f, 0.f);
+      __nv_bfloat16* dh_row = p.dh + ((g * KR) * (int64_t)p.F + c) * 64 + 2 * pq;
       const uint32_t* zs = reinterpret_cast<const uint32_t*>(smem + C::Z_OFF + zb * C::Z_BYTES);
       mbar_wait(bar_zfull + 8 * zb, zphase);
 #pragma unroll
@@ -513,14 +550,14 @@ k_dx_film_bwd_res(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         mbar_wait(bar_xfull + 8 * xb, xphase);
         mbar_wait(bar_tfull + 8 * tb, tphase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tacc = tmem_base + tb * C::NCOL + ((uint32_t)(q * 32) << 16);
-        const unsigned char* hs = smem + C::H_OFF + xb * C::H_BYTES;
+        const uint32_t tacc = tmem_base + tb * C::NCOL + ((uint32_t)(q * 32 + lg * 16) << 16);
+        const unsigned char* hs = smem + C::H_OFF + xb * C::H_BYTES + ci * 64 + 4 * pq;
 #pragma unroll 1
-        for (int j = 0; j < 2; ++j) {                           // 8 pixels of every robot per pass
-          const int pl = hw * 2 + j;                            // 16-byte pixel chunk inside the half-tile, 0..3
+        for (int j = 0; j < 2; ++j) {                           // 16 pixels of every robot per pass: 4 per thread
+          // r[u]: {direct px, px+1, aggregated px, px+1} for the first 8-pixel block, then the same for the second
           uint32_t r[KR][8];
 #pragma unroll
-          for (int u = 0; u < KR; ++u) tmem_ld8(tacc + u * 32 + pl * 8, r[u]);
+          for (int u = 0; u < KR; ++u) tmem_ld_16x256b_x2(tacc + u * 32 + j * 16, r[u]);
           tmem_ld_wait();
           if (j == 1) {                                         // this warp has read its part of the accumulator
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -531,50 +568,40 @@ k_dx_film_bwd_res(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           if (!(p.debug & 4)) {
 #pragma unroll
             for (int u = 0; u < KR; ++u) {
-              float2 s[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) s[i] = make_float2(0.f, 0.f);
+              float2 s0 = make_float2(__uint_as_float(r[u][0]), __uint_as_float(r[u][1]));
+              float2 s1 = make_float2(__uint_as_float(r[u][4]), __uint_as_float(r[u][5]));
 #pragma unroll
               for (int a = 0; a < KR; ++a) {
                 if (a == u) continue;
                 const float gm = gw[edge_id(KR, u, a)];
                 const float2 g2 = make_float2(gm, gm);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  s[i] = ffma2(g2, make_float2(__uint_as_float(r[a][2 * i]), __uint_as_float(r[a][2 * i + 1])), s[i]);
+                s0 = ffma2(g2, make_float2(__uint_as_float(r[a][2]), __uint_as_float(r[a][3])), s0);
+                s1 = ffma2(g2, make_float2(__uint_as_float(r[a][6]), __uint_as_float(r[a][7])), s1);
               }
-              uint32_t o[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float sx = __shfl_xor_sync(0xffffffffu, s[i].x, 8), sy = __shfl_xor_sync(0xffffffffu, s[i].y, 8);
-                o[i] = pack_bf16(__uint_as_float(r[u][2 * i]) + sx, __uint_as_float(r[u][2 * i + 1]) + sy);
-              }
-              if (!is_agg) *reinterpret_cast<uint4*>(dh_row + (int64_t)u * p.F * 64 + ph * 32 + pl * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+              __nv_bfloat16* o = dh_row + (int64_t)u * p.F * 64 + ph * 32 + j * 16;
+              *reinterpret_cast<uint32_t*>(o) = pack_bf16(s0.x, s0.y);
+              *reinterpret_cast<uint32_t*>(o + 8) = pack_bf16(s1.x, s1.y);
             }
           }
-          if (is_agg && !(p.debug & 2)) {
+          if (!(p.debug & 2)) {
 #pragma unroll
             for (int a = 0; a < KR; ++a) {
-              float2 t2 = make_float2(__uint_as_float(r[a][0]), __uint_as_float(r[a][1]));
-#pragma unroll
-              for (int i = 1; i < 4; ++i) t2 = fadd2(t2, make_float2(__uint_as_float(r[a][2 * i]), __uint_as_float(r[a][2 * i + 1])));
-              db[a] += t2.x + t2.y;
+              db[a] = fadd2(db[a], make_float2(__uint_as_float(r[a][2]), __uint_as_float(r[a][3])));
+              db[a] = fadd2(db[a], make_float2(__uint_as_float(r[a][6]), __uint_as_float(r[a][7])));
             }
 #pragma unroll
             for (int u = 0; u < KR; ++u) {
-              // h half-tile: [robot][channel][64-byte row], SWIZZLE_64B: 16-byte chunk index ^ ((row >> 1) & 3)
-              const uint4 h0 = *reinterpret_cast<const uint4*>(hs + u * (CT * 64) + ci * 64 + ((pl ^ ((ci >> 1) & 3)) << 4));
-              const uint32_t hw4[4] = {h0.x, h0.y, h0.z, h0.w};
-              float2 hv[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) hv[i] = make_float2(__uint_as_float(hw4[i] << 16), __uint_as_float(hw4[i] & 0xffff0000u));
+              // h half-tile: [robot][channel][64-byte row]; this thread's two pixel pairs of the pass
+              const uint32_t h0 = *reinterpret_cast<const uint32_t*>(hs + u * (CT * 64) + (((2 * j) ^ hsw) << 4));
+              const uint32_t h1 = *reinterpret_cast<const uint32_t*>(hs + u * (CT * 64) + (((2 * j + 1) ^ hsw) << 4));
+              const float2 hv0 = make_float2(__uint_as_float(h0 << 16), __uint_as_float(h0 & 0xffff0000u));
+              const float2 hv1 = make_float2(__uint_as_float(h1 << 16), __uint_as_float(h1 & 0xffff0000u));
 #pragma unroll
               for (int a = 0; a < KR; ++a) {
                 if (a == u) continue;
                 float2 acc = dg[edge_id(KR, u, a)];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  acc = ffma2(hv[i], make_float2(__uint_as_float(r[a][2 * i]), __uint_as_float(r[a][2 * i + 1])), acc);
+                acc = ffma2(hv0, make_float2(__uint_as_float(r[a][2]), __uint_as_float(r[a][3])), acc);
+                acc = ffma2(hv1, make_float2(__uint_as_float(r[a][6]), __uint_as_float(r[a][7])), acc);
                 dg[edge_id(KR, u, a)] = acc;
               }
             }
@@ -585,37 +612,53 @@ k_dx_film_bwd_res(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         if (++xb == 2) { xb = 0; xphase ^= 1; }
         if (++tb == NBUF) { tb = 0; tphase ^= 1; }
       }
-      // ---- both halves done: the two warps of a quadrant each hold the sums over their 2 x 16 pixels
-      if (hw == 1 && is_agg) {
+      // ---- both halves done: the four threads of a channel hold the sums over their 16 pixels each
 #pragma unroll
-        for (int e = 0; e < NE; ++e) xs[e] = dg[e].x + dg[e].y;
-#pragma unroll
-        for (int a = 0; a < KR; ++a) xs[NE + a] = db[a];
+      for (int e = 0; e < NE; ++e) {
+        float v = dg[e].x + dg[e].y;
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        dg[e].x = v;
       }
-      named_bar_sync(1 + q, 64);
-      if (hw == 0 && is_agg) {
+#pragma unroll
+      for (int a = 0; a < KR; ++a) {
+        float v = db[a].x + db[a].y;
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        db[a].x = v;
+      }
+      {
         __nv_bfloat16* dzc = p.dz + (g * NE) * 2 * (int64_t)p.F + 2 * c;
+        float sg = 0.f, sb = 0.f;
 #pragma unroll
         for (int u = 0; u < KR; ++u) {
 #pragma unroll
           for (int a = 0; a < KR; ++a) {
             if (a == u) continue;
             const int e = edge_id(KR, u, a);
+            if ((e & 3) != pq) continue;                        // the channel's four threads share its edges
             const uint32_t zw = zs[e * CT + ci];
             const float gam = __uint_as_float(zw << 16), bet = __uint_as_float(zw & 0xffff0000u);
-            float dgm = (dg[e].x + dg[e].y + xs[e]) * wmean, dbt = (db[a] + xs[NE + a]) * wmean;
+            float dgm = dg[e].x * wmean, dbt = db[a].x * wmean;
             if (p.fuse_sig) { dgm *= gam * (1.f - gam); dbt *= bet * (1.f - bet); }
             *reinterpret_cast<uint32_t*>(dzc + (int64_t)e * 2 * p.F) = pack_bf16(dgm, dbt);
+            sg += dgm; sb += dbt;
           }
         }
+        if (p.db2) {
+          sg += __shfl_xor_sync(0xffffffffu, sg, 1); sg += __shfl_xor_sync(0xffffffffu, sg, 2);
+          sb += __shfl_xor_sync(0xffffffffu, sb, 1); sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+          if (pq == 0) { dbacc[2 * c] += sg; dbacc[2 * c + 1] += sb; }
+        }
       }
-      named_bar_sync(1 + q, 64);                                // hand-over slots and the gamma/beta rows have been read
+      __syncwarp();                                             // the gamma/beta rows have been read
       if (lane == 0) mbar_arrive(bar_zempty + 8 * zb);
       if (++zb == 2) { zb = 0; zphase ^= 1; }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (p.db2) for (int i = threadIdx.x; i < 2 * p.F; i += NTHR) atomicAdd(p.db2 + i, dbacc[i]);     // one atomic per cell per CTA
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -623,8 +666,8 @@ k_dx_film_bwd_res(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 }
 
 template <int KR>
-static int launch_res(const void* Wp, const void* dy, const void* h, const void* z, void* dh, void* dz, int64_t graphs, int64_t F, int64_t Fo,
-                      int fuse_sig, cudaStream_t st) {
+static int launch_res(const void* Wp, const void* dy, const void* h, const void* z, void* dh, void* dz, float* db2, int64_t graphs, int64_t F,
+                      int64_t Fo, int fuse_sig, cudaStream_t st) {
   using C = CfgR<KR>;
   const int64_t nodes = graphs * KR, edges = graphs * C::NE;
   CUtensorMap tw, tdy, th, tz;
@@ -648,31 +691,33 @@ static int launch_res(const void* Wp, const void* dy, const void* h, const void*
     const uint32_t b[2] = {2 * CT, (uint32_t)C::NE};
     int rc = make_map(&tz, z, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
   }
+  const size_t smem = C::SMEM + (db2 ? (size_t)(2 * F * 4 + 127) / 128 * 128 : 0);
+  if (smem > 227 * 1024) return RGNN_E_UNSUPPORTED;
   static DeviceOnce once;
   if (once.need()) {
-    cudaError_t e = cudaFuncSetAttribute(k_dx_film_bwd_res<KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_dx_film_bwd_res<KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_dx_film_bwd_res)");
     once.mark();
   }
   Params p = {};
   p.tiles = (int)(F / CT); p.graphs = graphs; p.F = (int)F; p.Fo = (int)Fo; p.kblocks = (int)(Fo / BK);
-  p.dh = static_cast<__nv_bfloat16*>(dh); p.dz = static_cast<__nv_bfloat16*>(dz); p.fuse_sig = fuse_sig;
+  p.dh = static_cast<__nv_bfloat16*>(dh); p.dz = static_cast<__nv_bfloat16*>(dz); p.db2 = db2; p.fuse_sig = fuse_sig;
   { const char* e = getenv("RGNN_DXF_DEBUG"); p.debug = e ? atoi(e) : 0; }
   const int64_t work = graphs * p.tiles;
   const int grid = (int)(work < num_sms() ? work : num_sms());
   if (grid < 1) return 0;
-  k_dx_film_bwd_res<KR><<<grid, NTHR, C::SMEM, st>>>(tw, tdy, th, tz, p);
+  k_dx_film_bwd_res<KR><<<grid, NTHR, smem, st>>>(tw, tdy, th, tz, p);
   RGNN_LAUNCH_CHECK("k_dx_film_bwd_res");
   return 0;
 }
 
 template <int KR>
-static int launch(const void* Wp, const void* dy, const void* h, const void* z, void* dh, void* dz, int64_t graphs, int64_t F, int64_t Fo,
-                  int fuse_sig, cudaStream_t st) {
+static int launch(const void* Wp, const void* dy, const void* h, const void* z, void* dh, void* dz, float* db2, int64_t graphs, int64_t F,
+                  int64_t Fo, int fuse_sig, cudaStream_t st) {
   using C = Cfg<KR>;
   static int want_res = -1;     // RGNN_DXF_RES=0: never use the weight-resident pixel-half variant
   if (want_res < 0) { const char* e = getenv("RGNN_DXF_RES"); want_res = (e && e[0] == '0') ? 0 : 1; }
-  if (want_res) return launch_res<KR>(Wp, dy, h, z, dh, dz, graphs, F, Fo, fuse_sig, st);
+  if (want_res || db2) return launch_res<KR>(Wp, dy, h, z, dh, dz, db2, graphs, F, Fo, fuse_sig, st);     // (the column sums live in the pixel-half variant only)
   const int64_t nodes = graphs * KR, edges = graphs * C::NE;
   static int want_cl = -1;      // RGNN_DXF_CLUSTER=1|2|4: CTAs sharing one multicast copy of the graph's dY (default 2)
   if (want_cl < 0) { const char* e = getenv("RGNN_DXF_CLUSTER"); want_cl = e ? atoi(e) : 2; }
@@ -721,8 +766,9 @@ using namespace rgnn;
 // that, for every channel tile t (64 channels) and j < 8, rows 128 t + 16 j + (0..7) are Wc[:, 64 t + 8 j + (0..7)]^T (direct half) and rows
 // 128 t + 16 j + 8 + (0..7) are Wc[:, F + 64 t + 8 j + (0..7)]^T (aggregated half).  dy [G K, Fo, 64], h [G K, F, 64], z [G K (K-1), 2F]
 // (gamma, beta interleaved), dh [G K, F, 64], dz [G K (K-1), 2F], all bf16; G complete `robots`-node graphs (2..6) in reference edge order.
+// dbias2 (nullable): fp32 [2F], the column sums of dz are ADDED to it (zero it first): db2 of the edge encoder without a pass over dz.
 extern "C" int rgnn_tc_conv_dx_film_bwd(const void* W_perm, const void* dy, const void* h, const void* z, int fuse_sigmoid_grad,
-                                        void* dh, void* dz, int64_t graphs, int64_t robots, int64_t F, int64_t Fo, void* stream) {
+                                        void* dh, void* dz, float* dbias2, int64_t graphs, int64_t robots, int64_t F, int64_t Fo, void* stream) {
   RGNN_REQUIRE(W_perm && dy && h && z && dh && dz && graphs >= 0 && F > 0 && Fo > 0, RGNN_E_ARG, "rgnn_tc_conv_dx_film_bwd: bad arguments");
   RGNN_REQUIRE(robots >= 2 && robots <= 6, RGNN_E_UNSUPPORTED, "rgnn_tc_conv_dx_film_bwd: 2..6 robots per graph");
   RGNN_REQUIRE(F % 64 == 0 && Fo % 64 == 0, RGNN_E_UNSUPPORTED, "rgnn_tc_conv_dx_film_bwd: F %% 64 and Fo %% 64 required");
@@ -733,10 +779,10 @@ extern "C" int rgnn_tc_conv_dx_film_bwd(const void* W_perm, const void* dy, cons
   if (graphs == 0) return 0;
   cudaStream_t st = as_stream(stream);
   switch (robots) {
-    case 2: return dxf::launch<2>(W_perm, dy, h, z, dh, dz, graphs, F, Fo, fuse_sigmoid_grad, st);
-    case 3: return dxf::launch<3>(W_perm, dy, h, z, dh, dz, graphs, F, Fo, fuse_sigmoid_grad, st);
-    case 4: return dxf::launch<4>(W_perm, dy, h, z, dh, dz, graphs, F, Fo, fuse_sigmoid_grad, st);
-    case 5: return dxf::launch<5>(W_perm, dy, h, z, dh, dz, graphs, F, Fo, fuse_sigmoid_grad, st);
-    default: return dxf::launch<6>(W_perm, dy, h, z, dh, dz, graphs, F, Fo, fuse_sigmoid_grad, st);
+    case 2: return dxf::launch<2>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
+    case 3: return dxf::launch<3>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
+    case 4: return dxf::launch<4>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
+    case 5: return dxf::launch<5>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
+    default: return dxf::launch<6>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
   }
 }

@@ -392,7 +392,7 @@ class EdgeMLPFn(torch.autograd.Function):
         return None, dw1, db1, dw2, db2, None
 
 
-def edge_mlp_param_grads(pose, w2, a1, dzp, w2t=None):
+def edge_mlp_param_grads(pose, w2, a1, dzp, w2t=None, db2=None):
     """Parameter gradients of the edge encoder from dzp = dL/d(pre-sigmoid) [E, 2F] (autograd of models.py:146-151).
     w2t: the transposed bf16 weight (or its split planes) the forward's cast already produced."""
     e, hid = a1.shape
@@ -430,8 +430,9 @@ def edge_mlp_param_grads(pose, w2, a1, dzp, w2t=None):
         split = _splits_mn(f2, hid, max(1, (e + 63) // 64))
         partial = torch.empty((split, f2, hid), **f32) if split > 1 else None
         _gemm(dzp, (0, 0, 1, f2), a1, (0, 0, hid, 1), dw2, (0, hid, 1), f2, hid, e, split=split, partial=partial, tag="mlp2_dw")
-    db2 = torch.empty((f2,), **f32)
-    check(lib().rgnn_reduce_sum(dtype_code(dzp), ptr(dzp), e, f2, f2, 1, 1, 1, ptr(db2), stream()), "rgnn_reduce_sum")
+    if db2 is None:       # (the fused dX + FiLM-backward kernel hands the column sums over already)
+        db2 = torch.empty((f2,), **f32)
+        check(lib().rgnn_reduce_sum(dtype_code(dzp), ptr(dzp), e, f2, f2, 1, 1, 1, ptr(db2), stream()), "rgnn_reduce_sum")
     dw1, db1 = torch.empty((hid, 9), **f32), torch.empty((hid,), **f32)
     check(lib().rgnn_edge_mlp1_bwd(dtype_code(da1), ptr(pose), ptr(da1), ptr(dw1), ptr(db1), e, hid, stream()), "rgnn_edge_mlp1_bwd")
     return dw1, db1, dw2, db2
@@ -666,10 +667,12 @@ class GNNLayerFn(torch.autograd.Function):
         if getattr(ctx, "fused_bwd", False) and (need[0] or need_edge):
             f, fo = h.shape[1], wc2.shape[0]
             dh, dzp = torch.empty_like(h), torch.empty_like(z)
+            # db2 (bias gradient of the edge encoder's Linear(F,2F)) = column sums of dz: accumulated inside the kernel
+            db2 = torch.zeros((2 * f,), dtype=torch.float32, device=dy.device) if (need_edge and f <= 2048) else None
             nbytes = 2.0 * (ix.N * 64 * (2 * f + fo) + 2 * ix.E * 2 * f)
             with torch.cuda.device(dy.device), _lib.timed("dx_film_bwd", 2.0 * fo * 2 * f * ix.N * 64, nbytes):
-                check(lib().rgnn_tc_conv_dx_film_bwd(ptr(ctx.wtp), ptr(dy), ptr(h), ptr(z), 1, ptr(dh), ptr(dzp), ix.G, ix.complete_k, f, fo,
-                                                     stream()), "rgnn_tc_conv_dx_film_bwd")
+                check(lib().rgnn_tc_conv_dx_film_bwd(ptr(ctx.wtp), ptr(dy), ptr(h), ptr(z), 1, ptr(dh), ptr(dzp), ptr(db2), ix.G, ix.complete_k,
+                                                     f, fo, stream()), "rgnn_tc_conv_dx_film_bwd")
             _, _, dwc, dbc = _compress_backward(dy, h, gh, wc2, ctx.tc, False, False, need[6], need[7], planes=planes, wt=ctx.wt)
         else:
             dh_direct, dgh, dwc, dbc = _compress_backward(dy, h, gh, wc2, ctx.tc, need[0], need[0] or need_edge, need[6], need[7],
@@ -680,7 +683,7 @@ class GNNLayerFn(torch.autograd.Function):
         with torch.cuda.device(dy.device):
             if need[0] or need_edge:
                 if need_edge:
-                    dw1, db1, dw2, db2 = edge_mlp_param_grads(pose, w2f, a1, dzp, w2t=ctx.w2t)
+                    dw1, db1, dw2, db2 = edge_mlp_param_grads(pose, w2f, a1, dzp, w2t=ctx.w2t, db2=db2)
         return (dh if need[0] else None, None, dw1, db1, dw2, db2,
                 dwc.reshape(ctx.wshape) if dwc is not None else None, dbc, None)
 

@@ -163,7 +163,8 @@ def test_csr_guards(R):
 
 
 # ------------------------------------------------------------------------------------------ round-2 kernels
-@pytest.mark.parametrize("g_,k,f,fo", [(3, 5, 64, 64), (7, 5, 192, 128), (2, 2, 128, 64), (5, 6, 64, 192), (149, 3, 64, 64)])
+@pytest.mark.parametrize("g_,k,f,fo", [(3, 5, 64, 64), (7, 5, 192, 128), (2, 2, 128, 64), (5, 6, 64, 192), (149, 3, 64, 64),
+                                          (75, 5, 128, 128), (9, 4, 256, 64), (5, 6, 128, 192), (151, 3, 128, 64)])
 @pytest.mark.parametrize("res", ["1", "0"])
 def test_fused_dx_film_backward_guards(R, g_, k, f, fo, res, monkeypatch):
     """rgnn_tc_conv_dx_film_bwd (both variants): dh / dz are written completely and nothing else, incl. graph counts that are not a
@@ -183,7 +184,9 @@ def test_fused_dx_film_backward_guards(R, g_, k, f, fo, res, monkeypatch):
         wt = bf(2 * f, fo, seed=4, scale=0.05)
         wtp = wt.index_select(0, R.functional._dx_film_perm(f, wt.device))
         dh, dz = Guarded((n, f, 64), torch.bfloat16, 777.0), Guarded((e, 2 * f), torch.bfloat16, 777.0)
-        L.check(L.lib().rgnn_tc_conv_dx_film_bwd(L.ptr(wtp), L.ptr(dy), L.ptr(h), L.ptr(z), 1, L.ptr(dh.view), L.ptr(dz.view), g_, k, f, fo, L.stream()), "dxf")
+        db2 = Guarded((2 * f,), torch.float32, 0.0)
+        use_db2 = os.environ.get('RGNN_DXF_RES', '1') != '0'        # the column sums exist in the pixel-half variant only
+        L.check(L.lib().rgnn_tc_conv_dx_film_bwd(L.ptr(wtp), L.ptr(dy), L.ptr(h), L.ptr(z), 1, L.ptr(dh.view), L.ptr(dz.view), L.ptr(db2.view) if use_db2 else None, g_, k, f, fo, L.stream()), "dxf")
         dh.check("dx_film_bwd dh"); dz.check("dx_film_bwd dz")
         # values against the unfused formulas in fp32
         dcat = torch.einsum("ko,vop->vkp", wt.float(), dy.float())
@@ -201,6 +204,10 @@ def test_fused_dx_film_backward_guards(R, g_, k, f, fo, res, monkeypatch):
         got = dz.view.float().view(g_, k * (k - 1), f, 2)
         assert float((got[..., 0] - dgam).abs().max()) <= 2e-2 * float(dgam.abs().max())
         assert float((got[..., 1] - dbet).abs().max()) <= 2e-2 * float(dbet.abs().max())
+        ref_db2 = torch.stack((dgam.sum((0, 1)), dbet.sum((0, 1))), -1).reshape(-1)
+        if use_db2:
+            assert float((db2.view - ref_db2).abs().max()) <= 1e-3 * float(ref_db2.abs().max())
+        assert bool((db2.buf[:4096] == 0).all()) and bool((db2.buf[4096 + 2 * f:] == 0).all())
         print("ok")
     """)
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, RGNN_DXF_RES=res), capture_output=True, text=True, timeout=300)
