@@ -130,7 +130,8 @@ def check(rc, what):
 
 
 def ptr(t):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    # a plain int converts to the c_void_p parameter by itself; building the ctypes object first costs as much as the call
+    return None if t is None else t.data_ptr()
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
@@ -143,6 +144,25 @@ def stream():
     if _raw_stream is not None and _cur_device is not None:
         return ctypes.c_void_p(_raw_stream(_cur_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class on_device:
+    """`with on_device(t.device):` - torch.cuda.device() without its cost when the device is already current (the usual case:
+    one process per GPU).  The launch-bound script batch enters this a dozen times per step."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index
+
+    def __enter__(self):
+        self.prev = _cur_device() if _cur_device is not None else torch.cuda.current_device()
+        if self.idx is not None and self.idx != self.prev:
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.idx is not None and self.idx != self.prev:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def dtype_code(t):

@@ -112,7 +112,7 @@ class AggregateFn(torch.autograd.Function):
         if x.shape[0] != ix.N:
             raise ValueError(f"feature rows ({x.shape[0]}) != graph nodes ({ix.N})")
         out = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             _aggregate(ix, x, z, ctx.use_beta, nbr_scale, _POST[post], dst_scale, None, out, None, False)
         ctx.g, ctx.post = g, post
         ctx.save_for_backward(x, z, nbr_scale, dst_scale)
@@ -124,7 +124,7 @@ class AggregateFn(torch.autograd.Function):
         ix = ctx.g.index()
         dout = dout.contiguous()
         dx = dz = None
-        with torch.cuda.device(dout.device):
+        with _lib.on_device(dout.device):
             if z is not None and ctx.use_beta and ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:
                 dx, dz = _film_backward(ix, x, dout, z, None, False)
                 return dx, dz, None, None, None, None, None
@@ -160,7 +160,7 @@ class FilmMeanCatFn(torch.autograd.Function):
         if h.shape[0] != ix.N:
             raise ValueError(f"feature rows ({h.shape[0]}) != graph nodes ({ix.N})")
         out = torch.empty((h.shape[0], 2 * f) + tuple(h.shape[2:]), dtype=h.dtype, device=h.device)
-        with torch.cuda.device(h.device):
+        with _lib.on_device(h.device):
             _aggregate(ix, h, z, True, None, _lib.POST_MEAN, None, None, out.view(-1)[f * p:], out, False,
                        ldout=2 * f * p, shape=(f, p))
         ctx.g = g
@@ -175,7 +175,7 @@ class FilmMeanCatFn(torch.autograd.Function):
         f, p = _row_shape(h)
         dagg = dout.view(-1)[f * p:]          # second channel half, node stride 2FP
         dh = dz = None
-        with torch.cuda.device(dout.device):
+        with _lib.on_device(dout.device):
             if z is not None and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
                 dh, dz = _film_backward(ix, h, dagg, z, dout, False, ldd=2 * f * p, ldadd=2 * f * p, dh=torch.empty_like(h))
             elif ctx.needs_input_grad[0]:
@@ -350,7 +350,7 @@ def _edge_mlp_forward(pose, w1, b1, w2, b2, out_dtype):
     w2t = None                    # the K-major operand of dA1 = dZ . W2, produced by the same cast launch as the forward operand
     a1 = torch.empty((e, hid), dtype=out_dtype, device=pose.device)
     z = torch.empty((e, f2), dtype=out_dtype, device=pose.device)
-    with torch.cuda.device(pose.device):
+    with _lib.on_device(pose.device):
         check(lib().rgnn_edge_mlp1_fwd(dtype_code(a1), ptr(pose), ptr(w1), ptr(b1), ptr(a1), e, hid, stream()), "rgnn_edge_mlp1_fwd")
         if _lib.USE_TC and out_dtype == torch.bfloat16 and hid % 64 == 0 and f2 % 128 == 0 and e > 0:
             w2b, w2t = _cached_casts(w2_param, w2)
@@ -385,7 +385,7 @@ class EdgeMLPFn(torch.autograd.Function):
         pose, w2, a1, z = ctx.saved_tensors
         dz = dz.contiguous()
         dev = dz.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             dzp = torch.empty_like(z)
             check(lib().rgnn_sigmoid_grad(dtype_code(z), ptr(z), ptr(dz), ptr(dzp), z.numel(), stream()), "rgnn_sigmoid_grad")
             dw1, db1, dw2, db2 = edge_mlp_param_grads(pose, w2, a1, dzp, w2t=ctx.w2t)
@@ -458,7 +458,7 @@ def _compress_forward(h, gh, wc, bc):
     shape_ok = p == 64 and f % 64 == 0 and fo % 128 == 0 and n > 0
     tc = 1 if (_lib.USE_TC and h.dtype == torch.bfloat16 and shape_ok) else (3 if (_lib.USE_TC3 and h.dtype == torch.float32 and shape_ok) else 0)
     planes, wt = (None, None), None
-    with torch.cuda.device(h.device):
+    with _lib.on_device(h.device):
         if tc == 1:
             wb, wt = _cached_casts(wc, wc2)
             with _lib.timed("compress_fwd", 2.0 * fo * 2 * f * n * p):
@@ -491,7 +491,7 @@ def _compress_backward(dy, h, gh, wc2, tc, need_dh, need_dgh, need_dw, need_db, 
     tc_dw = tc == 1 and f % 256 == 0 and fo % 128 == 0
     tc3_dx = tc == 3 and f % 128 == 0 and fo % 64 == 0
     tc3_dw = tc == 3 and f % 256 == 0 and fo % 128 == 0 and planes[0] is not None
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         if (tc3_dx and (need_dh or need_dgh)) or (tc3_dw and need_dw):
             dy3 = _split3(dy)
         if tc3_dx and (need_dh or need_dgh):
@@ -633,7 +633,7 @@ class GNNLayerFn(torch.autograd.Function):
             bcf = bc.detach().float().contiguous()
             y = torch.empty((ix.N, fo) + tuple(h.shape[2:]), dtype=h.dtype, device=h.device)
             gh = torch.empty_like(h) if need_bwd else None
-            with torch.cuda.device(h.device):
+            with _lib.on_device(h.device):
                 wb, ctx.wt = _cached_casts(wc, wc2)
                 with _lib.timed("compress_film_fused_fwd", 2.0 * fo * 2 * f * ix.N * p):
                     check(lib().rgnn_tc_conv_film_fused(ptr(wb), ptr(h), ptr(z), ptr(bcf), ptr(y), ptr(gh), ix.G, ix.complete_k, f, fo,
@@ -644,7 +644,7 @@ class GNNLayerFn(torch.autograd.Function):
                 gh = h.new_empty(0)
         else:
             gh = torch.empty_like(h)
-            with torch.cuda.device(h.device):
+            with _lib.on_device(h.device):
                 _aggregate(ix, h, z, True, None, _lib.POST_MEAN, None, None, gh, None, False)
             y, wc2, ctx.tc, planes, ctx.wt = _compress_forward(h, gh, wc, bc)
         # backward plan: FiLM backward inside the dX GEMM's epilogue (dcat never written) when the shape allows
@@ -670,7 +670,7 @@ class GNNLayerFn(torch.autograd.Function):
             # db2 (bias gradient of the edge encoder's Linear(F,2F)) = column sums of dz: accumulated inside the kernel
             db2 = torch.zeros((2 * f,), dtype=torch.float32, device=dy.device) if (need_edge and f <= 2048) else None
             nbytes = 2.0 * (ix.N * 64 * (2 * f + fo) + 2 * ix.E * 2 * f)
-            with torch.cuda.device(dy.device), _lib.timed("dx_film_bwd", 2.0 * fo * 2 * f * ix.N * 64, nbytes):
+            with _lib.on_device(dy.device), _lib.timed("dx_film_bwd", 2.0 * fo * 2 * f * ix.N * 64, nbytes):
                 check(lib().rgnn_tc_conv_dx_film_bwd(ptr(ctx.wtp), ptr(dy), ptr(h), ptr(z), 1, ptr(dh), ptr(dzp), ptr(db2), ix.G, ix.complete_k,
                                                      f, fo, stream()), "rgnn_tc_conv_dx_film_bwd")
             _, _, dwc, dbc = _compress_backward(dy, h, gh, wc2, ctx.tc, False, False, need[6], need[7], planes=planes, wt=ctx.wt)
@@ -678,9 +678,9 @@ class GNNLayerFn(torch.autograd.Function):
             dh_direct, dgh, dwc, dbc = _compress_backward(dy, h, gh, wc2, ctx.tc, need[0], need[0] or need_edge, need[6], need[7],
                                                           planes=planes, wt=ctx.wt)
             if need[0] or need_edge:
-                with torch.cuda.device(dy.device):
+                with _lib.on_device(dy.device):
                     dh, dzp = _film_backward(ix, h, dgh, z, dh_direct, True)
-        with torch.cuda.device(dy.device):
+        with _lib.on_device(dy.device):
             if need[0] or need_edge:
                 if need_edge:
                     dw1, db1, dw2, db2 = edge_mlp_param_grads(pose, w2f, a1, dzp, w2t=ctx.w2t, db2=db2)
@@ -718,7 +718,7 @@ class LinearFn(torch.autograd.Function):
         if ident != 0.0:
             epi |= _lib.EPI_ADD_AUX
         ctx.tc = bool(_lib.USE_TC and x.dtype == torch.bfloat16 and din % 128 == 0 and dout % 128 == 0 and rows > 0)
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             # the identity mapping is folded into the bf16 weight operand only while beta (= alpha here) is large enough for
             # beta * w_ii to survive next to 1 - beta in a bf16 diagonal; deep GCNII layers (beta = log(lambda/l + 1) -> 0) keep the
             # residual as the fp32 epilogue term alpha * acc + ident * x, like the CUDA-core path and DGL do
@@ -750,7 +750,7 @@ class LinearFn(torch.autograd.Function):
         rows = x.numel() // din
         f32 = dict(dtype=torch.float32, device=dy.device)
         dx = dw = db = None
-        with torch.cuda.device(dy.device):
+        with _lib.on_device(dy.device):
             if ctx.needs_input_grad[0]:
                 dx = torch.empty_like(x)
                 epi = _lib.EPI_ADD_AUX if ctx.ident != 0.0 else 0
@@ -800,7 +800,7 @@ class AxpbyFn(torch.autograd.Function):
         if x.shape != y.shape or x.dtype != y.dtype:
             raise ValueError("axpby operands must match")
         out = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             check(lib().rgnn_axpby(dtype_code(x), float(a), ptr(x), float(b), ptr(y), ptr(out), x.numel(), stream()), "rgnn_axpby")
         ctx.a, ctx.b = float(a), float(b)
         return out
@@ -809,7 +809,7 @@ class AxpbyFn(torch.autograd.Function):
     def backward(ctx, d):
         d = d.contiguous()
         outs = []
-        with torch.cuda.device(d.device):
+        with _lib.on_device(d.device):
             for need, coef in ((ctx.needs_input_grad[0], ctx.a), (ctx.needs_input_grad[1], ctx.b)):
                 if not need:
                     outs.append(None)
@@ -849,7 +849,7 @@ class MeanMixFn(torch.autograd.Function):
         x, x0 = x.contiguous(), x0.contiguous()
         if x.shape != x0.shape or x.dtype != x0.dtype or x.shape[0] != ix.N:
             raise ValueError("mean_mix operands must be two [N, ...] tensors of one shape and dtype")
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             out = _mean_mix(ix, x, x0, sa, sb)
             if out is None:
                 agg = torch.empty_like(x)
@@ -864,7 +864,7 @@ class MeanMixFn(torch.autograd.Function):
         ix = ctx.g.index()
         d = d.contiguous()
         dx = dx0 = None
-        with torch.cuda.device(d.device):
+        with _lib.on_device(d.device):
             if ctx.needs_input_grad[0]:
                 dx = _mean_mix(ix, d, None, ctx.sa, 0.0)
                 if dx is None:
@@ -891,7 +891,7 @@ class BiasAddFn(torch.autograd.Function):
         x = x.contiguous()
         y = torch.empty_like(x)
         bf = bias.detach().float().contiguous()
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             check(lib().rgnn_bias_add(dtype_code(x), ptr(x), ptr(bf), ptr(y), x.numel() // bf.numel(), bf.numel(), stream()), "rgnn_bias_add")
         return y
 
@@ -902,7 +902,7 @@ class BiasAddFn(torch.autograd.Function):
         db = None
         if ctx.needs_input_grad[1]:
             db = torch.empty((cols,), dtype=torch.float32, device=dy.device)
-            with torch.cuda.device(dy.device):
+            with _lib.on_device(dy.device):
                 check(lib().rgnn_reduce_sum(dtype_code(dy), ptr(dy), dy.numel() // cols, cols, cols, 1, 1, 1, ptr(db), stream()),
                       "rgnn_reduce_sum")
         return dy, db
@@ -943,7 +943,7 @@ class LayoutCastFn(torch.autograd.Function):
             x = x.contiguous()
             out = torch.empty((n, f, hh, ww), dtype=dtype, device=x.device, memory_format=torch.channels_last)
             rows, cols = f, hh * ww
-        with torch.cuda.device(x.device), _lib.timed("seam", x.numel() * (x.element_size() + out.element_size())):
+        with _lib.on_device(x.device), _lib.timed("seam", x.numel() * (x.element_size() + out.element_size())):
             check(lib().rgnn_layout_cast(_DT[x.dtype], ptr(x), _DT[dtype], ptr(out), n, rows, cols, stream()), "rgnn_layout_cast")
         return out
 
@@ -959,7 +959,7 @@ class LayoutCastFn(torch.autograd.Function):
                 d = d.contiguous(memory_format=torch.channels_last)
             out = torch.empty((n, f, hh, ww), dtype=ctx.in_dtype, device=d.device)
             rows, cols = hh * ww, f
-        with torch.cuda.device(d.device):
+        with _lib.on_device(d.device):
             check(lib().rgnn_layout_cast(_DT[d.dtype], ptr(d), _DT[ctx.in_dtype], ptr(out), n, rows, cols, stream()), "rgnn_layout_cast")
         return out, None, None
 
