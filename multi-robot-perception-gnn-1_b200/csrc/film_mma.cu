@@ -37,13 +37,18 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// edge rows a thread keeps in flight: ALL of its rows at K = 64 (16 rows = 128 registers, free at that point of the kernels: the
+// accumulators are not live yet / any more).  One CTA per SM and 8 warps leave nothing else to hide a gather's latency behind:
+// ncu showed 54 % of all warp samples waiting on these loads with four rows in flight.
+__host__ __device__ constexpr int rows_in_flight(int per) { return per >= 16 ? 16 : (per >= 8 ? 8 : 4); }
+
 // Gamma_c[a][u] (bf16, zero diagonal) for the CTA's 8 channels from the edge-major z; optionally the beta row sums bs[c][a].
 // thread = (destination a, segment of sources u); the edge rows (32 B per edge for the 8 channels) are fetched FOUR AT A TIME before
 // any of them is scattered (a loop with one row in flight is latency-bound: 16 L2 round trips per CTA at K = 64), and the 8 beta
 // sums stay in registers and reach shared memory with ONE atomic per (thread, channel).
 template <bool WITH_BETA, int K>
 __device__ __forceinline__ void build_gamma(unsigned char* gs, float* bs, const __nv_bfloat16* __restrict__ zc0, int64_t zrow) {
-  constexpr int GP = gp_of(K), NSEG = 256 / K, PER = (K + NSEG - 1) / NSEG;
+  constexpr int GP = gp_of(K), NSEG = 256 / K, PER = (K + NSEG - 1) / NSEG, NB = rows_in_flight(PER);
   for (int i = threadIdx.x; i < CT * K; i += blockDim.x) {
     const int c = i / K, a = i - c * K;
     *reinterpret_cast<__nv_bfloat16*>(gs + (size_t)c * K * GP + a * GP + a * 2) = __float2bfloat16_rn(0.f);
@@ -72,11 +77,11 @@ __device__ __forceinline__ void build_gamma(unsigned char* gs, float* bs, const 
     for (int c = 0; c < CT; ++c) bsum[c] = 0.f;
     const int u0 = seg * PER;
 #pragma unroll
-    for (int b = 0; b < PER; b += 4) {
-      uint4 v[4][2];
-      bool ok[4];
+    for (int b = 0; b < PER; b += NB) {
+      uint4 v[NB][2];
+      bool ok[NB];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NB; ++j) {
         const int u = u0 + b + j;
         ok[j] = (b + j < PER) && u < K && u != a;
         if (ok[j]) {
@@ -86,7 +91,7 @@ __device__ __forceinline__ void build_gamma(unsigned char* gs, float* bs, const 
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NB; ++j) {
         if (!ok[j]) continue;
         const int u = u0 + b + j;
         const uint32_t w[8] = {v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w, v[j][1].x, v[j][1].y, v[j][1].z, v[j][1].w};
@@ -248,21 +253,19 @@ __global__ void __launch_bounds__(256) k_film_bwd_mma(const __nv_bfloat16* __res
     }
 #pragma unroll
     for (int mt = 0; mt < KT; ++mt) {
+      const int64_t col = (int64_t)(c0 + c) * P + (lane & 3) * 2;
 #pragma unroll
       for (int hrow = 0; hrow < 2; ++hrow) {
         const int u = mt * 16 + (lane >> 2) + hrow * 8;
-        const int64_t col = (int64_t)(c0 + c) * P + (lane & 3) * 2;
         __nv_bfloat16* o = dh + (n0 + u) * lddh + col;
         const __nv_bfloat16* ad = addend ? addend + (n0 + u) * ldadd + col : nullptr;
+        float2 t[8];                                                   // the row's 8 addend pairs are asked for together
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          float v0 = acc[mt][nt][2 * hrow] * w, v1 = acc[mt][nt][2 * hrow + 1] * w;
-          if (ad) {
-            const float2 t = ldg_pair<__nv_bfloat16>(ad + nt * 8);
-            v0 += t.x; v1 += t.y;
-          }
-          *reinterpret_cast<__nv_bfloat162*>(o + nt * 8) = __floats2bfloat162_rn(v0, v1);
-        }
+        for (int nt = 0; nt < 8; ++nt) t[nt] = ad ? ldg_pair<__nv_bfloat16>(ad + nt * 8) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          *reinterpret_cast<__nv_bfloat162*>(o + nt * 8) =
+              __floats2bfloat162_rn(acc[mt][nt][2 * hrow] * w + t[nt].x, acc[mt][nt][2 * hrow + 1] * w + t[nt].y);
       }
     }
   }
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(256) k_film_bwd_mma(const __nv_bfloat16* __res
   {
     __nv_bfloat16* dz0 = dz + e0 * 2 * (int64_t)F + 2 * c0;
     const int64_t zrow = 2 * (int64_t)F;
-    constexpr int NSEG = 256 / K, PER = (K + NSEG - 1) / NSEG;
+    constexpr int NSEG = 256 / K, PER = (K + NSEG - 1) / NSEG, NB = rows_in_flight(PER);
     if constexpr (PER < 4) {
       constexpr int NE = K * (K - 1);
       for (int e = threadIdx.x; e < NE; e += blockDim.x) {
@@ -357,11 +360,11 @@ __global__ void __launch_bounds__(256) k_film_bwd_mma(const __nv_bfloat16* __res
 #pragma unroll
       for (int cc = 0; cc < CT; ++cc) dbw[cc] = dbs[cc * K + a] * w;
 #pragma unroll
-      for (int b = 0; b < PER; b += 4) {          // four edge rows in flight, as in build_gamma
-        uint4 v[4][2];
-        bool ok[4];
+      for (int b = 0; b < PER; b += NB) {          // as in build_gamma
+        uint4 v[NB][2];
+        bool ok[NB];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NB; ++j) {
           const int u = u0 + b + j;
           ok[j] = (b + j < PER) && u < K && u != a;
           if (ok[j] && fuse_sig) {
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(256) k_film_bwd_mma(const __nv_bfloat16* __res
           }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NB; ++j) {
           if (!ok[j]) continue;
           const int u = u0 + b + j;
           const int64_t e = edge_id(K, u, a);
