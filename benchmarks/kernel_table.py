@@ -1,3 +1,5 @@
+"""Reads a bench.py JSON line on stdin and prints value, ms/step, launches/step and the per-kernel table (top 3 by share):
+   python bench.py --robots 64 --graphs 128 --no-e2e --no-cpu-baseline --no-other-configs | python benchmarks/kernel_table.py"""
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print(round(d['value']), round(d['ms_per_step'],3), d['gpu_launches']/d['steps'])

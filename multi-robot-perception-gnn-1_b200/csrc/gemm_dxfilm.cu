@@ -83,6 +83,11 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
   }
 }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 // 16 lanes x 256 bits, twice (16 columns): registers {row t/4: col 2(t%4), +1; row t/4 + 8: same cols} per 8-column block - the
 // mma.sync accumulator fragment layout
 __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
@@ -541,17 +546,17 @@ k_dx_film_bwd_res(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #pragma unroll
       for (int a = 0; a < KR; ++a) db[a] = make_float2(0.f, 0.f);
       __nv_bfloat16* dh_row = p.dh + ((g * KR) * (int64_t)p.F + c) * 64 + 2 * pq;
-      const uint32_t* zs = reinterpret_cast<const uint32_t*>(smem + C::Z_OFF + zb * C::Z_BYTES);
+      const uint32_t zs = base + C::Z_OFF + zb * C::Z_BYTES + ci * 4;
       mbar_wait(bar_zfull + 8 * zb, zphase);
 #pragma unroll
-      for (int e = 0; e < NE; ++e) gw[e] = __uint_as_float(zs[e * CT + ci] << 16) * wmean;
+      for (int e = 0; e < NE; ++e) gw[e] = __uint_as_float(lds_u32(zs + e * (CT * 4)) << 16) * wmean;
 #pragma unroll 1
       for (int ph = 0; ph < 2; ++ph) {
         mbar_wait(bar_xfull + 8 * xb, xphase);
         mbar_wait(bar_tfull + 8 * tb, tphase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + tb * C::NCOL + ((uint32_t)(q * 32 + lg * 16) << 16);
-        const unsigned char* hs = smem + C::H_OFF + xb * C::H_BYTES + ci * 64 + 4 * pq;
+        const uint32_t hs = base + C::H_OFF + xb * C::H_BYTES + ci * 64 + 4 * pq;      // (shared-window address: plain pointers compile to generic loads)
 #pragma unroll 1
         for (int j = 0; j < 2; ++j) {                           // 16 pixels of every robot per pass: 4 per thread
           // r[u]: {direct px, px+1, aggregated px, px+1} for the first 8-pixel block, then the same for the second
@@ -592,8 +597,8 @@ k_dx_film_bwd_res(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #pragma unroll
             for (int u = 0; u < KR; ++u) {
               // h half-tile: [robot][channel][64-byte row]; this thread's two pixel pairs of the pass
-              const uint32_t h0 = *reinterpret_cast<const uint32_t*>(hs + u * (CT * 64) + (((2 * j) ^ hsw) << 4));
-              const uint32_t h1 = *reinterpret_cast<const uint32_t*>(hs + u * (CT * 64) + (((2 * j + 1) ^ hsw) << 4));
+              const uint32_t h0 = lds_u32(hs + u * (CT * 64) + (((2 * j) ^ hsw) << 4));
+              const uint32_t h1 = lds_u32(hs + u * (CT * 64) + (((2 * j + 1) ^ hsw) << 4));
               const float2 hv0 = make_float2(__uint_as_float(h0 << 16), __uint_as_float(h0 & 0xffff0000u));
               const float2 hv1 = make_float2(__uint_as_float(h1 << 16), __uint_as_float(h1 & 0xffff0000u));
 #pragma unroll
@@ -637,7 +642,7 @@ k_dx_film_bwd_res(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             if (a == u) continue;
             const int e = edge_id(KR, u, a);
             if ((e & 3) != pq) continue;                        // the channel's four threads share its edges
-            const uint32_t zw = zs[e * CT + ci];
+            const uint32_t zw = lds_u32(zs + e * (CT * 4));
             const float gam = __uint_as_float(zw << 16), bet = __uint_as_float(zw & 0xffff0000u);
             float dgm = dg[e].x * wmean, dbt = db[a].x * wmean;
             if (p.fuse_sig) { dgm *= gam * (1.f - gam); dbt *= bet * (1.f - bet); }
