@@ -62,8 +62,9 @@ USE_FUSED = False  # FiLM aggregation fused into the compress GEMM's prologue (r
                    # with the aggregate stored for the backward, 1.74 vs 1.71 ms in eval), so it is opt-in.
 USE_FUSED_BWD = os.environ.get("RGNN_FUSED_BWD", "1") != "0"   # FiLM backward in the epilogue of the compress conv's dX GEMM (rgnn_tc_conv_dx_film_bwd): dcat never reaches HBM.
                        # bf16, P = 64, complete graphs of 2..6 robots; anything else runs dX GEMM + FiLM backward kernel.
-FUSED_BWD_MAX_F = int(os.environ.get("RGNN_FUSED_BWD_MAXF", "640"))   # widest layer that takes the fused backward: measured on B200 it wins at
-                       # F = 512 (10.74 vs 11.06 ms/step) and loses at F = 1280 / 2048, where the CTA-pair dX GEMM (1.5 PFLOP/s) dominates the pair
+FUSED_BWD_MAX_F = int(os.environ.get("RGNN_FUSED_BWD_MAXF", "896"))   # widest layer that takes the fused backward: measured on B200 it wins at
+                       # F = 512 (10.22 vs 11.06 ms/step) and F = 768 (20.07 vs 21.39 ms) and loses at F = 1280 (26.37 vs 25.42 ms) and F = 2048
+                       # (30.75 vs 28.55 ms), where the CTA-pair dX GEMM (1.5 PFLOP/s) dominates the pair
 USE_TC3 = True     # fp32 (parity mode) transforms as split-bf16 products on the tcgen05 path when the shape allows (rgnn_tc3_*); False:
                    # the CUDA-core FFMA GEMMs (rgnn_gemm)
 USE_TC = True      # bf16 transforms on the tcgen05 path when the shape allows (tests flip it to compare with rgnn_gemm)
