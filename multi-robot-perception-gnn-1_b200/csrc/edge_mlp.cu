@@ -191,14 +191,14 @@ __global__ void __launch_bounds__(256) k_mlp1_bwd_vec2(const float* __restrict__
 #pragma unroll
     for (int q = 0; q < VEC; ++q) red[threadIdx.x * VEC + q] = acc[q][j];
     __syncthreads();
-    if (rg == 0 && live) {
-#pragma unroll
-      for (int q = 0; q < VEC; ++q) {
-        float v = 0.f;
-        for (int g2 = 0; g2 < rgn; ++g2) v += red[(g2 * cv + c) * VEC + q];
-        const int f = fv * VEC + q;
-        if (j < 9) atomicAdd(dw1 + f * 9 + j, v); else atomicAdd(db1 + f, v);
-      }
+    // red[(g2 * cv + c) * VEC + q] = red[g2 * nout + o] with o = c * VEC + q: one thread per output o sums the row groups
+    // (consecutive threads, consecutive addresses), instead of the cv threads of row group 0 summing VEC outputs each
+    const int nout = cv * VEC;
+    for (int o = threadIdx.x; o < nout; o += blockDim.x) {
+      float v = 0.f;
+      for (int g2 = 0; g2 < rgn; ++g2) v += red[g2 * nout + o];
+      const int f = blockIdx.x * nout + o;
+      if (f < F) { if (j < 9) atomicAdd(dw1 + f * 9 + j, v); else atomicAdd(db1 + f, v); }
     }
   }
 }
@@ -255,7 +255,7 @@ extern "C" int rgnn_edge_mlp1_fwd(int dtype, const float* pose, const float* w1,
     const int64_t eb = (E + MLP1_EPB - 1) / MLP1_EPB;
     if (F % vec == 0 && (reinterpret_cast<uintptr_t>(a1) & 15u) == 0 && eb <= 65535) {
       const int fvn = (int)(F / vec);
-      int cv = 32;
+      int cv = 8;                                            // (bf16, 128 hidden features = 16 vectors: no idle half-warps)
       while (cv < fvn && cv < 256) cv <<= 1;                 // feature vectors per block (power of two), 256 / cv edge lanes
       dim3 grid((unsigned)((fvn + cv - 1) / cv), (unsigned)eb);
       if (dtype == RGNN_F32) k_mlp1_fwd_vec<float><<<grid, 256, 0, st>>>(pose, w1, b1, static_cast<float*>(a1), E, (int)F, cv);
@@ -285,7 +285,7 @@ extern "C" int rgnn_edge_mlp1_bwd(int dtype, const float* pose, const void* da1,
   const bool vec_ok = F % vec == 0 && (reinterpret_cast<uintptr_t>(da1) & 15u) == 0;
   if (vec_ok) {
     const int fvn = (int)(F / vec);
-    int cv = 32;
+    int cv = 8;                                            // (bf16, 128 hidden features = 16 vectors: no idle half-warps)
     while (cv < fvn && cv < 256) cv <<= 1;
     const int fbx = (fvn + cv - 1) / cv;
     int64_t chunks2 = (4 * num_sms() + fbx - 1) / fbx;          // ~4 blocks of 256 threads per SM
