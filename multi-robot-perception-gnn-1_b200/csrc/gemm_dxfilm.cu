@@ -5,21 +5,23 @@
 //   dh[u]  = dcat[u, :F] + (1/(K-1)) sum_{a != u} gamma_{u->a} * dcat[a, F:]          (autograd of edge_udf / node_udf, models.py:207-211)
 //   dgamma_{u->a} = (1/(K-1)) sum_p h[u,:,p] * dcat[a, F:, p] ,  dbeta_{u->a} = (1/(K-1)) sum_p dcat[a, F:, p] ;  dz = d(gamma,beta) * sigmoid'
 //
-// One CTA owns (graph g, 64 channels c0..c0+63): its accumulator tile is 128 rows x (K robots x 64 pixels) fp32 in TMEM - the 64
-// "direct" rows Wc[:, c]^T and the 64 "aggregated" rows Wc[:, F + c]^T of the SAME channels, for ALL robots of the graph, which is
-// exactly the set of values the FiLM backward of those channels needs.  The weight operand is row-permuted on the host so that
-// inside every group of 16 rows the first 8 are direct and the last 8 the aggregated rows of the same 8 channels: a channel's
-// two rows then live in the same warp, 8 lanes apart (TMEM lane = accumulator row), and meet through one __shfl_xor.
+// One CTA owns (graph g, 64 channels c0..c0+63): accumulator rows = the 64 "direct" rows Wc[:, c]^T and the 64 "aggregated" rows
+// Wc[:, F + c]^T of the SAME channels, columns = ALL robots of the graph - exactly the values the FiLM backward of those channels
+// needs.  The weight operand is row-permuted on the host: inside every group of 16 rows the first 8 are direct and the last 8 the
+// aggregated rows of the same 8 channels, so that the 16-lane x 256-bit TMEM load hands one thread BOTH rows of a channel.
+// A tile is processed as two half-tiles of 32 pixels: accumulator = 128 rows x (K robots x 32 px) = 160 columns at K = 5, three of
+// them fit in TMEM, and the FiLM epilogue of half-tile i runs under the loads and MMAs of half-tiles i+1, i+2.
 //
-//   warp 0  TMA producer : 3-stage ring of {A 128 x 64 (permuted Wc^T, K-major), B K x [64 o x 64 px] (dY, NCHW = MN-major)},
-//                          plus once per tile the graph's h tile (K x [64 ch x 64 px]) and its gamma/beta rows
-//   warp 1  MMA issuer   : tcgen05.mma cta_group::1, M = 128, N = 64 K (as 256 + rest), fp32 accumulate in TMEM
+//   warp 0  TMA producer : ring of {A 128 x 64 (permuted Wc^T, K-major SWIZZLE_128B), B K x [64 o x 32 px] (dY, NCHW = MN-major,
+//                          64-byte rows, SWIZZLE_64B)}; per half-tile the graph's h rows (double-buffered), per tile its gamma/beta rows
+//   warp 1  MMA issuer   : tcgen05.mma cta_group::1, M = 128, N = 32 K, fp32 accumulate in TMEM
 //   warp 2  TMEM alloc
-//   warps 4-7 epilogue   : tcgen05.ld 16 pixels x K robots at a time; aggregated-row lanes form the gather sum_a gamma dAgg[a] and
-//                          the per-edge pixel dots (a thread owns a whole channel row: no cross-lane reduction), direct-row lanes
-//                          add it to their accumulator values and store dh (32-byte stores); dz leaves as (gamma, beta) pairs.
-// The accumulator is single-buffered (K x 64 columns of the 512): MMAs of tile i+1 start when the epilogue of tile i has read it.
+//   warps 4-11 epilogue  : two warps per TMEM lane quadrant split its channels; tcgen05.ld.16x256b, FFMA2 math on all lanes, 4-byte
+//                          dh stores, per-edge sums completed by a reduce-scatter over a channel's four threads, dz as (gamma, beta)
+//                          pairs with sigmoid', dz column sums (db2 of the edge encoder) in shared memory -> one atomic per cell
 // HBM traffic per layer: dY + h read, dh written (3 tensor passes) instead of dX (1 + 2) and the FiLM backward (3 + 1).
+// History, knock-out timings and the variants that were measured and removed (single 320-column accumulator with cluster multicast,
+// CTA pairs, weight tile in tensor memory, L2 prefetch): profiles/r02i_fused_bwd_ab.txt, DESIGN.md 4.1.
 #include "tc_common.cuh"
 #include "film_common.cuh"
 
@@ -40,27 +42,6 @@ struct Params {
   float* db2;           // optional fp32 [2 F]: column sums of dz (the bias gradient of the edge encoder's last Linear) are ADDED here
   int fuse_sig;
   int debug;            // RGNN_DXF_DEBUG (experiments): 1 = epilogue only drains TMEM, 2 = no per-edge dots, 4 = no dh part, 8 = MMA issuer skips the MMAs
-};
-
-template <int KR> struct Cfg {
-  static constexpr int NE = KR * (KR - 1);
-  static constexpr int NCOL = 64 * KR;
-  static constexpr int N1 = NCOL <= 256 ? NCOL : 256;
-  static constexpr int N2 = NCOL - N1;
-  static constexpr uint32_t A_BYTES = BM * BK * 2;            // 16 KB
-  static constexpr uint32_t B_BYTES = KR * BK * 128;          // K x 8 KB
-  static constexpr uint32_t STAGE = A_BYTES + B_BYTES;
-  static constexpr uint32_t H_BYTES = KR * CT * 128;          // K x 8 KB, SWIZZLE_128B
-  static constexpr uint32_t Z_BYTES = ((NE * CT * 4 + 1023) / 1024) * 1024;
-  static constexpr uint32_t X_BYTES = ((4 * 16 * (NE + KR) * 4 + 1023) / 1024) * 1024;   // partial (dgamma, dbeta) sums handed between the two warps of a quadrant
-  static constexpr int NST_FIT = (227 * 1024 - 1024 - 512 - (int)H_BYTES - (int)Z_BYTES - (int)X_BYTES) / (int)STAGE;
-  static constexpr int NST = NST_FIT > 4 ? 4 : NST_FIT;
-  static_assert(NST >= 2, "shared memory budget");
-  static constexpr uint32_t H_OFF = NST * STAGE;
-  static constexpr uint32_t Z_OFF = H_OFF + H_BYTES;
-  static constexpr uint32_t X_OFF = Z_OFF + Z_BYTES;
-  static constexpr uint32_t BAR_OFF = X_OFF + X_BYTES;
-  static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 512;
 };
 
 // mbarrier wait for the single-lane producer / issuer loops: back off between polls.  These warps share their SM sub-partitions
@@ -96,302 +77,8 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)
                : "r"(taddr)
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-}
-
-// CL: CTAs per cluster.  The CL CTAs of a cluster take CL consecutive channel tiles of the SAME graph, so they all need the same B
-// operand (the graph's dY): each loads 1/CL of its robots and TMA-multicasts them into every CTA of the cluster.  L2 -> SM operand
-// traffic per tile drops from A + B to A + B / CL (the kernel re-reads dY once per channel tile: 8 times at F = 512 - with one
-// CTA per tile that alone is 16 GB per launch, ~0.9 ms of L2 bandwidth).
-template <int KR, int CL>
-__global__ void __launch_bounds__(NTHR, 1)
-k_dx_film_bwd(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmDYs,
-              const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmZ, const Params p) {
-  using C = Cfg<KR>;
-  constexpr int NST = C::NST, NE = C::NE;
-  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t base = smem_u32(smem);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NST);
-  const uint32_t bar_tfull = smem_u32(bars + 2 * NST), bar_tempty = smem_u32(bars + 2 * NST + 1);
-  const uint32_t bar_xfull = smem_u32(bars + 2 * NST + 2), bar_xempty = smem_u32(bars + 2 * NST + 3);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 4);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDY) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDYs) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmH) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmZ) : "memory");
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, CL); }   // a stage is free once EVERY CTA's MMAs on it retired
-    mbar_init(bar_tfull, 1);
-    mbar_init(bar_tempty, 8);
-    mbar_init(bar_xfull, 1);
-    mbar_init(bar_xempty, 8);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (CL > 1) cluster_sync_all();       // the peers' barriers exist before any multicast targets them
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int tiles_cl = p.tiles / CL;                            // tile groups per graph (host guarantees tiles % CL == 0)
-  const int64_t work_total = p.graphs * tiles_cl;
-  const int64_t w_first = blockIdx.x / CL, w_step = gridDim.x / CL;
-
-  if (warp == 0) {
-    // ================================ TMA producer ================================
-    if (lane == 0) {
-      // this CTA's share of the graph's robots (B operand): [n_lo, n_hi); the small map has a box of KR / CL robots, the other one more
-      constexpr int NLO = KR / CL;
-      const int n_lo = crank * KR / CL, n_hi = (crank + 1) * KR / CL;
-      int stage = 0; uint32_t phase = 0, xphase = 0;
-      for (int64_t w = w_first; w < work_total; w += w_step) {
-        const int t = (int)(w % tiles_cl) * CL + crank;
-        const int64_t g = w / tiles_cl;
-        // the tile's h / gamma-beta rows go into a single buffer that the previous tile's epilogue must have left; ask for them
-        // only after the first ring-full of operand blocks is on its way, so the operand prefetch overlaps that epilogue
-        const int aux_at = p.kblocks < NST ? p.kblocks - 1 : NST - 1;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          const uint32_t fb = bar_full + 8 * stage;
-          const uint32_t s0 = base + stage * C::STAGE;
-          mbar_expect_tx(fb, C::STAGE);
-          tma_2d(s0, &tmW, fb, kb * BK, t * BM);                                  // permuted Wc^T rows of this channel tile
-          if constexpr (CL == 1) {
-            tma_3d(s0 + C::A_BYTES, &tmDY, fb, 0, kb * BK, (int)(g * KR));        // dY of the graph's robots, 64 output channels
-          } else if (n_hi > n_lo) {
-            tma_3d_mc(s0 + C::A_BYTES + n_lo * (BK * 128), (n_hi - n_lo) == NLO ? &tmDYs : &tmDY, fb, 0, kb * BK, (int)(g * KR) + n_lo, MC_MASK);
-          }
-          if (++stage == NST) { stage = 0; phase ^= 1; }
-          if (kb == aux_at) {
-            mbar_wait(bar_xempty, xphase ^ 1);
-            xphase ^= 1;
-            mbar_expect_tx(bar_xfull, C::H_BYTES + NE * CT * 4);
-            tma_3d(base + C::H_OFF, &tmH, bar_xfull, 0, t * CT, (int)(g * KR));   // h[g's robots, c0..c0+63, :]
-            tma_2d(base + C::Z_OFF, &tmZ, bar_xfull, 2 * t * CT, (int)(g * NE));  // (gamma, beta) pairs of its edges, same channels
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    if (lane == 0) {
-      const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(C::N1 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)((C::N2 > 0 ? C::N2 : 64) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int stage = 0; uint32_t phase = 0, tphase = 0;
-      for (int64_t w = w_first; w < work_total; w += w_step) {
-        mbar_wait(bar_tempty, tphase ^ 1);               // the single accumulator has been drained
-        tphase ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = base + stage * C::STAGE, sb = sa + C::A_BYTES;
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = make_desc(sa + k * 32, 0, 1024);
-            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            if (p.debug & 8) continue;
-            umma(tmem_base, da, make_desc(sb + k * 2048, BK * 128, 1024), idesc1, acc);
-            if (C::N2 > 0) umma(tmem_base + C::N1, da, make_desc(sb + (C::N1 / 64) * (BK * 128) + k * 2048, BK * 128, 1024), idesc2, acc);
-          }
-          if (CL > 1) umma_commit_mc(bar_empty + 8 * stage, MC_MASK);   // every CTA's producer multicasts into this stage of every CTA
-          else umma_commit(bar_empty + 8 * stage);
-          if (kb == p.kblocks - 1) umma_commit(bar_tfull);
-          if (++stage == NST) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    // ================================ epilogue: FiLM backward ================================
-    const int q = warp & 3;                                     // TMEM lane quadrant
-    const int half = (warp - 4) >> 2;                           // pixel half this warp owns: [32 half, 32 half + 32)
-    const bool is_agg = ((lane >> 3) & 1) != 0;
-    const int ci = 8 * (2 * q + (lane >> 4)) + (lane & 7);      // channel inside the tile (see the row permutation, host side)
-    const float wmean = 1.0f / (KR - 1);
-    const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16);
-    const unsigned char* hs = smem + C::H_OFF;
-    const uint32_t* zs = reinterpret_cast<const uint32_t*>(smem + C::Z_OFF);
-    float* xs = reinterpret_cast<float*>(smem + C::X_OFF) + (q * 16 + (lane >> 4) * 8 + (lane & 7)) * (NE + KR);   // this channel's hand-over slot
-    uint32_t tphase = 0, xphase = 0;
-    for (int64_t w = w_first; w < work_total; w += w_step) {
-      const int t = (int)(w % tiles_cl) * CL + crank;
-      const int64_t g = w / tiles_cl;
-      const int c = t * CT + ci;
-      mbar_wait(bar_xfull, xphase);
-      xphase ^= 1;
-      mbar_wait(bar_tfull, tphase);
-      tphase ^= 1;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // gamma * 1/(K-1) of this channel's edges (aggregated-row lanes use them; direct-row lanes carry them along unused)
-      float gw[NE];
-#pragma unroll
-      for (int e = 0; e < NE; ++e) gw[e] = __uint_as_float(zs[e * CT + ci] << 16) * wmean;
-      float2 dg[NE];
-      float db[KR];
-#pragma unroll
-      for (int e = 0; e < NE; ++e) dg[e] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int a = 0; a < KR; ++a) db[a] = 0.f;
-      __nv_bfloat16* dh_row = p.dh + ((g * KR) * (int64_t)p.F + c) * 64;
-#pragma unroll 1
-      for (int j = 0; j < 4; ++j) {                             // 8 pixels of every robot per pass
-        const int pc = half * 4 + j;                            // 16-byte pixel chunk 0..7
-        uint32_t r[KR][8];
-#pragma unroll
-        for (int u = 0; u < KR; ++u) tmem_ld8(tacc + u * 64 + pc * 8, r[u]);
-        tmem_ld_wait();
-        if (j == 3) {                                           // this warp has read its part of the accumulator
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty);
-        }
-        if (p.debug & 1) continue;
-        // ---- dh: aggregated-row lanes form sum_a gamma_{u->a}/(K-1) * dAgg[a]; the direct-row lane of the same channel (8 lanes
-        //      down) adds its own accumulator values and stores the 8 pixels (16 bytes; the chunk next to it follows in the next pass)
-        if (!(p.debug & 4)) {
-#pragma unroll
-          for (int u = 0; u < KR; ++u) {
-            float2 s[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) s[i] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int a = 0; a < KR; ++a) {
-              if (a == u) continue;
-              const float gm = gw[edge_id(KR, u, a)];
-              const float2 g2 = make_float2(gm, gm);
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                s[i] = ffma2(g2, make_float2(__uint_as_float(r[a][2 * i]), __uint_as_float(r[a][2 * i + 1])), s[i]);
-            }
-            uint32_t o[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float sx = __shfl_xor_sync(0xffffffffu, s[i].x, 8), sy = __shfl_xor_sync(0xffffffffu, s[i].y, 8);
-              o[i] = pack_bf16(__uint_as_float(r[u][2 * i]) + sx, __uint_as_float(r[u][2 * i + 1]) + sy);
-            }
-            if (!is_agg) *reinterpret_cast<uint4*>(dh_row + (int64_t)u * p.F * 64 + pc * 8) = make_uint4(o[0], o[1], o[2], o[3]);
-          }
-        }
-        // ---- per-edge pixel dots (aggregated-row lanes): dgamma_{u->a} += h[u] . dAgg[a],  dbeta_a += sum dAgg[a]
-        if (is_agg && !(p.debug & 2)) {
-#pragma unroll
-          for (int a = 0; a < KR; ++a) {
-            float2 t2 = make_float2(__uint_as_float(r[a][0]), __uint_as_float(r[a][1]));
-#pragma unroll
-            for (int i = 1; i < 4; ++i) t2 = fadd2(t2, make_float2(__uint_as_float(r[a][2 * i]), __uint_as_float(r[a][2 * i + 1])));
-            db[a] += t2.x + t2.y;
-          }
-#pragma unroll
-          for (int u = 0; u < KR; ++u) {
-            const uint4 h0 = *reinterpret_cast<const uint4*>(hs + u * (CT * 128) + ci * 128 + ((pc ^ (ci & 7)) << 4));
-            const uint32_t hw[4] = {h0.x, h0.y, h0.z, h0.w};
-            float2 hv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) hv[i] = make_float2(__uint_as_float(hw[i] << 16), __uint_as_float(hw[i] & 0xffff0000u));
-#pragma unroll
-            for (int a = 0; a < KR; ++a) {
-              if (a == u) continue;
-              float2 acc = dg[edge_id(KR, u, a)];
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                acc = ffma2(hv[i], make_float2(__uint_as_float(r[a][2 * i]), __uint_as_float(r[a][2 * i + 1])), acc);
-              dg[edge_id(KR, u, a)] = acc;
-            }
-          }
-        }
-      }
-      // ---- the two warps of a quadrant each hold the sums over their 32 pixels: the upper-half warp hands its sums over through
-      //      shared memory, the lower-half warp finishes  dz = (dgamma * gamma (1 - gamma), dbeta * beta (1 - beta)) / (K - 1)
-      //      and stores one 4-byte (gamma, beta) pair per edge and channel
-      if (half == 1 && is_agg) {
-#pragma unroll
-        for (int e = 0; e < NE; ++e) xs[e] = dg[e].x + dg[e].y;
-#pragma unroll
-        for (int a = 0; a < KR; ++a) xs[NE + a] = db[a];
-      }
-      named_bar_sync(1 + q, 64);
-      if (half == 0 && is_agg) {
-        __nv_bfloat16* dzc = p.dz + (g * NE) * 2 * (int64_t)p.F + 2 * c;
-#pragma unroll
-        for (int u = 0; u < KR; ++u) {
-#pragma unroll
-          for (int a = 0; a < KR; ++a) {
-            if (a == u) continue;
-            const int e = edge_id(KR, u, a);
-            const uint32_t zw = zs[e * CT + ci];
-            const float gam = __uint_as_float(zw << 16), bet = __uint_as_float(zw & 0xffff0000u);
-            float dgm = (dg[e].x + dg[e].y + xs[e]) * wmean, dbt = (db[a] + xs[NE + a]) * wmean;
-            if (p.fuse_sig) { dgm *= gam * (1.f - gam); dbt *= bet * (1.f - bet); }
-            *reinterpret_cast<uint32_t*>(dzc + (int64_t)e * 2 * p.F) = pack_bf16(dgm, dbt);
-          }
-        }
-      }
-      named_bar_sync(1 + q, 64);                                // the hand-over slots and the h / gamma-beta buffer have been read
-      if (lane == 0) mbar_arrive(bar_xempty);                   // ... and may be refilled
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (CL > 1) cluster_sync_all();       // nobody leaves while a peer may still multicast into it or signal its barriers
-  if (warp == 2) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-  }
-}
-
-template <int KR, int CL>
-static int launch_cl(const CUtensorMap& tw, const CUtensorMap& tdy, const CUtensorMap& tdys, const CUtensorMap& th, const CUtensorMap& tz,
-                     const Params& p, cudaStream_t st) {
-  using C = Cfg<KR>;
-  static DeviceOnce once;
-  if (once.need()) {
-    cudaError_t e = cudaFuncSetAttribute(k_dx_film_bwd<KR, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_dx_film_bwd)");
-    once.mark();
-  }
-  const int64_t work = p.graphs * (p.tiles / CL);
-  int64_t groups = work < num_sms() / CL ? work : num_sms() / CL;
-  if (groups < 1) return 0;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(groups * CL));
-  cfg.blockDim = dim3(NTHR);
-  cfg.dynamicSmemBytes = C::SMEM;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  count_launch();
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_dx_film_bwd<KR, CL>, tw, tdy, tdys, th, tz, p);
-  if (e != cudaSuccess) return cuda_fail(e, "k_dx_film_bwd launch");
-  return 0;
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Variant with PIXEL-HALF accumulators, so that the epilogue overlaps the next MMAs.
-// The kernel above is bounded by what one SM can take in (~120 GB/s: A 128 KB + B 327 KB + h 45 KB per tile = 4.1 us) PLUS an
-// epilogue (TMEM drain 160 KB at 64 B/clk + ~3500 instructions per SM sub-partition = 4.5 us) that cannot overlap the next
-// tile's MMAs, because one K x 64-column accumulator leaves no room for a second one in TMEM (measured: 10.5 us per tile).  Here
-// a tile is processed as two half-tiles of 32 pixels: accumulator = 128 rows x (K robots x 32 pixels) = 160 columns at K = 5, THREE
-// of them fit in TMEM, so the FiLM epilogue of half-tile i runs under the loads and MMAs of half-tiles i+1, i+2.  The B operand is
-// then a [K robots x 64 o x 32 px] box = 64-byte rows, MN-major SWIZZLE_64B; the weight rows are fetched once per half-tile (from
-// L2); the per-edge sums of the two halves meet in the registers of the same epilogue threads.
+// Shared-memory / tensor-memory budget of the pixel-half design (a single K x 64-column accumulator, the first version, left no room
+// for a second one in TMEM: its epilogue could not overlap the next tile's MMAs, 10.5 us per tile).
 template <int KR> struct CfgR {
   static constexpr int NE = KR * (KR - 1);
   static constexpr int NCOL = 32 * KR;                        // accumulator columns of a half-tile (UMMA N: multiple of 16)
@@ -717,52 +404,6 @@ static int launch_res(const void* Wp, const void* dy, const void* h, const void*
   return 0;
 }
 
-template <int KR>
-static int launch(const void* Wp, const void* dy, const void* h, const void* z, void* dh, void* dz, float* db2, int64_t graphs, int64_t F,
-                  int64_t Fo, int fuse_sig, cudaStream_t st) {
-  using C = Cfg<KR>;
-  static int want_res = -1;     // RGNN_DXF_RES=0: never use the weight-resident pixel-half variant
-  if (want_res < 0) { const char* e = getenv("RGNN_DXF_RES"); want_res = (e && e[0] == '0') ? 0 : 1; }
-  if (want_res || db2) return launch_res<KR>(Wp, dy, h, z, dh, dz, db2, graphs, F, Fo, fuse_sig, st);     // (the column sums live in the pixel-half variant only)
-  const int64_t nodes = graphs * KR, edges = graphs * C::NE;
-  static int want_cl = -1;      // RGNN_DXF_CLUSTER=1|2|4: CTAs sharing one multicast copy of the graph's dY (default 2)
-  if (want_cl < 0) { const char* e = getenv("RGNN_DXF_CLUSTER"); want_cl = e ? atoi(e) : 2; }
-  const int tiles = (int)(F / CT);
-  int cl = want_cl;
-  while (cl > 1 && (tiles % cl != 0 || KR / cl < 1)) cl >>= 1;
-  CUtensorMap tw, tdy, tdys, th, tz;
-  {
-    const uint64_t d[2] = {(uint64_t)Fo, (uint64_t)(2 * F)}, s[1] = {(uint64_t)Fo * 2};
-    const uint32_t b[2] = {BK, BM};
-    int rc = make_map(&tw, Wp, 2, d, s, b); if (rc) return rc;
-  }
-  {
-    // cluster of cl CTAs: the graph's robots are split as evenly as possible; two box sizes cover every share
-    const uint64_t d[3] = {64, (uint64_t)Fo, (uint64_t)nodes}, s[2] = {128, (uint64_t)Fo * 128};
-    const uint32_t small = (uint32_t)(KR / cl), big = cl == 1 ? (uint32_t)KR : (uint32_t)(KR / cl + (KR % cl ? 1 : 0));
-    const uint32_t b1[3] = {64, BK, big}, b0[3] = {64, BK, small};
-    int rc = make_map(&tdy, dy, 3, d, s, b1); if (rc) return rc;
-    rc = make_map(&tdys, dy, 3, d, s, b0); if (rc) return rc;
-  }
-  {
-    const uint64_t d[3] = {64, (uint64_t)F, (uint64_t)nodes}, s[2] = {128, (uint64_t)F * 128};
-    const uint32_t b[3] = {64, CT, KR};
-    int rc = make_map(&th, h, 3, d, s, b); if (rc) return rc;
-  }
-  {
-    const uint64_t d[2] = {(uint64_t)(2 * F), (uint64_t)edges}, s[1] = {(uint64_t)(2 * F) * 2};
-    const uint32_t b[2] = {2 * CT, (uint32_t)C::NE};
-    int rc = make_map(&tz, z, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
-  }
-  Params p = {};
-  p.tiles = tiles; p.graphs = graphs; p.F = (int)F; p.Fo = (int)Fo; p.kblocks = (int)(Fo / BK);
-  p.dh = static_cast<__nv_bfloat16*>(dh); p.dz = static_cast<__nv_bfloat16*>(dz); p.fuse_sig = fuse_sig;
-  { const char* e = getenv("RGNN_DXF_DEBUG"); p.debug = e ? atoi(e) : 0; }
-  if (cl == 4) return launch_cl<KR, 4>(tw, tdy, tdys, th, tz, p, st);
-  if (cl == 2) return launch_cl<KR, 2>(tw, tdy, tdys, th, tz, p, st);
-  return launch_cl<KR, 1>(tw, tdy, tdys, th, tz, p, st);
-}
-
 }  // namespace dxf
 }  // namespace rgnn
 
@@ -785,10 +426,10 @@ extern "C" int rgnn_tc_conv_dx_film_bwd(const void* W_perm, const void* dy, cons
   if (graphs == 0) return 0;
   cudaStream_t st = as_stream(stream);
   switch (robots) {
-    case 2: return dxf::launch<2>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
-    case 3: return dxf::launch<3>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
-    case 4: return dxf::launch<4>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
-    case 5: return dxf::launch<5>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
-    default: return dxf::launch<6>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
+    case 2: return dxf::launch_res<2>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
+    case 3: return dxf::launch_res<3>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
+    case 4: return dxf::launch_res<4>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
+    case 5: return dxf::launch_res<5>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
+    default: return dxf::launch_res<6>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
   }
 }
