@@ -152,7 +152,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int oa = p.nprod > 1 ? p.pa[pj] * p.plane_a : 0, ob0 = p.nprod > 1 ? p.pb[pj] * p.plane_b0 : 0,
                   ob1 = p.nprod > 1 ? p.pb[pj] * p.plane_b1 : 0;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          mbar_wait_sleep(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t fb = bar_full + 8 * stage;
           const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
           if constexpr (TWO) {
@@ -339,7 +339,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       };
       if (use_aux && !empty) aux_fetch(eh * (BN / 128));
-      mbar_wait(bar_tfull + 8 * as, aphase);
+      mbar_wait_sleep(bar_tfull + 8 * as, aphase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(ew * 32) << 16);
       const int64_t m = (int64_t)tm * BM + row;
