@@ -234,13 +234,13 @@ k_dx_film_bwd_res(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       for (int a = 0; a < KR; ++a) db[a] = make_float2(0.f, 0.f);
       __nv_bfloat16* dh_row = p.dh + ((g * KR) * (int64_t)p.F + c) * 64 + 2 * pq;
       const uint32_t zs = base + C::Z_OFF + zb * C::Z_BYTES + ci * 4;
-      mbar_wait(bar_zfull + 8 * zb, zphase);
+      mbar_wait_backoff(bar_zfull + 8 * zb, zphase);
 #pragma unroll
       for (int e = 0; e < NE; ++e) gw[e] = __uint_as_float(lds_u32(zs + e * (CT * 4)) << 16) * wmean;
 #pragma unroll 1
       for (int ph = 0; ph < 2; ++ph) {
-        mbar_wait(bar_xfull + 8 * xb, xphase);
-        mbar_wait(bar_tfull + 8 * tb, tphase);
+        mbar_wait_backoff(bar_xfull + 8 * xb, xphase);
+        mbar_wait_backoff(bar_tfull + 8 * tb, tphase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + tb * C::NCOL + ((uint32_t)(q * 32 + lg * 16) << 16);
         const uint32_t hs = base + C::H_OFF + xb * C::H_BYTES + ci * 64 + 4 * pq;      // (shared-window address: plain pointers compile to generic loads)
