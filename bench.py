@@ -611,8 +611,9 @@ def main():
                 "traffic": traffic, "traffic_source": traffic_source, "algorithmic_per_launch": topd["work_total"] / max(1, topd["calls"]),
                 "peak_source": peak_src, "ms_avg_per_launch": kernels[top]["ms_avg"]}
     if "hbm_frac" in kernels[top]:
-        roofline["note"] = ("fused dX GEMM + FiLM backward: bounded by neither roofline but by what one SM can take in through shared memory "
-                            "(DESIGN.md 4.1); `achieved` counts its GEMM's flops, hbm_* its own algorithmic bytes (3 tensor passes + z/dz)")
+        roofline["note"] = ("fused dX GEMM + FiLM backward: its MMA phase reaches 0.57-0.60 of the tensor peak (B operand staged as 64-byte rows so "
+                            "that three pixel-half accumulators fit in TMEM; CTA pairs / weights in TMEM / prefetch measured, no gain: DESIGN.md 4.1); "
+                            "`achieved` counts its GEMM's flops, hbm_* its own algorithmic bytes (3 tensor passes + z/dz)")
         roofline["hbm_GBps"], roofline["hbm_frac"] = kernels[top]["hbm_GBps"], kernels[top]["hbm_frac"]
 
     cpu = None
