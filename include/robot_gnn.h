@@ -219,7 +219,7 @@ int rgnn_tc_conv_film_fused(const void* W, const void* h, const void* z, const f
  * HBM traffic: dY + h in, dh out (3 tensor passes) instead of 7 for rgnn_tc_conv1x1 (dX) + rgnn_film_backward. */
 int rgnn_tc_conv_dx_film_bwd(const void* W_perm, const void* dy, const void* h, const void* z, int fuse_sigmoid_grad,
                              void* dh, void* dz, float* dbias2, int64_t graphs, int64_t robots, int64_t F, int64_t Fo, void* stream);
-/* dbias2 (nullable): fp32 [2F]; the column sums of dz (= the bias gradient of nn.Linear(F,2F), models.py:149) are ADDED to it. */
+/* dbias2 (nullable): fp32 [2F]; receives the column sums of dz (= the bias gradient of nn.Linear(F,2F), models.py:149); overwritten. */
 
 /* weight gradient of the above: dW[m,k] = sum_v sum_p dy[v,m,p] x[v,k,p], x = x0 | x1; dW fp32 (row stride ldw);
  * dbias (nullable) fp32 [M] = sum_v sum_p dy[v,m,p], computed by the otherwise idle epilogue warps from the dy tiles the

@@ -39,7 +39,7 @@ struct Params {
   int F, Fo, kblocks;   // kblocks = Fo / 64
   __nv_bfloat16* dh;    // [G K, F, 64]
   __nv_bfloat16* dz;    // [G K (K-1), 2 F]
-  float* db2;           // optional fp32 [2 F]: column sums of dz (the bias gradient of the edge encoder's last Linear) are ADDED here
+  float* db2;           // optional fp32 [2 F]: column sums of dz (the bias gradient of the edge encoder's last Linear) are accumulated here (zeroed by the launcher)
   int fuse_sig;
   int debug;            // RGNN_DXF_DEBUG (experiments): 1 = epilogue only drains TMEM, 2 = no per-edge dots, 4 = no dh part, 8 = MMA issuer skips the MMAs
 };
@@ -413,7 +413,7 @@ using namespace rgnn;
 // that, for every channel tile t (64 channels) and j < 8, rows 128 t + 16 j + (0..7) are Wc[:, 64 t + 8 j + (0..7)]^T (direct half) and rows
 // 128 t + 16 j + 8 + (0..7) are Wc[:, F + 64 t + 8 j + (0..7)]^T (aggregated half).  dy [G K, Fo, 64], h [G K, F, 64], z [G K (K-1), 2F]
 // (gamma, beta interleaved), dh [G K, F, 64], dz [G K (K-1), 2F], all bf16; G complete `robots`-node graphs (2..6) in reference edge order.
-// dbias2 (nullable): fp32 [2F], the column sums of dz are ADDED to it (zero it first): db2 of the edge encoder without a pass over dz.
+// dbias2 (nullable): fp32 [2F], receives the column sums of dz (overwritten): db2 of the edge encoder without a pass over dz.
 extern "C" int rgnn_tc_conv_dx_film_bwd(const void* W_perm, const void* dy, const void* h, const void* z, int fuse_sigmoid_grad,
                                         void* dh, void* dz, float* dbias2, int64_t graphs, int64_t robots, int64_t F, int64_t Fo, void* stream) {
   RGNN_REQUIRE(W_perm && dy && h && z && dh && dz && graphs >= 0 && F > 0 && Fo > 0, RGNN_E_ARG, "rgnn_tc_conv_dx_film_bwd: bad arguments");
@@ -423,8 +423,12 @@ extern "C" int rgnn_tc_conv_dx_film_bwd(const void* W_perm, const void* dy, cons
                "rgnn_tc_conv_dx_film_bwd: 16-byte alignment");
   RGNN_REQUIRE(graphs * robots * (Fo > F ? Fo : F) < (1ll << 31) && graphs * robots * (robots - 1) < (1ll << 31), RGNN_E_RANGE,
                "rgnn_tc_conv_dx_film_bwd: too many rows for a tensor-map coordinate");
-  if (graphs == 0) return 0;
   cudaStream_t st = as_stream(stream);
+  if (dbias2) {       // the CTAs add their partial column sums with atomics: start from zero
+    cudaError_t e = cudaMemsetAsync(dbias2, 0, sizeof(float) * 2 * (size_t)F, st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset dbias2");
+  }
+  if (graphs == 0) return 0;
   switch (robots) {
     case 2: return dxf::launch_res<2>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);
     case 3: return dxf::launch_res<3>(W_perm, dy, h, z, dh, dz, dbias2, graphs, F, Fo, fuse_sigmoid_grad, st);

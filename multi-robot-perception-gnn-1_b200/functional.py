@@ -668,7 +668,7 @@ class GNNLayerFn(torch.autograd.Function):
             f, fo = h.shape[1], wc2.shape[0]
             dh, dzp = torch.empty_like(h), torch.empty_like(z)
             # db2 (bias gradient of the edge encoder's Linear(F,2F)) = column sums of dz: accumulated inside the kernel
-            db2 = torch.zeros((2 * f,), dtype=torch.float32, device=dy.device) if (need_edge and f <= 2048) else None
+            db2 = torch.empty((2 * f,), dtype=torch.float32, device=dy.device) if (need_edge and f <= 2048) else None
             nbytes = 2.0 * (ix.N * 64 * (2 * f + fo) + 2 * ix.E * 2 * f)
             with _lib.on_device(dy.device), _lib.timed("dx_film_bwd", 2.0 * fo * 2 * f * ix.N * 64, nbytes):
                 check(lib().rgnn_tc_conv_dx_film_bwd(ptr(ctx.wtp), ptr(dy), ptr(h), ptr(z), 1, ptr(dh), ptr(dzp), ptr(db2), ix.G, ix.complete_k,

@@ -183,7 +183,7 @@ def test_fused_dx_film_backward_guards(R, g_, k, f, fo):
         wt = bf(2 * f, fo, seed=4, scale=0.05)
         wtp = wt.index_select(0, R.functional._dx_film_perm(f, wt.device))
         dh, dz = Guarded((n, f, 64), torch.bfloat16, 777.0), Guarded((e, 2 * f), torch.bfloat16, 777.0)
-        db2 = Guarded((2 * f,), torch.float32, 0.0)
+        db2 = Guarded((2 * f,), torch.float32, 777.0)             # (overwritten, not accumulated into: the launcher zeroes it)
         L.check(L.lib().rgnn_tc_conv_dx_film_bwd(L.ptr(wtp), L.ptr(dy), L.ptr(h), L.ptr(z), 1, L.ptr(dh.view), L.ptr(dz.view), L.ptr(db2.view), g_, k, f, fo, L.stream()), "dxf")
         dh.check("dx_film_bwd dh"); dz.check("dx_film_bwd dz")
         # values against the unfused formulas in fp32
@@ -204,7 +204,7 @@ def test_fused_dx_film_backward_guards(R, g_, k, f, fo):
         assert float((got[..., 1] - dbet).abs().max()) <= 2e-2 * float(dbet.abs().max())
         ref_db2 = torch.stack((dgam.sum((0, 1)), dbet.sum((0, 1))), -1).reshape(-1)
         assert float((db2.view - ref_db2).abs().max()) <= 1e-3 * float(ref_db2.abs().max())
-        assert bool((db2.buf[:4096] == 0).all()) and bool((db2.buf[4096 + 2 * f:] == 0).all())
+        db2.check("dx_film_bwd db2")
         print("ok")
     """)
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ), capture_output=True, text=True, timeout=300)
