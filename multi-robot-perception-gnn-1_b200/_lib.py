@@ -94,24 +94,42 @@ def lib():
 PROFILE = None      # None = off; else dict: name -> list of (start_event, end_event, work)
 
 
-class timed:
-    """with timed("name", work): <C-ABI call>   - records CUDA events on the current stream when PROFILE is on."""
+class _Timed:
+    __slots__ = ("name", "work", "nbytes", "s")
 
-    def __init__(self, name, work=0.0, nbytes=0.0):
+    def __init__(self, name, work, nbytes):
         self.name, self.work, self.nbytes = name, work, nbytes      # nbytes: algorithmic HBM bytes of a kernel whose `work` is flops
 
     def __enter__(self):
-        if PROFILE is not None:
-            self.s = torch.cuda.Event(enable_timing=True)
-            self.s.record()
+        self.s = torch.cuda.Event(enable_timing=True)
+        self.s.record()
         return self
 
     def __exit__(self, *a):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
         if PROFILE is not None:
-            e = torch.cuda.Event(enable_timing=True)
-            e.record()
             PROFILE.setdefault(self.name, []).append((self.s, e, self.work, self.nbytes))
         return False
+
+
+class _NoTimer:
+    __slots__ = ()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_TIMER = _NoTimer()
+
+
+def timed(name, work=0.0, nbytes=0.0):
+    """with timed("name", work): <C-ABI call>   - records CUDA events on the current stream when PROFILE is on; otherwise one shared
+    do-nothing context (no object per call: the script batch is host-bound)."""
+    return _NO_TIMER if PROFILE is None else _Timed(name, work, nbytes)
 
 
 def profile_summary():

@@ -339,14 +339,20 @@ def _splits_mn(m, n, work_items):
     return _splits(((m + 63) // 64) * ((n + 63) // 64), work_items)
 
 
+def _f32c(t):
+    """fp32 contiguous view of a parameter for the C ABI: the tensor itself when it already is one (the usual case; every no-op
+    .detach() / .float() / .contiguous() still builds a tensor object, and the script batch is host-bound)."""
+    return t if (t.dtype is torch.float32 and t.is_contiguous()) else t.detach().float().contiguous()
+
+
 def _edge_mlp_forward(pose, w1, b1, w2, b2, out_dtype):
     _lib.require_cuda(pose, w1, b1, w2, b2)
-    pose = pose.float().contiguous()          # edge.float(), models.py:153
+    pose = _f32c(pose)                        # edge.float(), models.py:153
     e, hid, f2 = pose.shape[0], w1.shape[0], w2.shape[0]
     if pose.shape[1] != 9 or w1.shape != (hid, 9) or w2.shape != (f2, hid) or f2 % 2:
         raise ValueError("edge encoder expects pose [E,9], W1 [H,9], W2 [2F,H]")
     w2_param = w2
-    w1, b1, w2, b2 = (t.detach().float().contiguous() for t in (w1, b1, w2, b2))
+    w1, b1, w2, b2 = _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2)
     w2t = None                    # the K-major operand of dA1 = dZ . W2, produced by the same cast launch as the forward operand
     a1 = torch.empty((e, hid), dtype=out_dtype, device=pose.device)
     z = torch.empty((e, f2), dtype=out_dtype, device=pose.device)
@@ -453,7 +459,7 @@ def _compress_forward(h, gh, wc, bc):
     fo = wc2.shape[0]
     if wc2.shape[1] != 2 * f or gh.shape != h.shape or h.dtype != gh.dtype:
         raise ValueError("compress expects h, g_h [N,F,...] and weight [Fo, 2F(,1,1)]")
-    bcf = bc.detach().float().contiguous()
+    bcf = _f32c(bc)
     y = torch.empty((n, fo) + tuple(h.shape[2:]), dtype=h.dtype, device=h.device)
     shape_ok = p == 64 and f % 64 == 0 and fo % 128 == 0 and n > 0
     tc = 1 if (_lib.USE_TC and h.dtype == torch.bfloat16 and shape_ok) else (3 if (_lib.USE_TC3 and h.dtype == torch.float32 and shape_ok) else 0)
@@ -630,7 +636,7 @@ class GNNLayerFn(torch.autograd.Function):
         if fused:
             # aggregation in the GEMM prologue: g_h is produced in shared memory; it is written out only for the backward
             wc2 = wc.detach().float().reshape(fo, -1).contiguous()
-            bcf = bc.detach().float().contiguous()
+            bcf = _f32c(bc)
             y = torch.empty((ix.N, fo) + tuple(h.shape[2:]), dtype=h.dtype, device=h.device)
             gh = torch.empty_like(h) if need_bwd else None
             with _lib.on_device(h.device):
