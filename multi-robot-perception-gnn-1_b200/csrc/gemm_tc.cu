@@ -875,6 +875,11 @@ static int wgrad_impl(const void* dy, int64_t M, const void* x0, int64_t c0, con
   p.n_b0 = (int)c0; p.rows_a = (int)M; p.rows_b0 = (int)c0; p.rows_b1 = (int)c1;
   p.M = M; p.N = Nn; p.out0 = partial; p.ld0 = Nn;
   p.rowsum = dbias ? partial + splits * M * Nn : nullptr;     // [splits, M] behind the tile partials
+  if (splits == 1 && ldw % 4 == 0 && (reinterpret_cast<uintptr_t>(dW) & 15u) == 0) {
+    // one split (small batches, launch-bound): the tiles ARE the result - no partial buffer, no reduction launch
+    p.out0 = dW; p.ld0 = ldw; p.rowsum = dbias;
+    return launch<BN>(ta, tb0, tb1, p, st);
+  }
   int rc = launch<BN>(ta, tb0, tb1, p, st);
   if (rc) return rc;
   const int64_t n = M * Nn;
@@ -997,6 +1002,10 @@ static int gemm_nn_impl(const void* A, int64_t lda, const void* B, int64_t ldb, 
   splits = (kblocks + p.kb_per_split - 1) / p.kb_per_split;   // no empty split
   p.splits = (int)splits;
   p.M = M; p.N = N; p.out0 = partial; p.ld0 = N;
+  if (splits == 1 && alpha == 1.0f && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15u) == 0) {      // as in the weight-gradient GEMM above
+    p.out0 = C; p.ld0 = ldc;
+    return wide ? launch<256>(ta, tb, tb, p, st) : launch<128>(ta, tb, tb, p, st);
+  }
   int rc = wide ? launch<256>(ta, tb, tb, p, st) : launch<128>(ta, tb, tb, p, st);
   if (rc) return rc;
   const int64_t n = M * N;

@@ -311,7 +311,13 @@ def _split3_w(w, transpose=False):
     return out
 
 
+SMALL_K_BLOCKS = 48     # weight-gradient GEMMs with no more k-blocks than this run as ONE split: the tiles are written straight to the
+                        # result and the partial-sum launch disappears (the script batch of 8 graphs is launch-bound, not SM-bound)
+
+
 def _tc_splits(tiles, items):
+    if items <= SMALL_K_BLOCKS:
+        return 1
     return max(1, min(items, 148 // max(1, tiles)))
 
 
